@@ -1,0 +1,215 @@
+"""ctypes binding of the C ABI declared in include/astrea_b200.h.
+
+The product library is ``astrea_b200/lib/libastrea_b200.so`` (nvcc, sm_100a; ``python -m astrea_b200.build``).
+There is no CPU fallback: if the library is missing or was not built for the device, loading raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEVICE_LIB = os.path.join(_HERE, "lib", "libastrea_b200.so")
+
+# enums of include/astrea_b200.h
+PCM, PLM, PPM, WENO3, WENO5, WENO7 = range(6)
+MINMOD, VANLEER, OSPRE, VANALBADA, KOREN, SUPERBEE = range(6)
+LLF, LW, HLLC, HLLD = range(4)
+EULER, RK4, SSPRK22, SSPRK33, SSPRK43, SSPRK53, SSPRK54, SSPRK104 = range(8)
+EDGE, WRAP = 0, 1
+E_ARG, E_CUDA, E_NONFINITE, E_STATE = -1, -2, -3, -4
+
+
+class Cfg(C.Structure):
+    """struct astrea_cfg."""
+    _fields_ = [
+        ("dimension", C.c_int32), ("boundary", C.c_int32), ("nx", C.c_int64), ("ny", C.c_int64),
+        ("gamma", C.c_double), ("dx", C.c_double), ("cfl", C.c_double),
+        ("scheme", C.c_int32), ("ppm_author", C.c_int32), ("limiter", C.c_int32), ("solver", C.c_int32),
+        ("low_mach", C.c_int32), ("integrator", C.c_int32), ("magnetic_2d", C.c_int32), ("device", C.c_int32),
+        ("nx_global", C.c_int64), ("x_offset", C.c_int64),
+        ("threads_2d", C.c_int32), ("segment_2d", C.c_int32), ("tile_1d", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AstreaError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"astrea_b200 error {code}: {text}")
+        self.code = code
+
+
+class NonFiniteError(AstreaError, np.linalg.LinAlgError):
+    """Where the reference's np.linalg.eigvals raises LinAlgError (fv.py:158)."""
+
+
+_PD = C.POINTER(C.c_double)
+_SIGNATURES = {
+    "astrea_create": (C.c_void_p, [C.POINTER(Cfg)]),
+    "astrea_destroy": (None, [C.c_void_p]),
+    "astrea_last_error": (C.c_char_p, [C.c_void_p]),
+    "astrea_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "astrea_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "astrea_evolve_space": (C.c_int, [C.c_void_p, C.c_int, _PD]),
+    "astrea_evolve_time": (C.c_int, [C.c_void_p, C.c_double]),
+    "astrea_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _PD]),
+    "astrea_get_parity": (C.c_int, [C.c_void_p]),
+    "astrea_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "astrea_program_length": (C.c_int, [C.c_void_p]),
+    "astrea_instr_is_operator": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
+    "astrea_run_instr": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "astrea_finish_step": (C.c_int, [C.c_void_p]),
+    "astrea_halo_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "astrea_halo_ptrs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_PD), C.POINTER(_PD), C.POINTER(_PD), C.POINTER(_PD)]),
+    "astrea_halo_prepare": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_eigmax_device": (C.c_int, [C.c_void_p, C.POINTER(_PD)]),
+    "astrea_read_eigmax": (C.c_int, [C.c_void_p, _PD]),
+    "astrea_sync": (C.c_int, [C.c_void_p]),
+    "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
+    "astrea_launch_count": (C.c_int64, [C.c_void_p]),
+    "astrea_is_device_build": (C.c_int, []),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+
+def bind(path):
+    """dlopen ``path`` and attach the prototypes of include/astrea_b200.h."""
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+_device_lib = None
+
+
+def device_library():
+    """The sm_100a library.  Raises if it has not been built: the package has no other execution path."""
+    global _device_lib
+    if _device_lib is None:
+        if not os.path.exists(DEVICE_LIB):
+            raise ImportError(f"{DEVICE_LIB} is missing: build it with `python -m astrea_b200.build` "
+                              "(astrea_b200 has no CPU fallback)")
+        lib = bind(DEVICE_LIB)
+        if lib.astrea_is_device_build() != 1:
+            raise ImportError(f"{DEVICE_LIB} is not an sm_100a device build")
+        _device_lib = lib
+    return _device_lib
+
+
+class Context:
+    """One ``astrea_ctx``: a grid (or slab) resident on one GPU plus the step program of its integrator."""
+
+    def __init__(self, cfg, lib=None):
+        self.lib = lib if lib is not None else device_library()
+        self.cfg = cfg
+        self._h = self.lib.astrea_create(C.byref(cfg))
+        if not self._h:
+            raise AstreaError(E_ARG, self.lib.astrea_last_error(None).decode())
+        self.shape = (cfg.nx, 8) if cfg.dimension == 1 else (cfg.nx, cfg.ny, 8)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.astrea_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code):
+        if code != 0:
+            text = self.lib.astrea_last_error(self._h).decode()
+            raise (NonFiniteError if code == E_NONFINITE else AstreaError)(code, text)
+
+    # -- data movement
+    def upload(self, grid):
+        g = np.ascontiguousarray(grid, dtype=np.float64)
+        if g.shape != tuple(self.shape):
+            raise ValueError(f"grid shape {g.shape} != {tuple(self.shape)}")
+        self._check(self.lib.astrea_upload(self._h, g.ctypes.data))
+
+    def upload_ptr(self, host_ptr):
+        self._check(self.lib.astrea_upload(self._h, host_ptr))
+
+    def download(self, primitive=False, out=None):
+        out = np.empty(self.shape, dtype=np.float64) if out is None else out
+        self._check(self.lib.astrea_download(self._h, out.ctypes.data, 1 if primitive else 0))
+        return out
+
+    def download_ptr(self, host_ptr, primitive=False):
+        self._check(self.lib.astrea_download(self._h, host_ptr, 1 if primitive else 0))
+
+    # -- the two calls of the reference seam
+    def evolve_space(self, parity):
+        eig = (C.c_double * 2)()
+        self._check(self.lib.astrea_evolve_space(self._h, int(parity), eig))
+        return [eig[a] for a in range(self.cfg.dimension)]
+
+    def evolve_time(self, dt):
+        self._check(self.lib.astrea_evolve_time(self._h, float(dt)))
+
+    def step(self, t=0.0, t_stop=0.0):
+        dt = C.c_double()
+        self._check(self.lib.astrea_step(self._h, float(t), float(t_stop), C.byref(dt)))
+        return dt.value
+
+    @property
+    def parity(self):
+        return self.lib.astrea_get_parity(self._h)
+
+    @parity.setter
+    def parity(self, p):
+        self._check(self.lib.astrea_set_parity(self._h, int(p)))
+
+    # -- step program (multi-GPU hosts drive it instruction by instruction)
+    def program(self):
+        n = self.lib.astrea_program_length(self._h)
+        return [bool(self.lib.astrea_instr_is_operator(self._h, i)) for i in range(n)]
+
+    def set_dt(self, dt):
+        self._check(self.lib.astrea_set_dt(self._h, float(dt)))
+
+    def run_instr(self, i, external_rows=False):
+        self._check(self.lib.astrea_run_instr(self._h, i, 1 if external_rows else 0))
+
+    def finish_step(self):
+        self._check(self.lib.astrea_finish_step(self._h))
+
+    def halo_info(self):
+        rows, n = C.c_int64(), C.c_int64()
+        self._check(self.lib.astrea_halo_info(self._h, C.byref(rows), C.byref(n)))
+        return rows.value, n.value
+
+    def halo_ptrs(self, i):
+        p = [_PD() for _ in range(4)]
+        self._check(self.lib.astrea_halo_ptrs(self._h, i, *[C.byref(x) for x in p]))
+        return [C.cast(x, C.c_void_p).value for x in p]   # send_lo, send_hi, recv_lo, recv_hi
+
+    def halo_prepare(self, i):
+        self._check(self.lib.astrea_halo_prepare(self._h, i))
+
+    def eigmax_device(self):
+        p = _PD()
+        self._check(self.lib.astrea_eigmax_device(self._h, C.byref(p)))
+        return C.cast(p, C.c_void_p).value
+
+    def read_eigmax(self):
+        eig = (C.c_double * 2)()
+        self._check(self.lib.astrea_read_eigmax(self._h, eig))
+        return [eig[a] for a in range(self.cfg.dimension)]
+
+    def sync(self):
+        self._check(self.lib.astrea_sync(self._h))
+
+    @property
+    def stream_handle(self):
+        return self.lib.astrea_stream_handle(self._h)
+
+    @property
+    def launch_count(self):
+        return self.lib.astrea_launch_count(self._h)

@@ -1,0 +1,89 @@
+"""Build the native library of astrea_b200 in-tree.
+
+    python -m astrea_b200.build            # nvcc, sm_100a  -> astrea_b200/lib/libastrea_b200.so   (the product)
+    python -m astrea_b200.build --hostsim  # g++            -> tests/hostsim/libastrea_hostsim.so  (test infrastructure)
+
+Floating-point flags (DESIGN.md "Numerics"): FMA contraction off and IEEE division / square root, so that the
+device arithmetic follows the operation order of the reference numpy code.
+"""
+import argparse
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "astrea_b200", "csrc")
+SOURCES = ["api.cu", "inst_pcm.cu", "inst_plm.cu", "inst_ppm.cu", "inst_weno3.cu", "inst_weno5.cu", "inst_weno7.cu"]
+DEVICE_LIB = os.path.join(ROOT, "astrea_b200", "lib", "libastrea_b200.so")
+HOSTSIM_LIB = os.path.join(ROOT, "tests", "hostsim", "libastrea_hostsim.so")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+GXX_FLAGS = ["-O2", "-std=c++17", "-x", "c++", "-DASTREA_HOSTSIM", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+             "-Wno-unknown-pragmas"]
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
+        os.path.join(ROOT, "include", "astrea_b200.h")]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s\n%s" % (" ".join(cmd), res.stdout, res.stderr))
+    return res.stdout + res.stderr
+
+
+def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None):
+    """Compile every translation unit (in parallel) and link the shared library.  Returns its path."""
+    lib = HOSTSIM_LIB if hostsim else DEVICE_LIB
+    objdir = os.path.join(ROOT, "build", "hostsim" if hostsim else "sm_100a")
+    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    heads = _headers()
+    compiler = "g++" if hostsim else os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = list(GXX_FLAGS if hostsim else NVCC_FLAGS)
+    if ptxas_info and not hostsim:
+        flags += ["-Xptxas", "-v"]
+    objs, todo = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + heads + [os.path.abspath(__file__)]):
+            todo.append([compiler] + flags + ["-c", s, "-o", o])
+    logs = []
+    if todo:
+        with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as pool:
+            logs = list(pool.map(lambda c: _run(c, verbose), todo))
+    if todo or force or _stale(lib, objs):
+        if hostsim:
+            _run(["g++", "-shared", "-o", lib] + objs, verbose)
+        else:
+            _run([compiler, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], verbose)
+    if ptxas_info:
+        print("\n".join(logs))
+    return lib
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--hostsim", action="store_true")
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--ptxas-info", action="store_true")
+    a = ap.parse_args()
+    print(build(a.hostsim, a.force, a.verbose, a.ptxas_info))
+    sys.exit(0)

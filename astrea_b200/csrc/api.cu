@@ -1,0 +1,663 @@
+// C ABI of astrea_b200 (include/astrea_b200.h): context, register file, step program, launches.
+//
+// HBM layout: every state register is one ghost-padded plane [row][var][col] of fp64 with
+// GHOST cells on every side (2D: row = x, col = y; 1D: one row).  A spatial-operator evaluation is
+//     halo fill -> x sweep (reads the register)            -> d0   (x frame)
+//               -> transpose -> y sweep (transposed frame) -> d1t  (y frame)
+//               -> rate assembly L = -(d0 + d1)            -> rate buffer
+// and a Runge-Kutta register update is one combine kernel.  The order of operator evaluations and register
+// updates of a time step is a small "step program" built once per context from the integrator
+// (evolvers.py:79-206).
+#include "../../include/astrea_b200.h"
+#include "aux_kernels.cuh"
+#include "dispatch.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace astrea {
+
+int launch_sweep1d(int scheme, int solver, const Sweep1DParams& p, int nthreads, Stream st) {
+    switch (scheme) {
+        case SCH_PCM: return launch_sweep1d_pcm(solver, p, nthreads, st);
+        case SCH_PLM: return launch_sweep1d_plm(solver, p, nthreads, st);
+        case SCH_PPM: return launch_sweep1d_ppm(solver, p, nthreads, st);
+        case SCH_WENO3: return launch_sweep1d_weno3(solver, p, nthreads, st);
+        case SCH_WENO5: return launch_sweep1d_weno5(solver, p, nthreads, st);
+        case SCH_WENO7: return launch_sweep1d_weno7(solver, p, nthreads, st);
+        default: return -1;
+    }
+}
+
+int launch_sweep2d(int scheme, int solver, int ax, int sax, Sweep2DParams p, int nthreads, Stream st) {
+    switch (scheme) {
+        case SCH_PCM: return launch_sweep2d_pcm(solver, ax, sax, p, nthreads, st);
+        case SCH_PLM: return launch_sweep2d_plm(solver, ax, sax, p, nthreads, st);
+        case SCH_PPM: return launch_sweep2d_ppm(solver, ax, sax, p, nthreads, st);
+        case SCH_WENO3: return launch_sweep2d_weno3(solver, ax, sax, p, nthreads, st);
+        case SCH_WENO5: return launch_sweep2d_weno5(solver, ax, sax, p, nthreads, st);
+        case SCH_WENO7: return launch_sweep2d_weno7(solver, ax, sax, p, nthreads, st);
+        default: return -1;
+    }
+}
+
+// shared-memory doubles per thread of the 2D sweep kernel (Sweep2D::smem_bytes / 8 / nthreads)
+static int sweep2d_doubles_per_thread(int scheme, int solver) {
+    const bool ho = scheme_high_order(scheme);
+    const int lag = (solver == SOL_LLF && scheme != SCH_PCM) ? 1 : 0;
+    const int nq = ho ? 3 : 2, nw = recon_lo(scheme) + recon_hi(scheme) + 1, ni = 1 + lag;
+    return NVAR * (nq + nw + 4 * ni + 1) + 2 * ni;
+}
+
+}  // namespace astrea
+
+using namespace astrea;
+
+namespace {
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+struct Reg {
+    double* mem = nullptr;
+    Plane plane{};
+};
+
+// one term of a register update: a state register or a rate buffer, with its literal coefficient
+struct Term { int is_rate; int index; double coef; };
+struct Instr {
+    int is_operator;            // 1: rate[rate_out] = L(reg[src]);   0: reg[out] = combination of terms
+    int src, rate_out;
+    int out, bracket;
+    double scale;
+    std::vector<Term> terms;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct astrea_ctx {
+    astrea_cfg cfg{};
+    Stream st{};
+    std::string err;
+    int parity = 0;
+    int64_t launches = 0;
+    int64_t nrow = 0, ncol = 0;       // interior rows / columns of a register plane
+    int ghost_r = 0;                  // ghost rows (0 in 1D)
+    size_t plane_doubles = 0;
+    std::vector<Reg> regs, rates;
+    Reg qT, d0, d1t;                  // transposed input of the y sweep; flux differences of the two sweeps
+    unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
+    unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
+    int* flag = nullptr;              // non-finite wave speed seen in any operator since the last read
+    double* dt_dev = nullptr;
+    std::vector<Instr> prog;
+    int grid_reg = 0;                 // register holding the current grid
+    int final_reg = 0;                // register the last instruction writes
+    int next_instr = 0;               // 0: nothing run for this step yet
+    int threads2d = 0, tt2d = 0, colblocks_x = 0, colblocks_y = 0;
+    int tile1d = 0, threads1d = 0;
+    bool stream_owned = false;
+};
+
+namespace {
+
+int fail(astrea_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#ifdef ASTREA_DEVICE_BUILD
+std::string cuda_text(int e) { return std::string(cudaGetErrorString((cudaError_t)e)); }
+#else
+std::string cuda_text(int e) { return "hostsim error " + std::to_string(e); }
+#endif
+
+#define ASTREA_TRY(expr)                                                                   \
+    do {                                                                                   \
+        const int _e = (expr);                                                             \
+        if (_e != 0) return fail(c, _e < 0 ? ASTREA_E_ARG : ASTREA_E_CUDA,                 \
+                                 std::string(#expr) + ": " + (_e < 0 ? "unsupported selector combination" : cuda_text(_e))); \
+    } while (0)
+
+Plane make_plane(double* mem, int64_t ncol, int ghost_r) {
+    Plane p;
+    p.col_pitch = ncol + 2 * GHOST;
+    p.row_pitch = NVAR * p.col_pitch;
+    p.base = mem + (int64_t)ghost_r * p.row_pitch + GHOST;
+    return p;
+}
+
+bool alloc_reg(astrea_ctx* c, Reg& r, int64_t ncol) {
+    r.mem = (double*)dev_alloc(c->plane_doubles * sizeof(double));
+    if (!r.mem) return false;
+    r.plane = make_plane(r.mem, ncol, c->ghost_r);
+    return dev_zero(r.mem, c->plane_doubles * sizeof(double), c->st) == 0;
+}
+
+// ---------------------------------------------------------------------------------------- step programs
+// Registers: 0 = u (the grid).  Rates: 0 = L of the most recent operator unless a formula re-uses older ones.
+void add_op(std::vector<Instr>& p, int src, int rate_out) { p.push_back(Instr{1, src, rate_out, 0, 0, 1.0, {}}); }
+void add_comb(std::vector<Instr>& p, int out, double scale, std::vector<Term> t, int bracket = 0) {
+    p.push_back(Instr{0, 0, 0, out, bracket, scale, std::move(t)});
+}
+Term R(int reg, double coef) { return Term{0, reg, coef}; }
+Term L(int rate, double coef) { return Term{1, rate, coef}; }
+
+// evolvers.py:79-206, literal coefficients and evaluation order.  Returns (#registers, #rates).
+void build_program(int integrator, std::vector<Instr>& p, int& nregs, int& nrates, int& final_reg) {
+    p.clear();
+    add_op(p, 0, 0);   // evolve_space on the grid (astrea.py:67)
+    switch (integrator) {
+        case INT_SSPRK104: {   // evolvers.py:84-103; u = reg0, k = reg1, k5 = reg2, _k = reg3
+            nregs = 4; nrates = 1;
+            add_comb(p, 1, 1.0, {R(0, 1.0)});                                  // k = copy(grid)
+            for (int s = 0; s < 5; ++s) {
+                add_comb(p, 1, 1.0, {R(1, 1.0), L(0, 1.0 / 6)});
+                add_op(p, 1, 0);
+            }
+            add_comb(p, 2, 1.0, {R(0, 3.0 / 5), R(1, 6.0 / 15), L(0, 1.0 / 15)});
+            add_op(p, 2, 0);
+            add_comb(p, 3, 1.0, {R(2, 1.0)});
+            for (int s = 0; s < 4; ++s) {
+                add_comb(p, 3, 1.0, {R(3, 1.0), L(0, 1.0 / 6)});
+                add_op(p, 3, 0);
+            }
+            add_comb(p, 0, 1.0, {R(0, -11.0 / 35), R(2, 5.0 / 7), R(3, 3.0 / 5), L(0, 1.0 / 10)});
+            final_reg = 0;
+            break;
+        }
+        case INT_SSPRK54: {    // evolvers.py:105-124; k1..k4 = reg1..4; rate0 = latest, rate1 = L(k3)
+            nregs = 5; nrates = 2;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, .39175222657189)});
+            add_op(p, 1, 0);
+            add_comb(p, 2, 1.0, {R(0, .444370493651235), R(1, .555629506348765), L(0, .368410593050371)});
+            add_op(p, 2, 0);
+            add_comb(p, 3, 1.0, {R(0, .620101851488403), R(2, .379898148511597), L(0, .251891774271694)});
+            add_op(p, 3, 1);
+            add_comb(p, 4, 1.0, {R(0, .178079954393132), R(3, .821920045606868), L(1, .544974750228521)});
+            add_op(p, 4, 0);
+            add_comb(p, 0, 1.0, {R(2, .517231671970585), R(3, .096059710526147), L(1, .06369246866629),
+                                 R(4, .386708617503269), L(0, .226007483236906)});
+            final_reg = 0;
+            break;
+        }
+        case INT_SSPRK53: {    // evolvers.py:127-146; rate0 = L0, rate1 = L1, rate2 = latest
+            nregs = 5; nrates = 3;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, .3772689151171)});
+            add_op(p, 1, 1);
+            add_comb(p, 2, 1.0, {R(1, 1.0), L(1, .3772689151171)});
+            add_op(p, 2, 2);
+            add_comb(p, 3, 1.0, {R(0, .56656131914033), R(2, .43343868085967), L(2, .16352294089771)});
+            add_op(p, 3, 2);
+            add_comb(p, 4, 1.0, {R(0, .09299483444413), R(1, .0000209036962), R(3, .90698426185967), L(0, .00071997378654),
+                                 L(2, .34217696850008)});
+            add_op(p, 4, 2);
+            add_comb(p, 0, 1.0, {R(0, .0073613226092), R(1, .20127980325145), R(2, .00182955389682), R(4, .78952932024253),
+                                 L(0, .0027771981946), L(1, .00001567934613), L(2, .29786487010104)}, 1);
+            final_reg = 0;
+            break;
+        }
+        case INT_SSPRK43: {    // evolvers.py:148-163
+            nregs = 2; nrates = 1;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, .5)});
+            add_op(p, 1, 0);
+            add_comb(p, 1, 1.0, {R(1, 1.0), L(0, .5)});
+            add_op(p, 1, 0);
+            add_comb(p, 1, 1.0 / 6, {R(0, 4.0), R(1, 2.0), L(0, 1.0)});
+            add_op(p, 1, 0);
+            add_comb(p, 0, 1.0, {R(1, 1.0), L(0, .5)});
+            final_reg = 0;
+            break;
+        }
+        case INT_SSPRK33: {    // evolvers.py:165-176
+            nregs = 2; nrates = 1;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, 1.0)});
+            add_op(p, 1, 0);
+            add_comb(p, 1, .25, {R(0, 3.0), R(1, 1.0), L(0, 1.0)});
+            add_op(p, 1, 0);
+            add_comb(p, 0, 1.0 / 3, {R(0, 1.0), R(1, 2.0), L(0, 2.0)});
+            final_reg = 0;
+            break;
+        }
+        case INT_SSPRK22: {    // evolvers.py:178-185
+            nregs = 2; nrates = 1;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, 1.0)});
+            add_op(p, 1, 0);
+            add_comb(p, 0, .5, {R(0, 1.0), R(1, 1.0), L(0, 1.0)});
+            final_reg = 0;
+            break;
+        }
+        case INT_RK4: {        // evolvers.py:187-202; rates 0..3 = L0..L3
+            nregs = 2; nrates = 4;
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(0, .5)});
+            add_op(p, 1, 1);
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(1, .5)});
+            add_op(p, 1, 2);
+            add_comb(p, 1, 1.0, {R(0, 1.0), L(2, 1.0)});
+            add_op(p, 1, 3);
+            add_comb(p, 0, 1.0 / 6, {R(0, 1.0), L(0, 1.0), L(1, 2.0), L(2, 2.0), L(3, 1.0)}, 1);
+            final_reg = 0;
+            break;
+        }
+        default: {             // forward Euler, evolvers.py:204-206
+            nregs = 1; nrates = 1;
+            add_comb(p, 0, 1.0, {R(0, 1.0), L(0, 1.0)});
+            final_reg = 0;
+            break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------- launches
+int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
+    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1};
+    ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st));
+    c->launches++;
+    if (c->ghost_r > 0) {
+        h.phase = 1;
+        // interior slab edges are provided by the neighbour ranks; a physical 'edge' boundary is always local
+        const bool lo_phys = c->cfg.x_offset == 0, hi_phys = c->cfg.x_offset + c->cfg.nx == c->cfg.nx_global;
+        const bool single = c->cfg.nx == c->cfg.nx_global;
+        if (external_rows && !single) {
+            h.fill_lo = (c->cfg.boundary == BC_EDGE && lo_phys) ? 1 : 0;
+            h.fill_hi = (c->cfg.boundary == BC_EDGE && hi_phys) ? 1 : 0;
+        }
+        if (h.fill_lo || h.fill_hi) {
+            const int gx = (int)((c->ncol + 2 * GHOST + 255) / 256);
+            ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st));
+            c->launches++;
+        }
+    }
+    return 0;
+}
+
+int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first) {
+    const astrea_cfg& g = c->cfg;
+    Plane q = c->regs[ins.src].plane;
+    if (int e = fill_halo(c, q, external_rows)) return e;
+    unsigned long long* eig = first ? c->eig_bits : c->eig_scratch;
+    ASTREA_TRY(dev_zero(eig, 2 * sizeof(unsigned long long), c->st));
+    if (g.dimension == 1) {
+        Sweep1DParams p{};
+        p.q = q; p.d = c->d0.plane; p.n = g.ny; p.gamma = g.gamma; p.dx = g.dx;
+        p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach; p.tile = c->tile1d;
+        p.eigmax_bits = eig; p.flag = c->flag;
+        ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st));
+        c->launches++;
+    } else {
+        // sweep order and the solver's private axis counter (solvers.py:34-36,63; astrea.py:85)
+        const int order[2] = {c->parity ? 1 : 0, c->parity ? 0 : 1};
+        // the y sweep works on the transposed copy of the (ghost-filled) register
+        TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST};
+        {
+            const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
+            ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st));
+            c->launches++;
+        }
+        for (int k = 0; k < 2; ++k) {
+            const int ax = order[k], sax = k;
+            Sweep2DParams p{};
+            p.gamma = g.gamma; p.dx = g.dx; p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach;
+            p.flag = c->flag;
+            p.eigmax_bits = eig + ax;
+            int colblocks;
+            if (ax == 0) {
+                p.q = q; p.d = c->d0.plane;
+                p.ns = c->nrow; p.nt = c->ncol;
+                p.ns_glob = g.nx_global; p.s_off = g.x_offset; p.nt_glob = c->ncol; p.t_off = 0;
+                colblocks = c->colblocks_x;
+            } else {
+                p.q = c->qT.plane; p.d = c->d1t.plane;
+                p.ns = c->ncol; p.nt = c->nrow;
+                p.ns_glob = c->ncol; p.s_off = 0; p.nt_glob = g.nx_global; p.t_off = g.x_offset;
+                colblocks = c->colblocks_y;
+            }
+            const int ht = scheme_high_order(g.scheme) ? 3 : 1;
+            p.tt = (int)((p.nt + colblocks - 1) / colblocks);
+            const int nthreads = p.tt + 2 * ht;
+            int seg = g.segment_2d;
+            if (seg <= 0) {
+                // enough blocks to fill 148 SMs in whole waves, while the start-up rows of a segment stay a small share
+                for (int waves = 1; waves <= 64; ++waves) {
+                    const int64_t nseg = std::max<int64_t>(1, (148 * waves + colblocks - 1) / colblocks);
+                    seg = (int)((p.ns + nseg - 1) / nseg);
+                    if (seg <= 512) break;
+                }
+                seg = std::max(seg, 32);
+            }
+            p.seg = (int)std::min<int64_t>(seg, p.ns);
+            ASTREA_TRY(launch_sweep2d(g.scheme, g.solver, ax, sax, p, nthreads, c->st));
+            c->launches++;
+        }
+    }
+    RateParams r{};
+    r.d0 = c->d0.plane; r.d1t = c->d1t.plane; r.out = c->rates[ins.rate_out].plane;
+    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = nullptr; r.emf_pitch = 0; r.dx = g.dx; r.bc = g.boundary;
+    {
+        const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
+        ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st));
+        c->launches++;
+    }
+    return 0;
+}
+
+int run_combine(astrea_ctx* c, const Instr& ins) {
+    CombineParams p{};
+    p.out = c->regs[ins.out].plane;
+    p.nterms = (int)ins.terms.size();
+    for (int k = 0; k < p.nterms; ++k) {
+        const Term& t = ins.terms[k];
+        p.term[k] = t.is_rate ? c->rates[t.index].plane : c->regs[t.index].plane;
+        p.coef[k] = t.coef;
+        p.is_rate[k] = t.is_rate;
+    }
+    p.bracket_rates = ins.bracket;
+    p.scale = ins.scale;
+    p.dt = c->dt_dev;
+    p.nrow = c->nrow; p.ncol = c->ncol;
+    const int gx = (int)((c->ncol + 255) / 256);
+    ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st));
+    c->launches++;
+    return 0;
+}
+
+int check_cfg(const astrea_cfg* g, std::string& why) {
+    if (!g) { why = "cfg is NULL"; return -1; }
+    if (g->dimension != 1 && g->dimension != 2) { why = "dimension must be 1 or 2"; return -1; }
+    if (g->boundary != ASTREA_EDGE && g->boundary != ASTREA_WRAP) { why = "boundary must be ASTREA_EDGE or ASTREA_WRAP"; return -1; }
+    if (g->scheme < ASTREA_PCM || g->scheme > ASTREA_WENO7) { why = "unknown scheme"; return -1; }
+    if (g->ppm_author != ASTREA_PPM_MC) { why = "only the 'mc' PPM limiter is wired (evolvers.py:17)"; return -1; }
+    if (g->limiter < ASTREA_MINMOD || g->limiter > ASTREA_SUPERBEE) { why = "unknown slope limiter"; return -1; }
+    if (g->solver != ASTREA_LLF && g->solver != ASTREA_HLLC && g->solver != ASTREA_HLLD) {
+        why = "solver not available on the device path (Lax-Wendroff depends on LAPACK eigenvalue slot order, SURVEY Q11)";
+        return -1;
+    }
+    if (g->integrator < ASTREA_EULER || g->integrator > ASTREA_SSPRK104) { why = "unknown integrator"; return -1; }
+    if (g->magnetic_2d) { why = "magnetic_2d (constrained transport) is not available in this build"; return -1; }
+    if (g->dimension == 1) {
+        if (g->nx < 1 || g->ny != 1) { why = "1D: nx >= 1 cells, ny == 1"; return -1; }
+        if (g->nx_global != g->nx || g->x_offset != 0) { why = "1D grids are not decomposed"; return -1; }
+    } else {
+        if (g->nx < 1 || g->ny < 1) { why = "2D: nx, ny >= 1"; return -1; }
+        if (g->nx_global < g->nx || g->x_offset < 0 || g->x_offset + g->nx > g->nx_global) { why = "slab outside the global grid"; return -1; }
+        if (g->nx != g->nx_global && g->nx < GHOST) { why = "a slab needs at least GHOST rows"; return -1; }
+    }
+    if (!(g->gamma > 1.0) || !(g->dx > 0.0) || !(g->cfl > 0.0)) { why = "gamma > 1, dx > 0, cfl > 0 required"; return -1; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+astrea_ctx* astrea_create(const astrea_cfg* cfg) {
+    std::string why;
+    if (check_cfg(cfg, why) != 0) { g_create_error = why; return nullptr; }
+    astrea_ctx* c = new astrea_ctx();
+    c->cfg = *cfg;
+#ifdef ASTREA_DEVICE_BUILD
+    {
+        cudaError_t e = cudaSetDevice(cfg->device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st.s, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = std::string("CUDA: ") + cudaGetErrorString(e); delete c; return nullptr; }
+        c->stream_owned = true;
+    }
+#endif
+    const astrea_cfg& g = c->cfg;
+    if (g.dimension == 1) { c->nrow = 1; c->ncol = g.nx; c->ghost_r = 0; c->cfg.ny = g.nx; c->cfg.nx = 1; c->cfg.nx_global = 1; }
+    else { c->nrow = g.nx; c->ncol = g.ny; c->ghost_r = GHOST; }
+    // the transposed planes of the y sweep have the same number of elements
+    c->plane_doubles = (size_t)(c->nrow + 2 * c->ghost_r) * NVAR * (size_t)(c->ncol + 2 * GHOST);
+    if (g.dimension == 2) c->plane_doubles = std::max(c->plane_doubles, (size_t)(c->ncol + 2 * GHOST) * NVAR * (size_t)(c->nrow + 2 * GHOST));
+
+    int nregs = 1, nrates = 1;
+    build_program(g.integrator, c->prog, nregs, nrates, c->final_reg);
+    bool ok = true;
+    c->regs.resize(nregs);
+    c->rates.resize(nrates);
+    for (auto& r : c->regs) ok = ok && alloc_reg(c, r, c->ncol);
+    for (auto& r : c->rates) ok = ok && alloc_reg(c, r, c->ncol);
+    ok = ok && alloc_reg(c, c->d0, c->ncol);
+    if (g.dimension == 2) {
+        ok = ok && alloc_reg(c, c->qT, c->nrow) && alloc_reg(c, c->d1t, c->nrow);
+    } else {
+        ok = ok && alloc_reg(c, c->qT, c->ncol);   // scratch for primitive downloads
+    }
+    c->eig_bits = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
+    c->flag = (int*)dev_alloc(sizeof(int));
+    c->dt_dev = (double*)dev_alloc(sizeof(double));
+    ok = ok && c->eig_bits && c->flag && c->dt_dev;
+    if (!ok) {
+        g_create_error = "device allocation failed";
+        astrea_destroy(c);
+        return nullptr;
+    }
+    c->eig_scratch = c->eig_bits + 2;
+    dev_zero(c->eig_bits, 4 * sizeof(unsigned long long), c->st);
+    dev_zero(c->flag, sizeof(int), c->st);
+    dev_zero(c->dt_dev, sizeof(double), c->st);
+
+    // launch geometry
+    if (g.dimension == 1) {
+        const int lo = recon_lo(g.scheme) + 2, hi = recon_hi(g.scheme) + 3;
+        int tile = g.tile_1d > 0 ? g.tile_1d : 256 - lo - hi;
+        tile = std::max(1, std::min(tile, 256 - lo - hi));
+        c->tile1d = tile;
+        c->threads1d = tile + lo + hi;
+    } else {
+        const int per_thread = sweep2d_doubles_per_thread(g.scheme, g.solver);
+        int tmax = (int)(SMEM_LIMIT / (sizeof(double) * per_thread));
+        tmax = std::min(256, tmax / 32 * 32);
+        if (g.threads_2d > 0) tmax = std::max(32, std::min(tmax, g.threads_2d));
+        const int ht = scheme_high_order(g.scheme) ? 3 : 1;
+        c->threads2d = tmax;
+        c->tt2d = tmax - 2 * ht;
+        c->colblocks_x = (int)((c->ncol + c->tt2d - 1) / c->tt2d);   // x sweep: columns are y
+        c->colblocks_y = (int)((c->nrow + c->tt2d - 1) / c->tt2d);   // y sweep: columns are x
+    }
+    return c;
+}
+
+void astrea_destroy(astrea_ctx* c) {
+    if (!c) return;
+    stream_sync(c->st);
+    for (auto& r : c->regs) dev_free(r.mem);
+    for (auto& r : c->rates) dev_free(r.mem);
+    dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
+    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev);
+#ifdef ASTREA_DEVICE_BUILD
+    if (c->stream_owned) cudaStreamDestroy(c->st.s);
+#endif
+    delete c;
+}
+
+const char* astrea_last_error(const astrea_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int astrea_upload(astrea_ctx* c, const double* grid_aos) {
+    if (!c || !grid_aos) return fail(c, ASTREA_E_ARG, "astrea_upload: NULL argument");
+    const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
+    double* staging = c->d0.mem;     // d0 is scratch between operator evaluations
+    ASTREA_TRY(copy_h2d(staging, grid_aos, bytes, c->st));
+    PackParams p{c->regs[c->grid_reg].plane, staging, c->nrow, c->ncol, 1};
+    ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
+    c->launches++;
+    c->next_instr = 0;
+    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_upload: stream sync failed");
+}
+
+int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
+    if (!c || !grid_aos) return fail(c, ASTREA_E_ARG, "astrea_download: NULL argument");
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_download: a step is in flight (between evolve_space and evolve_time the scratch planes are live)");
+    Plane src = c->regs[c->grid_reg].plane;
+    if (as_primitive) {
+        if (c->cfg.nx != c->cfg.nx_global && c->cfg.dimension == 2 && scheme_high_order(c->cfg.scheme))
+            return fail(c, ASTREA_E_STATE, "astrea_download: primitive download of a slab needs the caller to exchange ghost rows first (use astrea_download_primitive_ext)");
+        if (int e = fill_halo(c, src, 0)) return e;
+        Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r);
+        PrimParams pp{src, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
+        ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
+        c->launches++;
+        src = w;
+    }
+    const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
+    double* staging = c->d0.mem;
+    PackParams p{src, staging, c->nrow, c->ncol, 0};
+    ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
+    c->launches++;
+    ASTREA_TRY(copy_d2h(grid_aos, staging, bytes, c->st));
+    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_download: stream sync failed");
+}
+
+int astrea_program_length(const astrea_ctx* c) { return c ? (int)c->prog.size() : ASTREA_E_ARG; }
+
+int astrea_instr_is_operator(const astrea_ctx* c, int i) {
+    if (!c || i < 0 || i >= (int)c->prog.size()) return ASTREA_E_ARG;
+    return c->prog[i].is_operator;
+}
+
+int astrea_set_dt(astrea_ctx* c, double dt) {
+    if (!c) return ASTREA_E_ARG;
+    ASTREA_TRY(copy_h2d(c->dt_dev, &dt, sizeof(double), c->st));
+    // the source is a stack variable: finish the copy before returning
+    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_set_dt: stream sync failed");
+}
+
+int astrea_run_instr(astrea_ctx* c, int i, int external_rows) {
+    if (!c || i < 0 || i >= (int)c->prog.size()) return fail(c, ASTREA_E_ARG, "astrea_run_instr: bad instruction index");
+    if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_instr: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
+    const Instr& ins = c->prog[i];
+    const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0) : run_combine(c, ins);
+    if (e) return e;
+    c->next_instr = i + 1;
+    return 0;
+}
+
+int astrea_finish_step(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    if (c->next_instr != (int)c->prog.size()) return fail(c, ASTREA_E_STATE, "astrea_finish_step: the step program has not run to its end");
+    c->grid_reg = c->final_reg;
+    c->parity ^= 1;
+    c->next_instr = 0;
+    return 0;
+}
+
+int astrea_read_eigmax(astrea_ctx* c, double* eigmax) {
+    if (!c || !eigmax) return fail(c, ASTREA_E_ARG, "astrea_read_eigmax: NULL argument");
+    unsigned long long bits[2] = {0, 0};
+    int flag = 0;
+    ASTREA_TRY(copy_d2h(bits, c->eig_bits, sizeof(bits), c->st));
+    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(int), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_read_eigmax: stream sync failed");
+    for (int a = 0; a < c->cfg.dimension; ++a) {
+        const int slot = c->cfg.dimension == 1 ? 0 : a;
+        std::memcpy(&eigmax[a], &bits[slot], sizeof(double));
+    }
+    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed (the reference raises LinAlgError: Array must not contain infs or NaNs, fv.py:158)");
+    return 0;
+}
+
+int astrea_evolve_space(astrea_ctx* c, int step_parity, double* eigmax) {
+    if (!c) return ASTREA_E_ARG;
+    c->parity = step_parity & 1;
+    c->next_instr = 0;
+    if (int e = astrea_run_instr(c, 0, 0)) return e;
+    return astrea_read_eigmax(c, eigmax);
+}
+
+int astrea_evolve_time(astrea_ctx* c, double dt) {
+    if (!c) return ASTREA_E_ARG;
+    if (c->next_instr != 1) return fail(c, ASTREA_E_STATE, "astrea_evolve_time: call astrea_evolve_space first");
+    if (int e = astrea_set_dt(c, dt)) return e;
+    for (int i = 1; i < (int)c->prog.size(); ++i)
+        if (int e = astrea_run_instr(c, i, 0)) return e;
+    // astrea.py:81 rebinds grid; the permutation reversal (astrea.py:85) is the caller's (astrea_step does both)
+    c->grid_reg = c->final_reg;
+    c->next_instr = 0;
+    int flag = 0;
+    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(int), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_evolve_time: stream sync failed");
+    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a Runge-Kutta stage (fv.py:158 raises LinAlgError)");
+    return 0;
+}
+
+int astrea_step(astrea_ctx* c, double t, double t_stop, double* dt_out) {
+    if (!c) return ASTREA_E_ARG;
+    double eig[2] = {0, 0};
+    if (int e = astrea_evolve_space(c, c->parity, eig)) return e;
+    double dt = c->cfg.cfl * (c->cfg.dx / eig[0]);
+    if (c->cfg.dimension == 2) dt = std::min(dt, c->cfg.cfl * (c->cfg.dx / eig[1]));
+    if (t_stop > t && t + dt >= t_stop) dt = t_stop - t;
+    if (dt_out) *dt_out = dt;
+    if (int e = astrea_set_dt(c, dt)) return e;
+    for (int i = 1; i < (int)c->prog.size(); ++i)
+        if (int e = astrea_run_instr(c, i, 0)) return e;
+    return astrea_finish_step(c);
+}
+
+int astrea_get_parity(const astrea_ctx* c) { return c ? c->parity : ASTREA_E_ARG; }
+int astrea_set_parity(astrea_ctx* c, int p) { if (!c) return ASTREA_E_ARG; c->parity = p & 1; return 0; }
+
+int astrea_download_face_field(astrea_ctx* c, double*) { return fail(c, ASTREA_E_ARG, "magnetic_2d is not available in this build"); }
+
+int astrea_halo_info(const astrea_ctx* c, int64_t* ghost_rows, int64_t* doubles_per_block) {
+    if (!c) return ASTREA_E_ARG;
+    if (ghost_rows) *ghost_rows = c->ghost_r;
+    if (doubles_per_block) *doubles_per_block = (int64_t)c->ghost_r * NVAR * (c->ncol + 2 * GHOST);
+    return 0;
+}
+
+int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, double** recv_lo, double** recv_hi) {
+    if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_ptrs: not an operator instruction");
+    const Plane& p = c->regs[c->prog[i].src].plane;
+    // whole padded rows (ghost columns included): the receiver's corner ghosts come along for free; the ghost
+    // columns of the interior rows sent here are filled by astrea_halo_prepare()
+    double* row0 = p.base - GHOST;
+    if (send_lo) *send_lo = row0;                                                  // rows 0 .. G-1
+    if (send_hi) *send_hi = row0 + (c->nrow - c->ghost_r) * p.row_pitch;           // rows n-G .. n-1
+    if (recv_lo) *recv_lo = row0 - (int64_t)c->ghost_r * p.row_pitch;              // rows -G .. -1
+    if (recv_hi) *recv_hi = row0 + c->nrow * p.row_pitch;                          // rows n .. n+G-1
+    return 0;
+}
+
+int astrea_halo_prepare(astrea_ctx* c, int i) {
+    if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: not an operator instruction");
+    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0};
+    ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st));
+    c->launches++;
+    return 0;
+}
+
+int astrea_eigmax_device(astrea_ctx* c, double** p) {
+    if (!c || !p) return ASTREA_E_ARG;
+    *p = reinterpret_cast<double*>(c->eig_bits);
+    return 0;
+}
+
+int astrea_sync(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_sync: stream sync failed");
+}
+
+uint64_t astrea_stream_handle(const astrea_ctx* c) {
+#ifdef ASTREA_DEVICE_BUILD
+    return c ? (uint64_t)(uintptr_t)c->st.s : 0;
+#else
+    (void)c;
+    return 0;
+#endif
+}
+
+int64_t astrea_launch_count(const astrea_ctx* c) { return c ? c->launches : 0; }
+
+int astrea_is_device_build(void) {
+#ifdef ASTREA_DEVICE_BUILD
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// Data-movement and Runge-Kutta kernels around the sweep kernels.
+//   pack / unpack     host AoS (N[,N],8) C-order  <->  ghost-padded planes [row][var][col]   (+ cons->prim on download,
+//                     astrea.py:47 snapshots are primitive: fv.py:97-101 / :126-143)
+//   halo fill         fv.add_boundary (fv.py:57-61) as ghost cells of the *state* array: 'wrap' | 'edge'
+//   transpose         grid.transpose(axes) of the reference's y sweep
+//   assemble rate     compute_L (evolvers.py:41-60): L = -(dF_x/dx + dF_y/dx)
+//   combine           one Runge-Kutta register update, evaluation order as written in evolvers.py:79-206
+#pragma once
+#include "physics.cuh"
+#include "runtime.cuh"
+
+namespace astrea {
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+struct PackParams {
+    Plane plane;
+    double* aos;          // device staging buffer, (nrow, ncol, 8) C-order
+    int64_t nrow, ncol;
+    int to_plane;         // 1: aos -> plane, 0: plane -> aos
+};
+struct PackKernel {
+    using Params = PackParams;
+    static constexpr int MAX_THREADS = 256;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t c = (int64_t)bx * NT + tid, r = by;
+            if (c >= p.ncol) return;
+            double* a = p.aos + (r * p.ncol + c) * NVAR;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                if (p.to_plane) *p.plane.at(r, v, c) = a[v]; else a[v] = *p.plane.at(r, v, c);
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ halo fill
+struct HaloParams {
+    Plane plane;
+    int64_t nrow, ncol;
+    int bc;
+    int phase;            // 0: ghost columns of interior rows, 1: ghost rows (full padded width, corners included)
+    int fill_lo, fill_hi; // phase 1: which row ghosts to fill locally (0 when a neighbour rank provides them)
+};
+struct HaloKernel {
+    using Params = HaloParams;
+    static constexpr int MAX_THREADS = 256;
+    static HD int64_t src(int64_t g, int64_t n, int bc) { return bc == BC_WRAP ? wrap_index(g, n) : clamp_index(g, 0, n - 1); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            if (p.phase == 0) {
+                // by = row, threads over the 2*GHOST ghost columns x NVAR
+                const int64_t r = by;
+                for (int e = tid; e < 2 * GHOST * NVAR; e += NT) {
+                    const int v = e / (2 * GHOST), g = e % (2 * GHOST);
+                    const int64_t c = g < GHOST ? g - GHOST : p.ncol + (g - GHOST);
+                    *p.plane.at(r, v, c) = *p.plane.at(r, v, src(c, p.ncol, p.bc));
+                }
+            } else {
+                // by = ghost row id (0..2*GHOST-1) x var, threads over padded columns
+                const int g = by / NVAR, v = by % NVAR;
+                const bool lo = g < GHOST;
+                if ((lo && !p.fill_lo) || (!lo && !p.fill_hi)) return;
+                const int64_t r = lo ? g - GHOST : p.nrow + (g - GHOST);
+                const int64_t rs = src(r, p.nrow, p.bc);
+                const int64_t c = (int64_t)bx * NT + tid - GHOST;
+                if (c < p.ncol + GHOST) *p.plane.at(r, v, c) = *p.plane.at(rs, v, c);
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ transpose
+struct TransposeParams {
+    Plane src, dst;       // dst(row = c, col = r) = src(row = r, col = c), ghosts included
+    int64_t r_lo, r_hi, c_lo, c_hi;   // half-open ranges of src rows / cols to move
+};
+struct TransposeKernel {
+    using Params = TransposeParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TILE = 32;
+    static size_t smem_bytes() { return sizeof(double) * TILE * (TILE + 1); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        double* tile = ex.smem();
+        const int64_t c0 = p.c_lo + (int64_t)bx * TILE, r0 = p.r_lo + (int64_t)by * TILE;
+        for (int v = 0; v < NVAR; ++v) {
+            ex.phase([&](int tid) {
+                const int tx = tid % TILE;
+                for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                    const int64_t r = r0 + ty, c = c0 + tx;
+                    if (r < p.r_hi && c < p.c_hi) tile[ty * (TILE + 1) + tx] = *p.src.at(r, v, c);
+                }
+            });
+            ex.phase([&](int tid) {
+                const int tx = tid % TILE;
+                for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                    const int64_t r = r0 + tx, c = c0 + ty;     // dst row = c, dst col = r
+                    if (r < p.r_hi && c < p.c_hi) *p.dst.at(c, v, r) = tile[tx * (TILE + 1) + ty];
+                }
+            });
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ assemble L
+struct RateParams {
+    Plane d0;             // (F[i+1]-F[i])/dx of the x sweep, [x][v][y]
+    Plane d1t;            // same of the y sweep in its own (transposed) frame, [y][v][x]; unused in 1D
+    Plane out;            // L = -(d0 + d1)
+    int64_t nrow, ncol;
+    int dimension;
+    // constrained transport (evolvers.py:52-58): overwrite the in-plane field rates with emf differences
+    const double* emf;    // corner field [x][y] with ghost ring, or nullptr
+    int64_t emf_pitch;
+    double dx;
+    int bc;
+};
+struct RateKernel {
+    using Params = RateParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TILE = 32;
+    static size_t smem_bytes() { return sizeof(double) * TILE * (TILE + 1); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        double* tile = ex.smem();
+        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        for (int v = 0; v < NVAR; ++v) {
+            if (p.dimension == 2) {
+                ex.phase([&](int tid) {     // read the y-sweep tile coalesced along its own columns (= x)
+                    const int tx = tid % TILE;
+                    for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                        const int64_t yr = c0 + ty, xc = r0 + tx;
+                        if (yr < p.ncol && xc < p.nrow) tile[ty * (TILE + 1) + tx] = *p.d1t.at(yr, v, xc);
+                    }
+                });
+            }
+            ex.phase([&](int tid) {
+                const int tx = tid % TILE;
+                for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                    const int64_t r = r0 + ty, c = c0 + tx;
+                    if (r >= p.nrow || c >= p.ncol) continue;
+                    double total = *p.d0.at(r, v, c);
+                    if (p.dimension == 2) total = total + tile[tx * (TILE + 1) + ty];
+                    if (p.emf != nullptr && (v == 5 || v == 6)) {
+                        const double* e = p.emf + r * p.emf_pitch + c;
+                        if (v == 5) total = (e[1] - e[0]) / p.dx;                       // +dE/dy
+                        else total = (-1.0 * (e[p.emf_pitch] - e[0])) / p.dx;           // -dE/dx
+                    }
+                    *p.out.at(r, v, c) = -total;
+                }
+            });
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ RK combine
+// out = scale * ( sum_k coef_k * X_k )              terms evaluated and added left to right;
+//   X_k is a state register (coef used as is) or a rate buffer (coef multiplied by dt first: (b*dt)*L),
+// or, for the two closing formulas that bracket the rates (evolvers.py:146 and :202),
+// out = sum_regs a_i R_i + scale * (dt * (sum_rates b_j L_j)).
+constexpr int MAX_TERMS = 8;
+struct CombineParams {
+    Plane out;
+    Plane term[MAX_TERMS];
+    double coef[MAX_TERMS];
+    int is_rate[MAX_TERMS];
+    int nterms;
+    int bracket_rates;    // 0: interleaved form, 1: bracketed form
+    double scale;         // 1.0 = no scaling
+    const double* dt;     // device scalar
+    int64_t nrow, ncol;
+};
+struct CombineKernel {
+    using Params = CombineParams;
+    static constexpr int MAX_THREADS = 256;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t c = (int64_t)bx * NT + tid;
+            const int64_t r = by;
+            if (c >= p.ncol) return;
+            const double dt = *p.dt;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                double acc = 0.0;
+                if (!p.bracket_rates) {
+                    for (int k = 0; k < p.nterms; ++k) {
+                        const double x = *p.term[k].at(r, v, c);
+                        const double t = p.is_rate[k] ? (p.coef[k] * dt) * x : p.coef[k] * x;
+                        acc = (k == 0) ? t : acc + t;
+                    }
+                    if (p.scale != 1.0) acc = p.scale * acc;
+                } else {
+                    double regs = 0.0, rates = 0.0;
+                    bool fr = true, fl = true;
+                    for (int k = 0; k < p.nterms; ++k) {
+                        const double x = *p.term[k].at(r, v, c);
+                        if (p.is_rate[k]) { const double t = p.coef[k] * x; rates = fl ? t : rates + t; fl = false; }
+                        else { const double t = p.coef[k] * x; regs = fr ? t : regs + t; fr = false; }
+                    }
+                    double tail = dt * rates;
+                    if (p.scale != 1.0) tail = p.scale * tail;
+                    acc = regs + tail;
+                }
+                *p.out.at(r, v, c) = acc;
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ cons -> prim for download
+struct PrimParams {
+    Plane q, w;           // w may alias a scratch register; ghosts of q must be valid for the 4th-order conversion
+    int64_t nrow, ncol;
+    int dimension, high_order;
+    double gamma;
+};
+struct PrimKernel {
+    using Params = PrimParams;
+    static constexpr int MAX_THREADS = 256;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t c = (int64_t)bx * NT + tid, r = by;
+            if (c >= p.ncol) return;
+            const double c24 = 1.0 / 24.0;
+            double q[NVAR], w[NVAR];
+            auto ld = [&](int64_t rr, int64_t cc, double* dst) {
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) dst[v] = *p.q.at(rr, v, cc);
+            };
+            ld(r, c, q);
+            if (!p.high_order) {
+                prim_of_cons(q, w, p.gamma);
+            } else {
+                double a[NVAR], b[NVAR], wa[NVAR], wb[NVAR], wc[NVAR], qa[NVAR], ws[NVAR];
+                prim_of_cons(q, wc, p.gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) { qa[v] = q[v]; ws[v] = 0.0; }
+                for (int ax = 0; ax < p.dimension; ++ax) {
+                    // 1D data live in a single row: its only axis is the column axis
+                    const bool along_rows = (p.dimension == 2 && ax == 0);
+                    ld(along_rows ? r - 1 : r, along_rows ? c : c - 1, a);
+                    ld(along_rows ? r + 1 : r, along_rows ? c : c + 1, b);
+                    prim_of_cons(a, wa, p.gamma);
+                    prim_of_cons(b, wb, p.gamma);
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v) {
+                        qa[v] = qa[v] - c24 * ((b[v] - q[v]) - (q[v] - a[v]));
+                        ws[v] = ws[v] + c24 * ((wb[v] - wc[v]) - (wc[v] - wa[v]));
+                    }
+                }
+                prim_of_cons(qa, w, p.gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) w[v] = w[v] + ws[v];
+            }
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) *p.w.at(r, v, c) = w[v];
+        });
+    }
+};
+
+}  // namespace astrea

@@ -1,0 +1,5 @@
+// Sweep-kernel instantiations for one reconstruction scheme (see dispatch.cuh).
+#include "dispatch.cuh"
+namespace astrea {
+ASTREA_DEFINE_SCHEME(weno7, SCH_WENO7)
+}

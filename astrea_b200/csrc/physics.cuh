@@ -1,0 +1,72 @@
+// Point-wise ideal-MHD physics in fp64, operation order as in the reference.
+//   cons<->prim            functions/fv.py:49-53, 89-101
+//   physical flux          functions/constructor.py:113-125
+//   Roe average            functions/constructor.py:167-176   (B is weighted the other way round)
+//   max |eigenvalue|       closed form |v_n| + c_fast of the Jacobian of constructor.py:129-163 (fv.py:157-162)
+#pragma once
+#include "common.cuh"
+
+namespace astrea {
+
+HD void prim_of_cons(const double* q, double* w, double gamma) {
+    const double rho = q[0];
+    const double vx = sdiv(q[1], rho), vy = sdiv(q[2], rho), vz = sdiv(q[3], rho);
+    const double p = (gamma - 1.0) * (q[4] - 0.5 * (rho * norm3sq(vx, vy, vz) + norm3sq(q[5], q[6], q[7])));
+    w[0] = rho; w[1] = vx; w[2] = vy; w[3] = vz; w[4] = p; w[5] = q[5]; w[6] = q[6]; w[7] = q[7];
+}
+
+HD void cons_of_prim(const double* w, double* q, double gamma) {
+    const double rho = w[0];
+    const double e = w[4] / (gamma - 1.0) + 0.5 * (rho * norm3sq(w[1], w[2], w[3]) + norm3sq(w[5], w[6], w[7]));
+    q[0] = rho; q[1] = w[1] * rho; q[2] = w[2] * rho; q[3] = w[3] * rho; q[4] = e; q[5] = w[5]; q[6] = w[6]; q[7] = w[7];
+}
+
+// AX = true sweep axis (0: x, 1: y); components keep their physical meaning under the reference's transposes.
+template <int AX>
+HD void physical_flux(const double* w, double* f, double gamma) {
+    constexpr int n = AX % 3, t1 = (AX + 1) % 3, t2 = (AX + 2) % 3;
+    const double rho = w[0], p = w[4];
+    const double vn = w[1 + n], bn = w[5 + n];
+    f[0] = rho * vn;
+    f[1 + n] = rho * (vn * vn) + p + 0.5 * norm3sq(w[5], w[6], w[7]) - bn * bn;
+    f[1 + t1] = rho * vn * w[1 + t1] - bn * w[5 + t1];
+    f[1 + t2] = rho * vn * w[1 + t2] - bn * w[5 + t2];
+    const double vdotb = (w[1] * w[5] + w[2] * w[6]) + w[3] * w[7];
+    f[4] = vn * (0.5 * rho * norm3sq(w[1], w[2], w[3]) + (gamma * p) / (gamma - 1.0) + norm3sq(w[5], w[6], w[7])) - bn * vdotb;
+    f[5 + n] = 0.0;
+    f[5 + t1] = w[5 + t1] * vn - bn * w[1 + t1];
+    f[5 + t2] = w[5 + t2] * vn - bn * w[1 + t2];
+}
+
+// make_Roe_average(first = w_plus, second = w_minus)
+HD void roe_state(const double* first, const double* second, double* out) {
+    const double s2 = sqrt(second[0]), s1 = sqrt(first[0]);
+    const double den = s2 + s1;
+    out[0] = s2 * s1;
+    out[1] = sdiv(first[1] * s1 + second[1] * s2, den);
+    out[2] = sdiv(first[2] * s1 + second[2] * s2, den);
+    out[3] = sdiv(first[3] * s1 + second[3] * s2, den);
+    out[4] = sdiv(s1 * first[4] + s2 * second[4], den);
+    out[5] = sdiv(first[5] * s2 + second[5] * s1, den);
+    out[6] = sdiv(first[6] * s2 + second[6] * s1, den);
+    out[7] = sdiv(first[7] * s2 + second[7] * s1, den);
+}
+
+HD void mean_state(const double* a, const double* b, double* out) {   // plm.py:45
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v) out[v] = 0.5 * (a[v] + b[v]);
+}
+
+// max |lambda| of the primitive Jacobian at state w along AX: |v_n| + fast magnetosonic speed.
+template <int AX>
+HD double spectral_radius(const double* w, double gamma) {
+    const double rho = w[0];
+    const double a2 = gamma * w[4] / rho;
+    const double b2 = ((w[5] * w[5] + w[6] * w[6]) + w[7] * w[7]) / rho;
+    const double bn2 = w[5 + AX] * w[5 + AX] / rho;
+    const double s = a2 + b2;
+    const double cf = sqrt(0.5 * (s + sqrt(s * s - 4.0 * (a2 * bn2))));
+    return fabs(w[1 + AX]) + cf;
+}
+
+}  // namespace astrea

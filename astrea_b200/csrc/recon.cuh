@@ -1,0 +1,183 @@
+// Reconstructions and limiters: one cell, one variable at a time.
+//   slope limiters            num_methods/limiters.py:10-49
+//   PLM                       schemes/plm.py:26-36
+//   PPM face interpolant      schemes/ppm.py:38
+//   PPM-mc extrapolant limiter num_methods/limiters.py:89-143 (the default author, evolvers.py:17)
+//   WENO-3/5/7                schemes/weno.py:22-149
+//
+// Every function takes an accessor ``A`` with
+//     double A.s(int64 k)   value of the primitive cell average at *logical* cell index k (already mapped)
+//     int64  A.b(int64 k)   boundary map of a logical index: identity where ghost data are genuine
+//                           (periodic / interior slab edges), clamp into the domain for 'edge'
+// Boundary handling is "pad the derived array" (SURVEY Q7): every derived quantity (d2c, d3, face value) is
+// evaluated at a mapped index from mapped neighbours, never from ghost-cell reconstructions.
+#pragma once
+#include "common.cuh"
+
+namespace astrea {
+
+// ----------------------------------------------------------------------------------------- slope limiters
+template <class A>
+HD double limited_slope(const A& acc, int64_t i, int limiter) {
+    const double c = acc.s(i);
+    const double a = c - acc.s(acc.b(i - 1));
+    const double b = acc.s(acc.b(i + 1)) - c;
+    if (limiter == LIM_MINMOD) {
+        if (a * b > 0.0) return (fabs(a) < fabs(b)) ? a : b;
+        return 0.0;
+    }
+    const double r = sdiv(a, b);
+    switch (limiter) {
+        case LIM_VANLEER: return (r + fabs(r)) / (1.0 + fabs(r)) * b;
+        case LIM_OSPRE: return 1.5 * ((r * r + r) / (r * r + r + 1.0)) * b;
+        case LIM_VANALBADA: return (r * r + r) / (r * r + 1.0) * b;
+        case LIM_KOREN: return npmax(0.0, npmin(npmin(2.0 * r, (2.0 + r) / 3.0), 2.0)) * b;
+        default: return npmax(0.0, npmax(npmin(2.0 * r, 1.0), npmin(r, 2.0))) * b;   // superbee
+    }
+}
+
+template <class A>
+HD void cell_faces_plm(const A& acc, int64_t i, int limiter, double& wL, double& wR) {
+    const double half = 0.5 * limited_slope(acc, i, limiter);
+    const double c = acc.s(i);
+    wL = c - half;
+    wR = c + half;
+}
+
+// ----------------------------------------------------------------------------------------- PPM
+// face value at the right face of (mapped) cell k
+template <class A>
+HD double ppm_face(const A& acc, int64_t k) {
+    return 7.0 / 12.0 * (acc.s(k) + acc.s(acc.b(k + 1))) - 1.0 / 12.0 * (acc.s(acc.b(k - 1)) + acc.s(acc.b(k + 2)));
+}
+template <class A>
+HD double ppm_d2c(const A& acc, int64_t k) {   // central second difference at (mapped) cell k
+    return acc.s(acc.b(k - 1)) - 2.0 * acc.s(k) + acc.s(acc.b(k + 1));
+}
+template <class A>
+HD double ppm_d3(const A& acc, int64_t k) {    // limiters.py:96 at (mapped) cell k
+    return ppm_d2c(acc, acc.b(k + 1)) - ppm_d2c(acc, k);
+}
+
+// McCorquodale & Colella limiter.  ``wF`` returns the face value kept for constrained transport (ppm.py:101).
+// The reference's grid-wide ``if cell_extrema.any()`` needs no reduction: when no extremum exists anywhere its
+// else-branch produces the same numbers as the if-branch, so the if-branch is always taken here.
+template <class A>
+HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, double& wF) {
+    const double C = 5.0 / 4.0;
+    const double c = acc.s(i);
+    const double m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
+    const double faceR = 7.0 / 12.0 * (c + p1) - 1.0 / 12.0 * (m1 + p2);
+    const double faceL = ppm_face(acc, acc.b(i - 1));
+    wF = faceR;
+    const double dwm = c - faceL, dwp = faceR - c;
+    const double d2f = 6.0 * (faceL - 2.0 * c + faceR);
+    const double d2c = m1 - 2.0 * c + p1;
+    const double d2c_m1 = ppm_d2c(acc, acc.b(i - 1)), d2c_p1 = ppm_d2c(acc, acc.b(i + 1));
+    const double d3 = d2c_p1 - d2c;
+    const bool extremum = (dwm * dwp <= 0.0) || ((c - m2) * (p2 - c) <= 0.0);
+    double d2lim = 0.0;
+    if (extremum) d2lim = npsign(d2c) * npmin(npmin(fabs(d2f), C * fabs(d2c)), npmin(C * fabs(d2c_p1), C * fabs(d2c_m1)));
+    const double scale = npmax(fabs(c), npmax(npmax(fabs(m1), fabs(p1)), npmax(fabs(m2), fabs(p2))));
+    const double rho = (fabs(d2f) > 1e-12 * scale) ? sdiv(d2lim, d2f) : 0.0;
+    const double d3_m1 = ppm_d3(acc, acc.b(i - 1)), d3_m2 = ppm_d3(acc, acc.b(i - 2)), d3_p2 = ppm_d3(acc, acc.b(i + 2));
+    const double d3min = npmin(npmin(d3_m1, d3), npmin(d3_m2, d3_p2));
+    const double d3max = npmax(npmax(d3_m1, d3), npmax(d3_m2, d3_p2));
+    const bool act = (rho < (1.0 - 1e-12)) || (0.1 * npmax(fabs(d3max), fabs(d3min)) <= (d3max - d3min));
+    wL = faceL;
+    wR = faceR;
+    if (act) {
+        if (dwm * dwp < 0.0) {
+            wL = c - rho * dwm;
+            wR = c + rho * dwp;
+        }
+        if (fabs(dwm) >= 2.0 * fabs(dwp)) wL = c - 2.0 * (1.0 - rho) * dwp - rho * dwm;
+        if (fabs(dwp) >= 2.0 * fabs(dwm)) wR = c + 2.0 * (1.0 - rho) * dwm + rho * dwp;
+    }
+}
+
+// ----------------------------------------------------------------------------------------- WENO
+template <class A>
+HD void cell_faces_weno3(const A& acc, int64_t i, double& wL, double& wR) {
+    const double eps = 1e-6, g0 = 1.0 / 3.0, g1 = 2.0 / 3.0;
+    const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1));
+    const double b0 = sq(c0 - m1), b1 = sq(p1 - c0);
+    const double e0 = sq(b0 + eps), e1 = sq(b1 + eps);
+    const double r0 = g0 / e0, r1 = g1 / e1;         // a0(g0), a1(g1)
+    const double l0 = g1 / e0, l1 = g0 / e1;         // a0(g1), a1(g0)
+    wR = (r0 / (r0 + r1)) * (1.5 * c0 - 0.5 * m1) + (r1 / (r0 + r1)) * (0.5 * c0 + 0.5 * p1);
+    wL = (l1 / (l0 + l1)) * (1.5 * c0 - 0.5 * p1) + (l0 / (l0 + l1)) * (0.5 * c0 + 0.5 * m1);
+}
+
+template <class A>
+HD void cell_faces_weno5(const A& acc, int64_t i, double& wL, double& wR) {
+    const double eps = 1e-6, g0 = 1.0 / 10.0, g1 = 3.0 / 5.0, g2 = 3.0 / 10.0;
+    const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
+    const double b0 = 13.0 / 12.0 * sq(m2 - 2.0 * m1 + c0) + 1.0 / 4.0 * sq(m2 - 4.0 * m1 + 3.0 * c0);
+    const double b1 = 13.0 / 12.0 * sq(m1 - 2.0 * c0 + p1) + 1.0 / 4.0 * sq(m1 - p1);
+    const double b2 = 13.0 / 12.0 * sq(c0 - 2.0 * p1 + p2) + 1.0 / 4.0 * sq(3.0 * c0 - 4.0 * p1 + p2);
+    const double e0 = sq(b0 + eps), e1 = sq(b1 + eps), e2 = sq(b2 + eps);
+    const double r0 = g0 / e0, r1 = g1 / e1, r2 = g2 / e2;
+    const double sR = r0 + r1 + r2;
+    wR = (r0 / sR) * (1.0 / 3.0 * m2 - 7.0 / 6.0 * m1 + 11.0 / 6.0 * c0)
+       + (r1 / sR) * (-1.0 / 6.0 * m1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * p1)
+       + (r2 / sR) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * p1 - 1.0 / 6.0 * p2);
+    const double l0 = g2 / e0, l1 = g1 / e1, l2 = g0 / e2;
+    const double sL = l0 + l1 + l2;
+    wL = (l0 / sL) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * m1 - 1.0 / 6.0 * m2)
+       + (l1 / sL) * (-1.0 / 6.0 * p1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * m1)
+       + (l2 / sL) * (1.0 / 3.0 * p2 - 7.0 / 6.0 * p1 + 11.0 / 6.0 * c0);
+}
+
+template <class A>
+HD void cell_faces_weno7(const A& acc, int64_t i, double& wL, double& wR) {
+    const double eps = 1e-6, g0 = 1.0 / 35.0, g1 = 12.0 / 35.0, g2 = 18.0 / 35.0, g3 = 4.0 / 35.0;
+    const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2)),
+                 m3 = acc.s(acc.b(i - 3)), p3 = acc.s(acc.b(i + 3));
+    const double b0 = m3 * (547.0 * m3 - 3882.0 * m2 + 4642.0 * m1 - 1854.0 * c0) + m2 * (7043.0 * m2 - 17246.0 * m1 + 7042.0 * c0)
+                    + m1 * (11003.0 * m1 - 9402.0 * c0) + c0 * (2107.0 * c0);
+    const double b1 = m2 * (267.0 * m2 - 1642.0 * m1 + 1602.0 * c0 - 494.0 * p1) + m1 * (2843.0 * m1 - 5966.0 * c0 + 1922.0 * p1)
+                    + c0 * (3443.0 * c0 - 2522.0 * p1) + p1 * (547.0 * p1);
+    const double b2 = m1 * (547.0 * m1 - 2522.0 * c0 + 1922.0 * p1 - 494.0 * p2) + c0 * (3443.0 * c0 - 5966.0 * p1 + 1602.0 * p2)
+                    + p1 * (2843.0 * p1 - 1642.0 * p2) + p2 * (267.0 * p2);
+    const double b3 = c0 * (2107.0 * c0 - 9402.0 * p1 + 7042.0 * p2 - 1854.0 * p3) + p1 * (11003.0 * p1 - 17246.0 * p2 + 4642.0 * p3)
+                    + p2 * (7043.0 * p2 - 3882.0 * p3) + p3 * (547.0 * p3);
+    const double e0 = sq(b0 + eps), e1 = sq(b1 + eps), e2 = sq(b2 + eps), e3 = sq(b3 + eps);
+    const double r0 = g0 / e0, r1 = g1 / e1, r2 = g2 / e2, r3 = g3 / e3;
+    const double sR = r0 + r1 + r2 + r3;
+    wR = (r0 / sR) * (-1.0 / 4.0 * m3 + 13.0 / 12.0 * m2 - 23.0 / 12.0 * m1 + 25.0 / 12.0 * c0)
+       + (r1 / sR) * (1.0 / 12.0 * m2 - 5.0 / 12.0 * m1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * p1)
+       + (r2 / sR) * (-1.0 / 12.0 * m1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * p1 - 1.0 / 12.0 * p2)
+       + (r3 / sR) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * p1 - 5.0 / 12.0 * p2 + 1.0 / 12.0 * p3);
+    const double l0 = g3 / e0, l1 = g2 / e1, l2 = g1 / e2, l3 = g0 / e3;
+    const double sL = l0 + l1 + l2 + l3;
+    wL = (l0 / sL) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * m1 - 5.0 / 12.0 * m2 + 1.0 / 12.0 * m3)
+       + (l1 / sL) * (-1.0 / 12.0 * p1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * m1 - 1.0 / 12.0 * m2)
+       + (l2 / sL) * (1.0 / 12.0 * p2 - 5.0 / 12.0 * p1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * m1)
+       + (l3 / sL) * (-1.0 / 4.0 * p3 + 13.0 / 12.0 * p2 - 23.0 / 12.0 * p1 + 25.0 / 12.0 * c0);
+}
+
+// Dispatch: wL / wR of cell i (mapped index) for one variable; wF = the face state handed to constrained
+// transport (pcm.py:35, plm.py:57, ppm.py:101, weno.py:184).
+template <int SCHEME, class A>
+HD void cell_faces(const A& acc, int64_t i, int limiter, double& wL, double& wR, double& wF) {
+    if (SCHEME == SCH_PCM) {
+        wL = wR = wF = acc.s(i);
+    } else if (SCHEME == SCH_PLM) {
+        cell_faces_plm(acc, i, limiter, wL, wR);
+        wF = wR;
+    } else if (SCHEME == SCH_PPM) {
+        cell_faces_ppm_mc(acc, i, wL, wR, wF);
+    } else if (SCHEME == SCH_WENO3) {
+        cell_faces_weno3(acc, i, wL, wR);
+        wF = wR;
+    } else if (SCHEME == SCH_WENO5) {
+        cell_faces_weno5(acc, i, wL, wR);
+        wF = wR;
+    } else {
+        cell_faces_weno7(acc, i, wL, wR);
+        wF = wR;
+    }
+}
+
+}  // namespace astrea

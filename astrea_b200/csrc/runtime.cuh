@@ -1,0 +1,155 @@
+// Execution layer: one kernel body, two back ends.
+//
+// A kernel is a struct ``K`` with
+//     template <class Ex> static HD void block(const K::Params& p, int bx, int by, Ex& ex);
+// whose body is a sequence of ``ex.phase([&](int tid) {...});`` calls.  ``phase`` runs the lambda for every
+// thread of the block and ends with a block-wide barrier.
+//   * device build : ``phase`` calls the lambda with threadIdx.x and then __syncthreads()
+//   * hostsim build: ``phase`` loops tid = 0..nthreads-1 (test infrastructure, see common.cuh)
+// Per-thread values that live across phases are declared as ``typename Ex::template Local<T>`` and indexed
+// by tid (a register-resident T on the device, an array on the host).
+#pragma once
+#include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef ASTREA_DEVICE_BUILD
+#include <cuda_runtime.h>
+#endif
+
+namespace astrea {
+
+#ifdef ASTREA_DEVICE_BUILD
+// ------------------------------------------------------------------------------------------- device back end
+struct DeviceExec {
+    template <class T>
+    struct Local {
+        T v;
+        __device__ explicit Local(DeviceExec&) {}
+        __device__ T& operator[](int) { return v; }
+    };
+    __device__ int nthreads() const { return blockDim.x; }
+    __device__ double* smem() const {
+        extern __shared__ __align__(16) double astrea_dyn_smem[];
+        return astrea_dyn_smem;
+    }
+    template <class F>
+    __device__ __forceinline__ void phase(F&& f) {
+        f((int)threadIdx.x);
+        __syncthreads();
+    }
+    // Block-wide max of a non-negative per-thread value -> atomicMax on the bit pattern of *dst; ``bad``
+    // (non-finite seen) is OR-ed into *flag.  Call from block scope (not inside a phase): get(tid, val, bad).
+    template <class G>
+    __device__ void publish_max(G&& get, unsigned long long* dst, int* flag) {
+        __shared__ double red[32];
+        __shared__ int redbad[32];
+        double val = 0.0;
+        bool bad = false;
+        get((int)threadIdx.x, val, bad);
+        for (int o = 16; o > 0; o >>= 1) {
+            val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
+            bad = bad | (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane == 0) { red[warp] = val; redbad[warp] = bad; }
+        __syncthreads();
+        if (warp == 0) {
+            val = lane < nw ? red[lane] : 0.0;
+            bad = lane < nw ? (bool)redbad[lane] : false;
+            for (int o = 16; o > 0; o >>= 1) {
+                val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
+                bad = bad | (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
+            }
+            if (lane == 0) {
+                atomicMax(dst, (unsigned long long)__double_as_longlong(val));
+                if (bad) atomicOr(flag, 1);
+            }
+        }
+        __syncthreads();
+    }
+};
+
+template <class K>
+__global__ void __launch_bounds__(K::MAX_THREADS) kernel_entry(const typename K::Params p) {
+    DeviceExec ex;
+    K::block(p, (int)blockIdx.x, (int)blockIdx.y, ex);
+}
+
+struct Stream { cudaStream_t s; };
+
+template <class K>
+inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream st) {
+    static size_t configured_bytes = 48 * 1024;     // per kernel: the opt-in dynamic shared-memory size set so far
+    if (smem_bytes > configured_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured_bytes = smem_bytes;
+    }
+    kernel_entry<K><<<dim3(gx, gy, 1), dim3(nthreads, 1, 1), smem_bytes, st.s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+inline void* dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline int dev_zero(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAsync(p, 0, bytes, st.s); }
+inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s); }
+inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s); }
+inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st.s); }
+inline int stream_sync(Stream st) { return (int)cudaStreamSynchronize(st.s); }
+
+#else
+// ------------------------------------------------------------------------------------------- hostsim back end
+struct HostExec {
+    int nthr;
+    std::vector<double> shared;
+    template <class T>
+    struct Local {
+        std::vector<T> v;
+        explicit Local(HostExec& ex) : v(ex.nthr) {}
+        T& operator[](int tid) { return v[tid]; }
+    };
+    HostExec(int n, size_t smem_bytes) : nthr(n), shared(smem_bytes / sizeof(double) + 1) {}
+    int nthreads() const { return nthr; }
+    double* smem() { return shared.data(); }
+    template <class F>
+    void phase(F&& f) {
+        for (int t = 0; t < nthr; ++t) f(t);
+    }
+    template <class G>
+    void publish_max(G&& get, unsigned long long* dst, int* flag) {
+        for (int t = 0; t < nthr; ++t) {
+            double val = 0.0, cur;
+            bool bad = false;
+            get(t, val, bad);
+            std::memcpy(&cur, dst, 8);
+            if (val > cur) std::memcpy(dst, &val, 8);
+            if (bad) *flag |= 1;
+        }
+    }
+};
+
+struct Stream { int s; };
+
+template <class K>
+inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream) {
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) {
+            HostExec ex(nthreads, smem_bytes);
+            K::block(p, bx, by, ex);
+        }
+    return 0;
+}
+
+inline void* dev_alloc(size_t bytes) { return std::malloc(bytes); }
+inline void dev_free(void* p) { std::free(p); }
+inline int dev_zero(void* p, size_t bytes, Stream) { std::memset(p, 0, bytes); return 0; }
+inline int copy_h2d(void* d, const void* h, size_t bytes, Stream) { std::memcpy(d, h, bytes); return 0; }
+inline int copy_d2h(void* h, const void* d, size_t bytes, Stream) { std::memcpy(h, d, bytes); return 0; }
+inline int copy_d2d(void* d, const void* s, size_t bytes, Stream) { std::memcpy(d, s, bytes); return 0; }
+inline int stream_sync(Stream) { return 0; }
+#endif
+
+}  // namespace astrea

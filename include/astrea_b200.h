@@ -1,0 +1,130 @@
+/* astrea_b200 — C ABI of the B200-native per-timestep finite-volume update of mervyzr/astrea.
+ *
+ * The reference has no plugin or FFI interface: the seam is the Python call pair
+ *     fluxes = evolvers.evolve_space(grid, sim_variables)            astrea.py:67   (num_methods/evolvers.py:12-34)
+ *     grid   = evolvers.evolve_time(grid, fluxes, dt, sim_variables) astrea.py:81   (num_methods/evolvers.py:38-206)
+ * plus the read of fluxes[axes]['eigmax'] at astrea.py:70-71 and the primitive snapshot at astrea.py:47.
+ * Every entry point below names the reference line(s) it stands in for.  All functions take plain pointers
+ * and sizes; host buffers stay owned by the caller, device state is owned by the context.  One host thread
+ * per context; all work of a context is ordered on one CUDA stream.
+ *
+ * Return value: 0 on success, a negative ASTREA_E_* code on failure (astrea_last_error() gives the text).
+ */
+#ifndef ASTREA_B200_H
+#define ASTREA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct astrea_ctx astrea_ctx;
+
+enum { ASTREA_PCM = 0, ASTREA_PLM = 1, ASTREA_PPM = 2, ASTREA_WENO3 = 3, ASTREA_WENO5 = 4, ASTREA_WENO7 = 5 };   /* sim_variables.subgrid, evolvers.py:14-21 */
+enum { ASTREA_PPM_MC = 0 };                                                                                   /* evolvers.py:17 passes author='mc' */
+enum { ASTREA_MINMOD = 0, ASTREA_VANLEER = 1, ASTREA_OSPRE = 2, ASTREA_VANALBADA = 3, ASTREA_KOREN = 4, ASTREA_SUPERBEE = 5 }; /* limiters.py:10-49 */
+enum { ASTREA_LLF = 0, ASTREA_LW = 1, ASTREA_HLLC = 2, ASTREA_HLLD = 3 };                                         /* sim_variables.solver, solvers.py:13-31 */
+enum { ASTREA_EULER = 0, ASTREA_RK4 = 1, ASTREA_SSPRK22 = 2, ASTREA_SSPRK33 = 3, ASTREA_SSPRK43 = 4,
+       ASTREA_SSPRK53 = 5, ASTREA_SSPRK54 = 6, ASTREA_SSPRK104 = 7 };                                          /* sim_variables.timestep, evolvers.py:79-206 */
+enum { ASTREA_EDGE = 0, ASTREA_WRAP = 1 };                                                                       /* sim_variables.boundary (np.pad mode), fv.py:57-61 */
+
+enum {
+    ASTREA_OK = 0,
+    ASTREA_E_ARG = -1,        /* bad argument / unsupported selector combination */
+    ASTREA_E_CUDA = -2,       /* CUDA runtime error */
+    ASTREA_E_NONFINITE = -3,  /* non-finite wave speed: where the reference raises LinAlgError out of fv.py:158 (astrea.py:211-217) */
+    ASTREA_E_STATE = -4       /* call order violated (e.g. evolve_time without evolve_space) */
+};
+
+/* The subset of the reference's sim_variables namedtuple that the hot path reads
+ * (functions/generic.py:159-286, static/tests.py:317-328). */
+typedef struct astrea_cfg {
+    int32_t dimension;     /* 1 | 2 */
+    int32_t boundary;      /* ASTREA_EDGE | ASTREA_WRAP */
+    int64_t nx;            /* local cells along x (1D: the only axis) */
+    int64_t ny;            /* local cells along y (1D: 1) */
+    double gamma;
+    double dx;             /* cell width, dx == dy (tests.py:326-327) */
+    double cfl;
+    int32_t scheme;        /* ASTREA_PCM .. ASTREA_WENO7 */
+    int32_t ppm_author;    /* ASTREA_PPM_MC */
+    int32_t limiter;       /* slope limiter of PLM */
+    int32_t solver;        /* ASTREA_LLF .. ASTREA_HLLD */
+    int32_t low_mach;      /* solvers.py:92 low_mach switch of HLLC */
+    int32_t integrator;    /* ASTREA_EULER .. ASTREA_SSPRK104 */
+    int32_t magnetic_2d;   /* constrained-transport update on (generic.py:243) */
+    int32_t device;        /* CUDA device ordinal */
+    /* slab decomposition along x; single process: nx_global = nx, x_offset = 0 */
+    int64_t nx_global;
+    int64_t x_offset;
+    int32_t threads_2d;    /* 0 = default; threads per block of the 2D sweep kernels */
+    int32_t segment_2d;    /* 0 = default; cells marched per block along the sweep */
+    int32_t tile_1d;       /* 0 = default; cells per block of the 1D sweep kernel */
+    int32_t reserved;
+} astrea_cfg;
+
+/* sim_variables -> device context.  Stands in for the namedtuple built at astrea.py:132-133. */
+astrea_ctx* astrea_create(const astrea_cfg* cfg);
+void astrea_destroy(astrea_ctx* ctx);
+const char* astrea_last_error(const astrea_ctx* ctx);   /* ctx may be NULL: error of the last failed astrea_create */
+
+/* grid (conservative cell averages, C-order (nx[,ny],8) float64 host array; constructor.py:11-109 output,
+ * the `grid` argument of astrea.py:67) -> device. */
+int astrea_upload(astrea_ctx* ctx, const double* grid_aos);
+/* device -> host, same layout.  as_primitive != 0 applies sim_variables.convert_conservative first, i.e. what
+ * astrea.py:47 snapshots (without its transpose). */
+int astrea_download(astrea_ctx* ctx, double* grid_aos, int as_primitive);
+
+/* evolvers.evolve_space(grid, sim_variables) for the uploaded grid (astrea.py:67).  step_parity = number of
+ * permutation reversals so far mod 2 (astrea.py:85).  eigmax[a] receives fluxes[axes_a]['eigmax'] for
+ * sweep axis a = 0..dimension-1 (astrea.py:70).  Returns ASTREA_E_NONFINITE where fv.py:158 would raise. */
+int astrea_evolve_space(astrea_ctx* ctx, int step_parity, double* eigmax);
+/* evolvers.evolve_time(grid, fluxes, dt, sim_variables) (astrea.py:81): all remaining Runge-Kutta stages.  The new
+ * grid replaces the context's state. */
+int astrea_evolve_time(astrea_ctx* ctx, double dt);
+/* One pass of the loop body astrea.py:67-85: evolve_space, dt = cfl*min(dx/eigmax) (:70-71), clip so that
+ * t + dt does not pass t_stop (:74-75; pass t_stop <= t to disable), evolve_time, flip the parity. */
+int astrea_step(astrea_ctx* ctx, double t, double t_stop, double* dt_out);
+int astrea_get_parity(const astrea_ctx* ctx);
+int astrea_set_parity(astrea_ctx* ctx, int step_parity);
+
+/* magnetic_2d only: evolve_time overwrites the in-plane B of the caller's grid with face averages before the
+ * stages (evolvers.py:73-76).  Copies those two components (host array (nx,ny,2): Bx, By). */
+int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);
+
+/* ---- Step program: the spatial-operator evaluations and Runge-Kutta register updates of one time step, in the
+ * order evolvers.py:70-206 performs them.  Instruction 0 is always the operator on the current grid (what
+ * evolve_space does); astrea_evolve_time runs instructions 1..n-1.  A multi-GPU host (one process per GPU) drives
+ * the instructions itself so that it can exchange the ghost rows of the register an operator is about to read:
+ *     for i in range(astrea_program_length(ctx)):
+ *         if astrea_instr_is_operator(ctx, i): <NCCL send/recv on astrea_halo_ptrs(ctx, i, ...)>
+ *         astrea_run_instr(ctx, i, external_rows)
+ * Each halo block is ghost_rows x 8 variables x col_pitch doubles, contiguous (the [row][var][col] layout). */
+int astrea_program_length(const astrea_ctx* ctx);
+int astrea_instr_is_operator(const astrea_ctx* ctx, int instr);
+int astrea_set_dt(astrea_ctx* ctx, double dt);                 /* dt of astrea.py:70-78, read by the register updates */
+/* external_rows != 0: the caller has filled the x ghost rows (neighbour ranks); only ghost columns are filled here */
+int astrea_run_instr(astrea_ctx* ctx, int instr, int external_rows);
+int astrea_finish_step(astrea_ctx* ctx);                       /* adopt the last register as the grid, flip the parity (astrea.py:81,85) */
+int astrea_halo_info(const astrea_ctx* ctx, int64_t* ghost_rows, int64_t* doubles_per_block);
+int astrea_halo_ptrs(astrea_ctx* ctx, int instr, double** send_lo, double** send_hi, double** recv_lo, double** recv_hi);
+/* fill the ghost columns of the interior rows of the register instruction `instr` reads, so that the rows handed to
+ * the neighbours carry their corner cells; call before the exchange */
+int astrea_halo_prepare(astrea_ctx* ctx, int instr);
+/* device addresses of eigmax[2] (as written by the last operator 0) for an all-reduce(MAX) across ranks */
+int astrea_eigmax_device(astrea_ctx* ctx, double** eigmax_dev);
+int astrea_read_eigmax(astrea_ctx* ctx, double* eigmax);        /* sync + copy to host, ASTREA_E_NONFINITE as above */
+int astrea_sync(astrea_ctx* ctx);
+/* cudaStream_t of the context as an integer (for torch.cuda.ExternalStream); 0 in the host-simulated build */
+uint64_t astrea_stream_handle(const astrea_ctx* ctx);
+
+/* Number of kernels this library launched on the context's stream since creation (bench.py "gpu_launches"). */
+int64_t astrea_launch_count(const astrea_ctx* ctx);
+/* 1 when built by nvcc for sm_100a, 0 for the host-simulated test build. */
+int astrea_is_device_build(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
