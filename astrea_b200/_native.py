@@ -68,6 +68,10 @@ _SIGNATURES = {
     "astrea_sync": (C.c_int, [C.c_void_p]),
     "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
     "astrea_launch_count": (C.c_int64, [C.c_void_p]),
+    "astrea_save_state": (C.c_int, [C.c_void_p]),
+    "astrea_restore_state": (C.c_int, [C.c_void_p]),
+    "astrea_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_profile_read": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64)]),
     "astrea_is_device_build": (C.c_int, []),
 }
 EXPORTS = tuple(_SIGNATURES)
@@ -205,6 +209,21 @@ class Context:
 
     def sync(self):
         self._check(self.lib.astrea_sync(self._h))
+
+    def save_state(self):
+        self._check(self.lib.astrea_save_state(self._h))
+
+    def restore_state(self):
+        self._check(self.lib.astrea_restore_state(self._h))
+
+    def profile(self, enable=True):
+        self._check(self.lib.astrea_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} since the last read; classes: sweep, transpose, update, halo."""
+        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
+        self._check(self.lib.astrea_profile_read(self._h, ms, n))
+        return {name: (ms[k], n[k]) for k, name in enumerate(("sweep", "transpose", "update", "halo"))}
 
     @property
     def stream_handle(self):

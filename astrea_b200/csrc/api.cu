@@ -100,6 +100,14 @@ struct astrea_ctx {
     int threads2d = 0, tt2d = 0, colblocks_x = 0, colblocks_y = 0;
     int tile1d = 0, threads1d = 0;
     bool stream_owned = false;
+    Reg saved;                        // astrea_save_state copy of the grid
+    int saved_parity = 0;
+    // optional per-launch timing (astrea_profile): event pairs per kernel class
+    int profiling = 0;
+#ifdef ASTREA_DEVICE_BUILD
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+#endif
 };
 
 namespace {
@@ -108,6 +116,32 @@ int fail(astrea_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
 }
+
+enum { CLS_SWEEP = 0, CLS_TRANSPOSE = 1, CLS_UPDATE = 2, CLS_HALO = 3, CLS_COUNT = 4 };
+
+// Brackets one launch with CUDA events on the context's stream when profiling is on.
+struct Timed {
+    astrea_ctx* c;
+    Timed(astrea_ctx* ctx, int cls) : c(ctx) {
+#ifdef ASTREA_DEVICE_BUILD
+        if (c->profiling) {
+            astrea_ctx::Span sp{cls, nullptr, nullptr};
+            cudaEventCreate(&sp.a);
+            cudaEventCreate(&sp.b);
+            cudaEventRecord(sp.a, c->st.s);
+            c->spans.push_back(sp);
+        }
+#else
+        (void)cls;
+#endif
+    }
+    ~Timed() {
+#ifdef ASTREA_DEVICE_BUILD
+        if (c->profiling) cudaEventRecord(c->spans.back().b, c->st.s);
+#endif
+        c->launches++;
+    }
+};
 
 #ifdef ASTREA_DEVICE_BUILD
 std::string cuda_text(int e) { return std::string(cudaGetErrorString((cudaError_t)e)); }
@@ -254,8 +288,7 @@ void build_program(int integrator, std::vector<Instr>& p, int& nregs, int& nrate
 // ---------------------------------------------------------------------------------------- launches
 int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
     HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1};
-    ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st));
-    c->launches++;
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     if (c->ghost_r > 0) {
         h.phase = 1;
         // interior slab edges are provided by the neighbour ranks; a physical 'edge' boundary is always local
@@ -267,8 +300,7 @@ int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
         }
         if (h.fill_lo || h.fill_hi) {
             const int gx = (int)((c->ncol + 2 * GHOST + 255) / 256);
-            ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st));
-            c->launches++;
+            { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st)); }
         }
     }
     return 0;
@@ -285,8 +317,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
         p.q = q; p.d = c->d0.plane; p.n = g.ny; p.gamma = g.gamma; p.dx = g.dx;
         p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach; p.tile = c->tile1d;
         p.eigmax_bits = eig; p.flag = c->flag;
-        ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st));
-        c->launches++;
+        { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st)); }
     } else {
         // sweep order and the solver's private axis counter (solvers.py:34-36,63; astrea.py:85)
         const int order[2] = {c->parity ? 1 : 0, c->parity ? 0 : 1};
@@ -294,8 +325,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
         TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST};
         {
             const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
-            ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st));
-            c->launches++;
+            { Timed timed(c, CLS_TRANSPOSE); ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st)); }
         }
         for (int k = 0; k < 2; ++k) {
             const int ax = order[k], sax = k;
@@ -329,8 +359,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 seg = std::max(seg, 32);
             }
             p.seg = (int)std::min<int64_t>(seg, p.ns);
-            ASTREA_TRY(launch_sweep2d(g.scheme, g.solver, ax, sax, p, nthreads, c->st));
-            c->launches++;
+            { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep2d(g.scheme, g.solver, ax, sax, p, nthreads, c->st)); }
         }
     }
     RateParams r{};
@@ -338,8 +367,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = nullptr; r.emf_pitch = 0; r.dx = g.dx; r.bc = g.boundary;
     {
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
-        ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st));
-        c->launches++;
+        { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st)); }
     }
     return 0;
 }
@@ -359,8 +387,7 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
     p.dt = c->dt_dev;
     p.nrow = c->nrow; p.ncol = c->ncol;
     const int gx = (int)((c->ncol + 255) / 256);
-    ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st));
-    c->launches++;
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st)); }
     return 0;
 }
 
@@ -467,7 +494,7 @@ void astrea_destroy(astrea_ctx* c) {
     for (auto& r : c->regs) dev_free(r.mem);
     for (auto& r : c->rates) dev_free(r.mem);
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
-    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev);
+    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->stream_owned) cudaStreamDestroy(c->st.s);
 #endif
@@ -482,8 +509,7 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     double* staging = c->d0.mem;     // d0 is scratch between operator evaluations
     ASTREA_TRY(copy_h2d(staging, grid_aos, bytes, c->st));
     PackParams p{c->regs[c->grid_reg].plane, staging, c->nrow, c->ncol, 1};
-    ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
-    c->launches++;
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     c->next_instr = 0;
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_upload: stream sync failed");
 }
@@ -498,15 +524,13 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
         if (int e = fill_halo(c, src, 0)) return e;
         Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r);
         PrimParams pp{src, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
-        ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
-        c->launches++;
+        { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
         src = w;
     }
     const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
     double* staging = c->d0.mem;
     PackParams p{src, staging, c->nrow, c->ncol, 0};
-    ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
-    c->launches++;
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     ASTREA_TRY(copy_d2h(grid_aos, staging, bytes, c->st));
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_download: stream sync failed");
 }
@@ -625,8 +649,7 @@ int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, d
 int astrea_halo_prepare(astrea_ctx* c, int i) {
     if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: not an operator instruction");
     HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0};
-    ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st));
-    c->launches++;
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     return 0;
 }
 
@@ -651,6 +674,49 @@ uint64_t astrea_stream_handle(const astrea_ctx* c) {
 }
 
 int64_t astrea_launch_count(const astrea_ctx* c) { return c ? c->launches : 0; }
+
+int astrea_save_state(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_save_state: a step is in flight");
+    if (!c->saved.mem && !alloc_reg(c, c->saved, c->ncol)) return fail(c, ASTREA_E_CUDA, "astrea_save_state: device allocation failed");
+    ASTREA_TRY(copy_d2d(c->saved.mem, c->regs[c->grid_reg].mem, c->plane_doubles * sizeof(double), c->st));
+    c->saved_parity = c->parity;
+    return 0;
+}
+
+int astrea_restore_state(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    if (!c->saved.mem) return fail(c, ASTREA_E_STATE, "astrea_restore_state: nothing saved");
+    ASTREA_TRY(copy_d2d(c->regs[c->grid_reg].mem, c->saved.mem, c->plane_doubles * sizeof(double), c->st));
+    ASTREA_TRY(dev_zero(c->flag, sizeof(int), c->st));
+    c->parity = c->saved_parity;
+    c->next_instr = 0;
+    return 0;
+}
+
+int astrea_profile(astrea_ctx* c, int enable) {
+    if (!c) return ASTREA_E_ARG;
+    c->profiling = enable ? 1 : 0;
+    return 0;
+}
+
+int astrea_profile_read(astrea_ctx* c, double* ms_by_class, int64_t* launches_by_class) {
+    if (!c || !ms_by_class || !launches_by_class) return fail(c, ASTREA_E_ARG, "astrea_profile_read: NULL argument");
+    for (int k = 0; k < CLS_COUNT; ++k) { ms_by_class[k] = 0.0; launches_by_class[k] = 0; }
+#ifdef ASTREA_DEVICE_BUILD
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_profile_read: stream sync failed");
+    for (auto& sp : c->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        ms_by_class[sp.cls] += ms;
+        launches_by_class[sp.cls] += 1;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    c->spans.clear();
+#endif
+    return 0;
+}
 
 int astrea_is_device_build(void) {
 #ifdef ASTREA_DEVICE_BUILD

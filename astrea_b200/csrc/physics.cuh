@@ -57,7 +57,14 @@ HD void mean_state(const double* a, const double* b, double* out) {   // plm.py:
     for (int v = 0; v < NVAR; ++v) out[v] = 0.5 * (a[v] + b[v]);
 }
 
-// max |lambda| of the primitive Jacobian at state w along AX: |v_n| + fast magnetosonic speed.
+// max |lambda| of the primitive Jacobian (constructor.py:129-163) at state w along AX, in closed form.
+// The spectrum is {0, v, v +- sqrt(x)} for x in {c_a^2, c_f^2, c_s^2}, with c_a^2 = Bn^2/rho and c_f^2, c_s^2 the
+// roots of x^2 - (a^2 + b^2) x + a^2 c_a^2.  For a physical state all x >= 0 and the maximum is |v| + c_f.  The
+// reference feeds unphysical reconstructed states (negative pressure) to np.linalg.eigvals as they are; a root
+// x < 0 then gives the complex pair v +- i sqrt(-x) of modulus sqrt(v^2 - x), which is what np.abs returns
+// (fv.py:157-162), so those branches are kept.
+HD double wave_modulus(double vn, double x) { return x >= 0.0 ? vn + sqrt(x) : sqrt(vn * vn + (-x)); }
+
 template <int AX>
 HD double spectral_radius(const double* w, double gamma) {
     const double rho = w[0];
@@ -65,8 +72,21 @@ HD double spectral_radius(const double* w, double gamma) {
     const double b2 = ((w[5] * w[5] + w[6] * w[6]) + w[7] * w[7]) / rho;
     const double bn2 = w[5 + AX] * w[5 + AX] / rho;
     const double s = a2 + b2;
-    const double cf = sqrt(0.5 * (s + sqrt(s * s - 4.0 * (a2 * bn2))));
-    return fabs(w[1 + AX]) + cf;
+    const double disc = s * s - 4.0 * (a2 * bn2);
+    const double vn = fabs(w[1 + AX]);
+    if (disc >= 0.0) {
+        const double root = sqrt(disc);
+        const double cf2 = 0.5 * (s + root), cs2 = 0.5 * (s - root);
+        if (cs2 >= 0.0 && bn2 >= 0.0) return vn + sqrt(cf2);
+        return npmax(npmax(wave_modulus(vn, cf2), wave_modulus(vn, cs2)), wave_modulus(vn, bn2));
+    }
+    if (disc < 0.0) {   // complex conjugate roots x = p +- iq (needs rho < 0)
+        const double p = 0.5 * s, q = 0.5 * sqrt(-disc);
+        const double m = sqrt(p * p + q * q);
+        const double al = sqrt(0.5 * (m + p)), be = sqrt(0.5 * (m - p));
+        return npmax(sqrt((vn + al) * (vn + al) + be * be), wave_modulus(vn, bn2));
+    }
+    return disc;        // NaN
 }
 
 }  // namespace astrea

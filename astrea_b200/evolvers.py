@@ -68,11 +68,11 @@ def evolve_space(grid, sim_variables, device=0, _lib=None):
     return fluxes
 
 
-def evolve_time(grid, fluxes, dt, sim_variables, device=0, _lib=None):
+def evolve_time(grid, fluxes, dt, sim_variables, device=0, _lib=None, out=None):
     ctx = _context(sim_variables, device, _lib)
     handle = next(iter(fluxes.values()))["flux"]
     if not isinstance(handle, DeviceFlux) or handle.ctx is not ctx or handle.token != ctx._token:
         raise ValueError("evolve_time: `fluxes` must come from the latest evolve_space call on this grid")
     ctx.evolve_time(dt)
-    out = ctx.download()
+    out = ctx.download(out=out)      # `out`: optional preallocated (e.g. pinned) host array for the new grid
     return out.reshape(np.shape(grid))

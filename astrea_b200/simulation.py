@@ -1,0 +1,188 @@
+"""Device-resident time loop: the body of ``core_run`` (astrea.py:31-85) with the grid kept in HBM.
+
+Single GPU: every step is ``astrea_step`` (operator, dt = cfl*min(dx/eigmax), Runge-Kutta stages, parity flip).
+
+Several GPUs (one process per GPU, ``torch.distributed``): the grid is cut into slabs along x.
+The host walks the step program of the context; before each spatial-operator evaluation it exchanges GHOST
+ghost rows of the register that operator reads with the two neighbouring ranks (NCCL send/recv on the context's
+stream; the ring closes for periodic boundaries, a physical 'edge' boundary is filled locally), and after the
+first operator it all-reduces (MAX) the two per-axis wave speeds so that every rank takes the same dt
+(astrea.py:70-71).  No other collective is on the path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+from .initial import initial_slab, initial_state, problem
+from .selectors import MAGNETIC_2D, make_cfg, scheme_enum, stages_of
+
+
+class _CudaBlock:
+    """A raw device address as something torch can wrap (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def _tensor_at(ptr, count, on_device, device_index=0):
+    import torch
+    if on_device:
+        return torch.as_tensor(_CudaBlock(ptr, count), device=torch.device("cuda", device_index))
+    buf = (ctypes.c_double * count).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+
+
+class SlabExchange:
+    """Halo rows and the wave-speed reduction of one rank, over ``torch.distributed`` (nccl on GPUs, gloo in tests)."""
+
+    def __init__(self, ctx, rank, world, periodic, on_device, device_index=0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.ctx, self.rank, self.world, self.periodic = ctx, rank, world, periodic
+        self.on_device, self.device_index = on_device, device_index
+        self.rows, self.count = ctx.halo_info()
+        self.lo = (rank - 1) % world if (periodic or rank > 0) else None
+        self.hi = (rank + 1) % world if (periodic or rank < world - 1) else None
+        self._views = {}
+        self.stream = torch.cuda.ExternalStream(ctx.stream_handle, device=device_index) if on_device else None
+
+    def _blocks(self, instr):
+        if instr not in self._views:
+            self._views[instr] = [_tensor_at(p, self.count, self.on_device, self.device_index) for p in self.ctx.halo_ptrs(instr)]
+        return self._views[instr]
+
+    def halo(self, instr):
+        dist = self.dist
+        send_lo, send_hi, recv_lo, recv_hi = self._blocks(instr)
+        self.ctx.halo_prepare(instr)
+        def op(kind, block, peer, tag):
+            return dist.P2POp(kind, block, peer) if self.on_device else dist.P2POp(kind, block, peer, tag=tag)
+
+        # order matters when both neighbours are the same peer (world == 2): the first message travels "upwards"
+        ops = []
+        if self.hi is not None:
+            ops.append(op(dist.isend, send_hi, self.hi, 0))
+        if self.lo is not None:
+            ops.append(op(dist.isend, send_lo, self.lo, 1))
+        if self.lo is not None:
+            ops.append(op(dist.irecv, recv_lo, self.lo, 0))
+        if self.hi is not None:
+            ops.append(op(dist.irecv, recv_hi, self.hi, 1))
+        if not ops:
+            return
+        if self.on_device:
+            with self.torch.cuda.stream(self.stream):
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            self.ctx.sync()
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def global_eigmax(self):
+        """The per-axis wave speeds of operator 0, maximised over the ranks, plus the "non-finite seen" flag OR-ed
+        over the ranks so that every rank raises together where the reference raises."""
+        torch, dist = self.torch, self.dist
+        try:
+            vals, bad = self.ctx.read_eigmax(), 0.0
+        except N.NonFiniteError:
+            vals, bad = [0.0, 0.0], 1.0
+        dev = torch.device("cuda", self.device_index) if self.on_device else torch.device("cpu")
+        t = torch.tensor(list(vals) + [bad], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e0, e1, bad = t.tolist()
+        if bad:
+            raise N.NonFiniteError(N.E_NONFINITE, "non-finite wave speed on some rank (the reference raises LinAlgError, fv.py:158)")
+        return [e0, e1]
+
+
+class Simulation:
+    """One run of the reference's time loop on the device(s).
+
+    ``config`` / ``cells`` / ``subgrid`` / ``solver`` / ``timestep`` / ``cfl`` / ``gamma`` have the meaning of the
+    reference's parameters.yml keys (static/.default.yml).  With ``world > 1`` this rank holds ``cells_x`` rows
+    starting at ``rank * cells_x`` of a global ``(world * cells_x) x cells`` grid.
+    """
+
+    def __init__(self, config, cells, dimension, subgrid, solver, timestep, cfl=0.5, gamma=1.4, device=0, boundary=None,
+                 rank=0, world=1, cells_x=None, grid=None, _lib=None, **geometry):
+        self.config, self.cells, self.dimension = config.lower(), int(cells), int(dimension)
+        prob = problem(self.config, self.cells, gamma)
+        self.boundary = boundary or prob["boundary"]
+        self.dx, self.t_end = prob["dx"], prob["t_end"]
+        self.cfl, self.gamma = cfl, gamma
+        self.rank, self.world = rank, world
+        self.high_order = scheme_enum(subgrid) >= N.PPM
+        self.magnetic_2d = self.config in MAGNETIC_2D
+        nx = self.cells if cells_x is None else int(cells_x)
+        if world > 1 and dimension != 2:
+            raise ValueError("only 2D grids are decomposed")
+        self.nx_local, self.nx_global, self.x_offset = nx, nx * world, rank * nx
+        self.cfg = make_cfg(dimension=dimension, nx=nx, ny=self.cells, boundary=self.boundary, gamma=gamma, dx=self.dx, cfl=cfl,
+                            subgrid=subgrid, solver=solver, timestep=timestep, magnetic_2d=self.magnetic_2d, device=device,
+                            nx_global=self.nx_global, x_offset=self.x_offset, **geometry)
+        self.ctx = N.Context(self.cfg, lib=_lib)
+        self.stages = stages_of(self.cfg.integrator)
+        self.on_device = self.ctx.lib.astrea_is_device_build() == 1
+        self.exchange = SlabExchange(self.ctx, rank, world, self.boundary == "wrap", self.on_device, device) if world > 1 else None
+        self.t, self.steps_done = 0.0, 0
+        self._program = self.ctx.program()
+        if grid is None:
+            grid = self.initial_grid()
+        self.ctx.upload(grid)
+
+    def initial_grid(self):
+        """constructor.initialise(sim_variables, convert=True) for this rank's rows."""
+        if self.dimension == 2 and (self.nx_local != self.cells or self.world > 1):
+            return initial_slab(self.config, self.nx_local, self.cells, self.x_offset, self.nx_global, self.gamma, self.high_order)
+        return initial_state(self.config, self.cells, self.dimension, self.gamma, self.high_order, boundary=self.boundary)
+
+    def step(self, t_stop=None):
+        """One pass of astrea.py:67-85.  Returns dt."""
+        stop = self.t - 1.0 if t_stop is None else t_stop
+        if self.exchange is None:
+            dt = self.ctx.step(self.t, stop)
+        else:
+            dt = None
+            for i, is_operator in enumerate(self._program):
+                if is_operator:
+                    self.exchange.halo(i)
+                    self.ctx.run_instr(i, external_rows=True)
+                    if i == 0:
+                        eig = self.exchange.global_eigmax()
+                        dt = self.cfl * min(self.dx / e for e in eig)
+                        if stop > self.t and self.t + dt >= stop:
+                            dt = stop - self.t
+                        self.ctx.set_dt(dt)
+                else:
+                    self.ctx.run_instr(i)
+            self.ctx.finish_step()
+        self.t += dt
+        self.steps_done += 1
+        return dt
+
+    def check_finite(self):
+        """Raise NonFiniteError (a LinAlgError) on every rank if any Runge-Kutta stage so far saw a non-finite wave
+        speed — the reference raises inside evolve_time at that stage (fv.py:158)."""
+        if self.exchange is not None:
+            self.exchange.global_eigmax()
+        else:
+            self.ctx.read_eigmax()
+
+    def run(self, nsteps):
+        return [self.step() for _ in range(nsteps)]
+
+    def state(self, primitive=False):
+        """This rank's rows as the reference's ndarray (conservative averages, or the astrea.py:47 primitive snapshot)."""
+        if primitive and self.exchange is not None and self.high_order:
+            raise NotImplementedError("primitive snapshots of a decomposed 4th-order run: gather the conservative state instead")
+        return self.ctx.download(primitive=primitive)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the per-timestep finite-volume update (BASELINE.json metric: cell-updates/s, fp64, per RK step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|c1]
+
+A "step" is one full Runge-Kutta step (all stages) of every cell of the workload.  Default workload (N=1) is
+BASELINE config 2: Lax-Liu 3, 2048^2, PPM + HLLC, SSPRK(3,3), periodic.  With N > 1 (torchrun, one rank per GPU)
+every rank holds a slab of the same size (weak scaling) of a global (N*2048) x 2048 periodic grid; ranks exchange
+ghost rows over NCCL before every spatial operator and all-reduce the wave speeds once per step.
+
+The reference's own run of this configuration stops with LinAlgError after a few steps (the horizon
+is re-measured here at run time), so the timed loop returns to the initial state every `horizon` steps with a
+device-to-device copy that is inside the timed region.
+
+`--impl reference` times the CPU implementation of the same path (the numpy oracle, a restatement pinned bit for
+bit to the reference; the reference itself does not exist on the GPU box) on all host cores as independent
+single-threaded replicas, on a bounded sample (the reference is single-threaded and cannot hold 2048^2 in memory).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config, cells per GPU side, dimension, subgrid, solver, timestep, description)
+    "c1": ("sod", 1024, 1, "plm", "lf", "ssprk(2,2)", "1D Sod 1024 PLM+minmod+LLF SSPRK(2,2) edge"),
+    "c2": ("ll3", 2048, 2, "ppm", "hllc", "ssprk(3,3)", "2D Lax-Liu 3 2048^2 PPM+HLLC SSPRK(3,3) periodic"),
+    "c3": ("khi", 4096, 2, "weno5", "hllc", "ssprk(3,3)", "2D Kelvin-Helmholtz 4096^2 WENO5+HLLC SSPRK(3,3) periodic"),
+    "c5": ("ll6", 8192, 2, "ppm", "hllc", "ssprk(3,3)", "2D Lax-Liu 6 8192^2 per GPU PPM+HLLC SSPRK(3,3) periodic"),
+}
+MAX_HORIZON = 8
+
+
+def alg_bytes_per_cell_update(stages):
+    """64 B of state per cell; stage 1 reads u and writes k, later stages read u, k and write k'."""
+    return 64 * (2 + 3 * (stages - 1))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _oracle_sample(args):
+    """One bounded sample on one core: `steps` full RK steps of the workload's scheme on a cells^2 (or cells) grid."""
+    config, cells, dim, subgrid, solver, timestep, steps, eigen = args
+    from astrea_b200.initial import initial_state, problem
+    from oracle import OracleConfig, advance
+    prob = problem(config, cells, 1.4)
+    cfg = OracleConfig(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
+                       boundary=prob["boundary"], dx=prob["dx"], eigen=eigen)
+    g0 = initial_state(config, cells, dim, 1.4, cfg.high_order)
+    t0 = time.perf_counter()
+    g, dts = advance(g0, cfg, steps)
+    return time.perf_counter() - t0, bool(np.isfinite(g).all())
+
+
+def cpu_sample_spec(workload, cells):
+    config, _, dim, subgrid, solver, timestep, _ = WORKLOADS[workload]
+    steps = 2 if dim == 2 else 200
+    return (config, cells, dim, subgrid, solver, timestep, steps, "lapack")
+
+
+def run_reference_arm(a):
+    """The CPU implementation of the path on all host cores (independent single-threaded replicas)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    config, _, dim, subgrid, solver, timestep, desc = WORKLOADS[a.workload]
+    cells = 128 if dim == 2 else 1024
+    spec = cpu_sample_spec(a.workload, cells)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cells_per_sample = cells ** dim * spec[6]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(a.warmup):
+            pool.map(_oracle_sample, [spec] * cores)
+        times = []
+        for _ in range(a.steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_sample, [spec] * cores)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = cores * cells_per_sample * a.steps / total
+    sample = (f"{cores} replicas x ({config} {cells}{'^2' if dim == 2 else ''} {subgrid}+{solver} {timestep}, {spec[6]} RK steps) per bench step; "
+              "numpy oracle pinned bit-for-bit to the reference (np.linalg.eigvals wave speeds)")
+    line = {"impl": "reference", "metric": "cell-updates/sec (fp64, per RK step)", "value": value, "unit": "cell-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "cpu_sample_cells": cells, "note": "reference numpy path is single-threaded; all cores used as replicas"},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from astrea_b200 import _native as N
+    from astrea_b200 import evolvers
+    from astrea_b200.simulation import Simulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU), see the module docstring")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N.device_library()       # fail loudly if the CUDA library is missing
+
+    config, cells, dim, subgrid, solver, timestep, desc = WORKLOADS[a.workload]
+    if a.cells:
+        cells = a.cells
+    from astrea_b200.selectors import integrator_enum, stages_of
+    stages = stages_of(integrator_enum(timestep))
+    geometry = {}
+    if a.threads_2d:
+        geometry["threads_2d"] = a.threads_2d
+    if a.segment_2d:
+        geometry["segment_2d"] = a.segment_2d
+    sim = Simulation(config, cells, dim, subgrid, solver, timestep, device=local, rank=rank, world=world,
+                     cells_x=cells if dim == 2 else None, **geometry)
+    ctx = sim.ctx
+    stream = torch.cuda.ExternalStream(ctx.stream_handle, device=local)
+    cells_per_rank = cells ** dim
+    ctx.save_state()
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # finite horizon of this configuration (the reference raises LinAlgError beyond it)
+    horizon = 0
+    try:
+        for _ in range(MAX_HORIZON):
+            sim.step()
+            sim.check_finite()       # a non-finite wave speed in any stage ends the reference's run (fv.py:158)
+            horizon += 1
+    except np.linalg.LinAlgError:
+        pass
+    if world > 1:
+        h = torch.tensor([horizon], device=f"cuda:{local}")
+        dist.all_reduce(h, op=dist.ReduceOp.MIN)
+        horizon = int(h.item())
+    if horizon == 0:
+        raise SystemExit("the workload produces non-finite wave speeds in its first step")
+    ctx.restore_state()
+
+    def run_steps(n):
+        for k in range(n):
+            if k % horizon == 0:
+                ctx.restore_state()
+            sim.step()
+
+    run_steps(a.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_steps(a.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * cells_per_rank * a.steps / (ms * 1e-3)
+
+    # per-kernel-class device time of `horizon` steps (CUDA events around every launch, on the launching stream)
+    ctx.restore_state()
+    ctx.profile(True)
+    for _ in range(horizon):
+        sim.step()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    total_ms = sum(v[0] for v in prof.values())
+    sweep_ms, sweep_n = prof["sweep"]
+    peak, peak_src = load_peaks()
+    alg = alg_bytes_per_cell_update(stages)
+    sweeps_per_step = stages * dim
+    bytes_per_sweep_launch = cells_per_rank * alg / sweeps_per_step
+    sweep_avg_ms = sweep_ms / max(1, sweep_n)
+    achieved = bytes_per_sweep_launch / (sweep_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "Sweep2D" if dim == 2 else "Sweep1D",
+                "alg_bytes_per_cell_update": alg, "alg_bytes_per_launch": bytes_per_sweep_launch,
+                "kernel_avg_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
+                "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
+                "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            tr = json.load(fh).get(a.workload)
+        if tr:
+            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tr.get("source")
+
+    # end to end through the reference-facing calls, host buffers in and out every step
+    e2e = measure_e2e(a, sim, horizon, world, rank, local, stream, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        spec = cpu_sample_spec(a.workload, 256 if dim == 2 else 1024)
+        secs, finite = _oracle_sample(spec)
+        n = spec[1] ** dim * spec[6]
+        cpu = {"value": n / secs, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+               "sample": f"{spec[0]} {spec[1]}{'^2' if dim == 2 else ''} {spec[3]}+{spec[4]} {spec[5]}, {spec[6]} RK steps, {secs:.1f} s, "
+                         "numpy oracle (bit-identical to the reference, single-threaded like it)"}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/sec (fp64, per RK step)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc if not a.cells else desc + f" (cells overridden: {cells})", "cells_per_gpu": cells_per_rank,
+                           "global_cells": world * cells_per_rank, "stages_per_step": stages, "decomposition": f"x-slabs x{world}",
+                           "finite_horizon_steps": horizon,
+                           "l2": "state per register (%.0f MB) exceeds the 126 MB L2" % (cells_per_rank * 64 / 1e6)
+                                 if cells_per_rank * 64 > 126e6 else "working set fits L2 (small workload)",
+                           "restore": f"device-to-device return to the initial state every {horizon} steps, inside the timed region"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    sim.close()
+    evolvers.release()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
+    """Same metric with the grid crossing the host/device boundary every step: pinned host array in, host array out.
+    N = 1: the drop-in pair evolvers.evolve_space / evolve_time (astrea.py:67,81).  N > 1: upload / step / download of
+    each rank's slab."""
+    import torch
+    import torch.distributed as dist
+    from collections import namedtuple
+    from astrea_b200 import evolvers
+    ctx = sim.ctx
+    shape = tuple(ctx.shape)
+    ic = torch.empty(shape, dtype=torch.float64).pin_memory()
+    out = torch.empty(shape, dtype=torch.float64).pin_memory()
+    ctx.restore_state()
+    ic_np, out_np = ic.numpy(), out.numpy()
+    ctx.download(out=ic_np)
+    nbytes = ic_np.nbytes
+    steps = max(horizon, min(a.steps, 2 * horizon))
+    if world == 1:
+        SV = namedtuple("simulation_variables", "dimension cells boundary gamma dx cfl subgrid solver solver_category timestep magnetic_2d permutations")
+        config, cells, dim, subgrid, solver, timestep, _ = WORKLOADS[a.workload]
+        cells = a.cells or cells
+        perms = {0: (0, 1)} if dim == 1 else {0: (0, 1, 2), 1: (1, 0, 2)}
+        sv0 = SV(dim, cells, sim.boundary, sim.gamma, sim.dx, sim.cfl, subgrid, solver, "hll" if solver.startswith("hll") else "lax",
+                 timestep, False, perms)
+
+        def one_pass():
+            sv, grid = sv0, ic_np
+            for n in range(steps):
+                if n % horizon == 0:
+                    sv, grid = sv0, ic_np
+                fluxes = evolvers.evolve_space(grid, sv, device=local)
+                dt = sv.cfl * min(sv.dx / f["eigmax"] for f in fluxes.values())
+                grid = evolvers.evolve_time(grid, fluxes, dt, sv, device=local, out=out_np)
+                sv = sv._replace(permutations=dict(reversed(list(sv.permutations.items()))))
+        one_pass()                      # warm-up (creates the context)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one_pass()
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+    else:
+        def one_pass():
+            for n in range(steps):
+                if n % horizon == 0:
+                    ctx.upload_ptr(ic_np.ctypes.data)
+                    ctx.parity = 0
+                else:
+                    ctx.upload_ptr(out_np.ctypes.data)
+                sim.step()
+                ctx.download_ptr(out_np.ctypes.data)
+        one_pass()
+        barrier()
+        t0 = time.perf_counter()
+        one_pass()
+        barrier()
+        secs = time.perf_counter() - t0
+        t = torch.tensor([secs], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    cells_per_rank = int(np.prod(shape[:-1]))
+    return {"value": world * cells_per_rank * steps / secs, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "steps": steps, "api": "evolvers.evolve_space + evolvers.evolve_time (numpy in / numpy out)" if world == 1
+            else "Context.upload + Simulation.step + Context.download per rank", "timer": "host wall clock around synchronised calls"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--cells", type=int, default=0, help="override the cells per side (per GPU)")
+    ap.add_argument("--threads-2d", type=int, default=0)
+    ap.add_argument("--segment-2d", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

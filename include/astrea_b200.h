@@ -119,6 +119,17 @@ int astrea_sync(astrea_ctx* ctx);
 /* cudaStream_t of the context as an integer (for torch.cuda.ExternalStream); 0 in the host-simulated build */
 uint64_t astrea_stream_handle(const astrea_ctx* ctx);
 
+/* Device-side copy of the current grid (and step parity) and its restoration: lets a host loop return to a known
+ * state without a host round trip (the reference re-runs constructor.initialise, astrea.py:35). */
+int astrea_save_state(astrea_ctx* ctx);
+int astrea_restore_state(astrea_ctx* ctx);
+
+/* Per-launch timing with CUDA events on the context's stream, summed per kernel class:
+ * 0 = sweep kernels, 1 = transpose, 2 = rate assembly + Runge-Kutta update, 3 = halo fill / pack / unpack.
+ * astrea_profile_read synchronises, returns the sums since the last read (arrays of 4) and clears them. */
+int astrea_profile(astrea_ctx* ctx, int enable);
+int astrea_profile_read(astrea_ctx* ctx, double* ms_by_class, int64_t* launches_by_class);
+
 /* Number of kernels this library launched on the context's stream since creation (bench.py "gpu_launches"). */
 int64_t astrea_launch_count(const astrea_ctx* ctx);
 /* 1 when built by nvcc for sm_100a, 0 for the host-simulated test build. */

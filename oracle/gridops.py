@@ -178,23 +178,41 @@ def primitive_jacobian(w, gamma, axis):
     return A
 
 
-def fast_speed(w, gamma, axis):
-    """Closed form of max|eig(primitive_jacobian)| - |v_n| : the fast magnetosonic speed.
+def closed_spectral_radius(w, gamma, axis):
+    """max|eig(primitive_jacobian)| in closed form (what the device computes instead of calling LAPACK).
 
-    The spectrum of constructor.py:129-163 is {0, v, v±c_a, v±c_s, v±c_f}, so
-    ``max|lambda| = |v_n| + c_f``; BASELINE.md §3 records agreement with LAPACK to 5.6e-15.
+    The spectrum of constructor.py:129-163 is {0, v, v +- sqrt(x)} for x in {c_a^2, c_f^2, c_s^2}.
+    For physical states that is ``|v_n| + c_f`` (agrees with LAPACK to 5.6e-15).  Unphysical
+    reconstructed states (negative pressure) give x < 0, i.e. the complex pair v +- i sqrt(-x) whose modulus
+    sqrt(v^2 - x) is what np.abs(np.linalg.eigvals(..)) returns at fv.py:157-162.
     """
-    rho, P, B = w[..., 0], w[..., 4], w[..., 5:8]
-    a2 = gamma * P / rho
-    b2 = ((B[..., 0] * B[..., 0] + B[..., 1] * B[..., 1]) + B[..., 2] * B[..., 2]) / rho
-    bn2 = B[..., axis] * B[..., axis] / rho
-    s = a2 + b2
-    return np.sqrt(.5 * (s + np.sqrt(s * s - 4 * (a2 * bn2))))
+    with np.errstate(all="ignore"):
+        rho, P, B = w[..., 0], w[..., 4], w[..., 5:8]
+        a2 = gamma * P / rho
+        b2 = ((B[..., 0] * B[..., 0] + B[..., 1] * B[..., 1]) + B[..., 2] * B[..., 2]) / rho
+        bn2 = B[..., axis] * B[..., axis] / rho
+        s = a2 + b2
+        disc = s * s - 4 * (a2 * bn2)
+        vn = np.abs(w[..., axis + 1])
+
+        def modulus(x):
+            return np.where(x >= 0, vn + np.sqrt(np.abs(x)), np.sqrt(vn * vn + (-x)))
+
+        root = np.sqrt(np.abs(disc))
+        cf2, cs2 = .5 * (s + root), .5 * (s - root)
+        physical = vn + np.sqrt(np.abs(cf2))
+        real_roots = np.maximum(np.maximum(modulus(cf2), modulus(cs2)), modulus(bn2))
+        p, q = .5 * s, .5 * np.sqrt(np.abs(disc))
+        m = np.sqrt(p * p + q * q)
+        al, be = np.sqrt(np.abs(.5 * (m + p))), np.sqrt(np.abs(.5 * (m - p)))
+        complex_roots = np.maximum(np.sqrt((vn + al) * (vn + al) + be * be), modulus(bn2))
+        return np.where(disc >= 0, np.where((cs2 >= 0) & (bn2 >= 0), physical, real_roots),
+                        np.where(disc < 0, complex_roots, disc))
 
 
 def spectral_radius(w, cfg, axis):
     """fv.py:157-162 — per point max|lambda| of the primitive Jacobian (+ the raw spectrum for Lax-Wendroff)."""
     if cfg.eigen == "closed":
-        return None, np.abs(w[..., axis]) * 0 + (np.abs(w[..., axis + 1]) + fast_speed(w, cfg.gamma, axis))
+        return None, closed_spectral_radius(w, cfg.gamma, axis)
     spectrum = np.linalg.eigvals(primitive_jacobian(w, cfg.gamma, axis))
     return spectrum, np.max(np.abs(spectrum), axis=-1)

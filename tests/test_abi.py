@@ -1,0 +1,57 @@
+"""The C-ABI shared library: builds for sm_100a, loads without a GPU, exports what include/astrea_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, _has_gpu
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "astrea_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(astrea_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from astrea_b200 import _native
+    assert _declared() == sorted(_native.EXPORTS)
+
+
+def test_device_library_exports_every_symbol(device_lib_path):
+    lib = ctypes.CDLL(device_lib_path)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    lib.astrea_is_device_build.restype = ctypes.c_int
+    assert lib.astrea_is_device_build() == 1
+
+
+def test_device_library_contains_sm100a_code(device_lib_path):
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", device_lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_hostsim_library_is_not_a_device_build(hostsim_lib):
+    assert hostsim_lib.astrea_is_device_build() == 0
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the failure mode on a machine without a GPU")
+def test_no_cpu_fallback_without_gpu(device_lib_path):
+    """Without a CUDA device the product library refuses to create a context (there is no CPU path)."""
+    from astrea_b200 import _native as N
+    from astrea_b200.selectors import make_cfg
+    cfg = make_cfg(dimension=1, cells=64, boundary="edge", gamma=1.4, dx=1 / 64, cfl=.5, subgrid="plm", solver="lf",
+                   timestep="ssprk(2,2)")
+    with pytest.raises(N.AstreaError) as err:
+        N.Context(cfg)
+    assert "CUDA" in str(err.value)
+
+
+def test_package_refuses_non_device_library(monkeypatch, hostsim_lib):
+    from astrea_b200 import _native as N, build
+    monkeypatch.setattr(N, "DEVICE_LIB", build.HOSTSIM_LIB)
+    monkeypatch.setattr(N, "_device_lib", None)
+    with pytest.raises(ImportError):
+        N.device_library()

@@ -1,0 +1,202 @@
+"""Parity of the sm_100a library with the oracle and the reference's golden vectors, through the C ABI, on a B200.
+
+Tolerances (north star): 1e-12 relative L1 per variable after one step, 1e-10 after N steps.  The device arithmetic
+is compiled without FMA contraction and with IEEE division / square root, so the comparison with the closed-form
+oracle is expected to be bit-exact; the assertion is the north-star tolerance, the bit-equality is reported.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_case, golden_index, rel_l1
+from cases import run_native, run_oracle
+from astrea_b200.initial import initial_state, problem
+
+pytestmark = pytest.mark.gpu
+HYDRO = sorted(c for c, m in golden_index().items() if not m["magnetic_2d"])
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from astrea_b200 import _native
+    return _native.device_library()      # raises if the CUDA library is missing: there is no fallback
+
+
+@pytest.mark.parametrize("cid", HYDRO)
+def test_golden_vs_reference_output(lib, cid):
+    meta, data = golden_case(cid)
+    got, _, eigs = run_native(lib, meta, data["g0"], meta["steps"], dts=list(data["dts"]))
+    tol = 1e-10 if (meta["steps"] > 1 or "weno7" in cid) else 1e-12
+    assert np.all(rel_l1(got, data["g"]) <= tol), rel_l1(got, data["g"])
+    for n, e in enumerate(eigs):
+        ref = list(data["eigmax"][n])
+        ref = ref[::-1] if (n % 2 and meta["dimension"] == 2) else ref
+        assert np.allclose(e, ref, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("cid", HYDRO)
+def test_golden_single_step_vs_oracle(lib, cid):
+    meta, data = golden_case(cid)
+    want, dts = run_oracle(meta, data["g0"], 1)
+    got, used, _ = run_native(lib, meta, data["g0"], 1)
+    assert np.allclose(used, dts, rtol=1e-14, atol=0)
+    assert np.all(rel_l1(got, want) <= 1e-12), rel_l1(got, want)
+
+
+@pytest.mark.parametrize("cid", HYDRO)
+def test_golden_all_steps_bit_exact_vs_oracle(lib, cid):
+    meta, data = golden_case(cid)
+    want, dts = run_oracle(meta, data["g0"], meta["steps"])
+    got, used, _ = run_native(lib, meta, data["g0"], meta["steps"])
+    assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
+    assert used == dts and np.array_equal(got, want, equal_nan=True), "within tolerance but not bit-identical"
+
+
+def _meta(config, cells, dim, subgrid, solver, timestep, bc):
+    prob = problem(config, cells, 1.4)
+    return dict(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
+                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=False)
+
+
+MATRIX = [(cfg, sub, sol, bc, dim)
+          for dim, cfg in ((1, "sod"), (2, "ll4"))
+          for sub in ("pcm", "plm", "ppm", "weno3", "weno5", "weno7")
+          for sol in ("lf", "hllc")
+          for bc in ("edge", "wrap")]
+
+
+@pytest.mark.parametrize("config,subgrid,solver,bc,dim", MATRIX, ids=["-".join(map(str, m)) for m in MATRIX])
+def test_scheme_solver_matrix(lib, config, subgrid, solver, bc, dim):
+    """Ragged sizes and many blocks: 1D 1531 cells, 2D 203 x 203 (not multiples of any tile)."""
+    cells = 1531 if dim == 1 else 203
+    meta = _meta(config, cells, dim, subgrid, solver, "ssprk(3,3)", bc)
+    high = subgrid.startswith("w") or subgrid == "ppm"
+    g0 = initial_state(config, cells, dim, 1.4, high, boundary=bc)
+    want, dts = run_oracle(meta, g0, 2)
+    got, used, _ = run_native(lib, meta, g0, 2, segment_2d=37)
+    assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
+    assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("timestep", ["euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"])
+def test_every_integrator(lib, timestep):
+    meta = _meta("ll12", 96, 2, "plm", "hllc", timestep, None)
+    g0 = initial_state("ll12", 96, 2, 1.4, False)
+    want, dts = run_oracle(meta, g0, 3)
+    got, used, _ = run_native(lib, meta, g0, 3)
+    assert np.all(rel_l1(got, want) <= 1e-10)
+    assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+def test_sod_full_run(lib):
+    """BASELINE config 1 to t_end = 0.2: 896 steps, parity 1e-10 with the oracle at the end."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle import advance
+    meta = _meta("sod", 1024, 1, "plm", "lf", "ssprk(2,2)", None)
+    g0 = initial_state("sod", 1024, 1, 1.4, False)
+    ctx = N.Context(native_cfg(meta), lib=lib)
+    ctx.upload(g0)
+    t, steps, dts = 0.0, 0, []
+    while t < 0.2:
+        dt = ctx.step(t, 0.2)
+        dts.append(dt)
+        t += dt
+        steps += 1
+    got = ctx.download()
+    ctx.close()
+    assert steps == 896
+    cfg = oracle_cfg(meta)
+    want = np.copy(g0)
+    for dt in dts:
+        want, _ = advance(want, cfg, 1, dts=[dt])
+        cfg.step_parity = 0
+    assert np.all(rel_l1(got, want) <= 1e-10)
+
+
+def test_nonfinite_raises_linalgerror(lib):
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll3", 64, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    g0 = initial_state("ll3", 64, 2, 1.4, True)
+    g0[5, 7, 0] = np.nan
+    ctx = N.Context(native_cfg(meta), lib=lib)
+    ctx.upload(g0)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.step()
+    ctx.close()
+
+
+def test_reference_horizon_is_reproduced(lib):
+    """The reference's LL3 PPM+HLLC run dies of LinAlgError in its third step: so does the device run."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll3", 128, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    ctx = N.Context(native_cfg(meta), lib=lib)
+    ctx.upload(initial_state("ll3", 128, 2, 1.4, True))
+    ctx.step()
+    ctx.step()
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.step()
+        ctx.step()
+    ctx.close()
+
+
+def test_drop_in_evolvers_functions(lib):
+    """evolve_space / evolve_time with the reference's call signature and a sim_variables-like namedtuple."""
+    from collections import namedtuple
+    from astrea_b200 import evolvers
+    from cases import oracle_cfg
+    from oracle import advance
+    meta = _meta("ll6", 64, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    SV = namedtuple("simulation_variables", "dimension cells boundary gamma dx cfl subgrid solver solver_category timestep magnetic_2d permutations")
+    perms = {0: (0, 1, 2), 1: (1, 0, 2)}
+    sv = SV(2, 64, meta["boundary"], 1.4, meta["dx"], .5, "ppm", "hllc", "hll", "ssprk(3,3)", False, perms)
+    grid = initial_state("ll6", 64, 2, 1.4, True)
+    want, dts = advance(np.copy(grid), oracle_cfg(meta), 3)
+    for n in range(3):
+        fluxes = evolvers.evolve_space(grid, sv)
+        dt = sv.cfl * min(sv.dx / f["eigmax"] for f in fluxes.values())
+        grid = evolvers.evolve_time(grid, fluxes, dt, sv)
+        sv = sv._replace(permutations=dict(reversed(list(sv.permutations.items()))))     # astrea.py:85
+    evolvers.release()
+    assert np.all(rel_l1(grid, want) <= 1e-10)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def _run_big(lib, cells, subgrid, solver, steps, g0, **geometry):
+    meta = _meta("ll3", cells, 2, subgrid, solver, "ssprk(3,3)", "wrap")
+    return run_native(lib, meta, g0, steps, **geometry)
+
+
+def test_full_size_shift_equivariance_and_conservation(lib):
+    """BASELINE config 2 size (2048^2, PPM+HLLC, SSPRK3, periodic): the oracle cannot run this size, so use
+    properties.  (a) shifting the periodic initial data by (s_x, s_y) cells shifts the result, bit for bit — this
+    exercises every block seam and the halo fill; (b) the conserved totals change only by round-off."""
+    cells = 2048
+    g0 = initial_state("ll3", cells, 2, 1.4, True)
+    a, dts_a, _ = _run_big(lib, cells, "ppm", "hllc", 1, g0)
+    shift = (301, 77)
+    b, dts_b, _ = _run_big(lib, cells, "ppm", "hllc", 1, np.ascontiguousarray(np.roll(g0, shift, axis=(0, 1))))
+    assert dts_a == dts_b
+    assert np.array_equal(np.roll(a, shift, axis=(0, 1)), b)
+    tot0, tot1 = g0.sum(axis=(0, 1)), a.sum(axis=(0, 1))
+    scale = np.abs(g0).sum(axis=(0, 1))
+    assert np.all(np.abs(tot1 - tot0) <= 1e-11 * np.where(scale > 0, scale, 1))
+
+
+def test_full_size_tiling_independence(lib):
+    cells = 1024
+    g0 = initial_state("ll3", cells, 2, 1.4, True)
+    a, _, _ = _run_big(lib, cells, "ppm", "hllc", 2, g0)
+    b, _, _ = _run_big(lib, cells, "ppm", "hllc", 2, g0, threads_2d=96, segment_2d=100)
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_medium_size_vs_oracle(lib):
+    """256^2 PPM+HLLC SSPRK3, the largest size the oracle finishes in seconds: both finite steps."""
+    meta = _meta("ll3", 256, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    g0 = initial_state("ll3", 256, 2, 1.4, True)
+    want, dts = run_oracle(meta, g0, 2)
+    got, used, _ = run_native(lib, meta, g0, 2)
+    assert np.all(rel_l1(got, want) <= 1e-10)
+    assert np.allclose(used, dts, rtol=1e-13, atol=0)

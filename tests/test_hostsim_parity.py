@@ -1,0 +1,157 @@
+"""Kernel logic against the oracle without a GPU.
+
+The kernel sources build a second way (g++, -DASTREA_HOSTSIM): the same block/phase code, executed thread by
+thread on the CPU behind the same C ABI.  That library is test infrastructure (the astrea_b200 package never
+loads it); it lets every index map, halo rule and limiter branch of the CUDA kernels be checked against the oracle
+in the build container.  The `-m gpu` tests repeat these comparisons on the device library.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_case, golden_index, rel_l1
+from cases import run_native, run_oracle
+from astrea_b200.initial import initial_state, problem
+
+HYDRO = sorted(c for c, m in golden_index().items() if not m["magnetic_2d"])
+
+
+@pytest.mark.parametrize("cid", HYDRO)
+def test_golden_cases_bit_exact_vs_oracle(hostsim_lib, cid):
+    meta, data = golden_case(cid)
+    want, dts = run_oracle(meta, data["g0"], meta["steps"])
+    got, used, _ = run_native(hostsim_lib, meta, data["g0"], meta["steps"])
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("cid", HYDRO)
+def test_golden_cases_vs_reference(hostsim_lib, cid):
+    """Against the reference's own output, fed the reference's dt sequence through evolve_space / evolve_time."""
+    meta, data = golden_case(cid)
+    got, _, eigs = run_native(hostsim_lib, meta, data["g0"], meta["steps"], dts=list(data["dts"]))
+    tol = 1e-10 if "weno7" in cid else 1e-12 * meta["steps"]
+    assert np.all(rel_l1(got, data["g"]) <= tol)
+    # eigmax[a] is per sweep axis a; the reference lists them in iteration order (reversed on odd steps)
+    for n, e in enumerate(eigs):
+        ref = list(data["eigmax"][n])
+        ref = ref[::-1] if (n % 2 and meta["dimension"] == 2) else ref
+        assert np.allclose(e, ref, rtol=1e-11, atol=0)
+
+
+def _meta(config, cells, dim, subgrid, solver, timestep, bc):
+    prob = problem(config, cells, 1.4)
+    return dict(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
+                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=False)
+
+
+# every scheme x solver, both boundary modes, odd sizes, with the grid cut into many blocks
+MATRIX = [(cfg, sub, sol, bc, dim)
+          for dim, cfg in ((1, "sod"), (2, "ll4"))
+          for sub in ("pcm", "plm", "ppm", "weno3", "weno5", "weno7")
+          for sol in ("lf", "hllc")
+          for bc in ("edge", "wrap")]
+
+
+@pytest.mark.parametrize("config,subgrid,solver,bc,dim", MATRIX, ids=["-".join(map(str, m)) for m in MATRIX])
+def test_scheme_solver_matrix_multiblock(hostsim_lib, config, subgrid, solver, bc, dim):
+    cells = 61 if dim == 1 else 38
+    meta = _meta(config, cells, dim, subgrid, solver, "ssprk(3,3)", bc)
+    high = subgrid.startswith("w") or subgrid == "ppm"
+    g0 = initial_state(config, cells, dim, 1.4, high, boundary=bc)
+    want, dts = run_oracle(meta, g0, 2)
+    got, used, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=32, segment_2d=11, tile_1d=13)
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+INTEGRATORS = ["euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"]
+
+
+@pytest.mark.parametrize("timestep", INTEGRATORS)
+@pytest.mark.parametrize("dim", [1, 2])
+def test_every_integrator(hostsim_lib, timestep, dim):
+    cells = 64 if dim == 1 else 24
+    config = "sod" if dim == 1 else "ll12"
+    meta = _meta(config, cells, dim, "plm", "hllc", timestep, None)
+    g0 = initial_state(config, cells, dim, 1.4, False)
+    want, dts = run_oracle(meta, g0, 3)
+    got, used, _ = run_native(hostsim_lib, meta, g0, 3)
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("limiter", ["minmod", "vanleer", "ospre", "vanalbada", "koren", "superbee"])
+def test_slope_limiters(hostsim_lib, limiter):
+    """limiters.py:10-49: only minmod is wired into plm.py:27; the others are selectable through the C ABI."""
+    meta = _meta("sod", 96, 1, "plm", "lf", "ssprk(2,2)", None)
+    g0 = initial_state("sod", 96, 1, 1.4, False)
+    from cases import oracle_cfg
+    from oracle import advance
+    cfg = oracle_cfg(meta)
+    cfg.slope_limiter = limiter
+    want, dts = advance(np.copy(g0), cfg, 3)
+    got, used, _ = run_native(hostsim_lib, meta, g0, 3, limiter=limiter)
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_geometry_does_not_change_results(hostsim_lib):
+    """Block shape is an implementation detail: any tiling gives bit-identical states."""
+    meta = _meta("ll3", 40, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    g0 = initial_state("ll3", 40, 2, 1.4, True)
+    base, _, _ = run_native(hostsim_lib, meta, g0, 2)
+    for threads, seg in ((32, 7), (48, 40), (64, 16)):
+        got, _, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=threads, segment_2d=seg)
+        assert np.array_equal(got, base, equal_nan=True)
+
+
+def test_primitive_download(hostsim_lib):
+    """astrea.py:47 snapshots sim_variables.convert_conservative(grid): 4th-order for PPM/WENO, pointwise otherwise."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle.gridops import prim_avg_of_cons_avg
+    for dim, sub, bc in ((1, "plm", "edge"), (1, "ppm", "edge"), (2, "weno5", "wrap"), (2, "ppm", "edge"), (2, "pcm", "wrap")):
+        cells = 50 if dim == 1 else 20
+        config = "sod" if dim == 1 else "ll3"
+        meta = _meta(config, cells, dim, sub, "lf", "euler", bc)
+        g0 = initial_state(config, cells, dim, 1.4, sub != "plm" and sub != "pcm", boundary=bc)
+        ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+        ctx.upload(g0)
+        assert np.array_equal(ctx.download(), g0)
+        assert np.array_equal(ctx.download(primitive=True), prim_avg_of_cons_avg(g0, oracle_cfg(meta)))
+        ctx.close()
+
+
+def test_nonfinite_wave_speed_raises(hostsim_lib):
+    """Where np.linalg.eigvals raises LinAlgError in the reference (fv.py:158) the ABI returns
+    ASTREA_E_NONFINITE and the binding raises a LinAlgError subclass."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("sod", 64, 1, "plm", "lf", "ssprk(2,2)", None)
+    g0 = initial_state("sod", 64, 1, 1.4, False)
+    g0[10, 4] = np.nan
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.step()
+    ctx.close()
+
+
+def test_call_order_is_enforced(hostsim_lib):
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("sod", 64, 1, "plm", "lf", "ssprk(2,2)", None)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(initial_state("sod", 64, 1, 1.4, False))
+    with pytest.raises(N.AstreaError) as err:
+        ctx.evolve_time(1e-3)
+    assert err.value.code == N.E_STATE
+    ctx.close()
+
+
+def test_unsupported_selectors_fail_loudly(hostsim_lib):
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("sod", 64, 1, "plm", "lw", "ssprk(2,2)", None)     # Lax-Wendroff: SURVEY Q11
+    with pytest.raises(N.AstreaError):
+        N.Context(native_cfg(meta), lib=hostsim_lib)

@@ -1,0 +1,53 @@
+"""The reference's string selectors (evolvers.py:14-21, solvers.py:13-31, evolvers.py:79-81, weno.py:159-165)."""
+import pytest
+
+from astrea_b200 import _native as N
+from astrea_b200 import selectors as S
+from oracle import config as O
+
+
+@pytest.mark.parametrize("name,want", [("pcm", N.PCM), ("c", N.PCM), ("plm", N.PLM), ("linear", N.PLM), ("l", N.PLM), ("ppm", N.PPM),
+                                       ("parabolic", N.PPM), ("p", N.PPM), ("weno", N.WENO5), ("w", N.WENO5), ("weno3", N.WENO3),
+                                       ("weno-5", N.WENO5), ("weno7", N.WENO7), ("weno9", N.WENO5), ("wenoz", N.WENO5)])
+def test_scheme(name, want):
+    assert S.scheme_enum(name) == want
+    kind, order = O.scheme_of(name)
+    assert {("pcm", 0): N.PCM, ("plm", 0): N.PLM, ("ppm", 0): N.PPM, ("weno", 3): N.WENO3, ("weno", 5): N.WENO5,
+            ("weno", 7): N.WENO7}[(kind, order)] == want
+
+
+@pytest.mark.parametrize("name,want", [("lf", N.LLF), ("llf", N.LLF), ("lax-friedrich", N.LLF), ("lw", N.LW),
+                                       ("lax-wendroff", N.LLF),   # solvers.py:28 tests endswith("w"): only "lw" selects Lax-Wendroff
+                                      
+                                       ("hllc", N.HLLC), ("c", N.HLLC), ("hlld", N.HLLD), ("d", N.HLLD)])
+def test_solver(name, want):
+    assert S.solver_enum(name) == want
+    assert {"llf": N.LLF, "lw": N.LW, "hllc": N.HLLC, "hlld": N.HLLD}[O.solver_of(name)] == want
+
+
+def test_out_of_scope_solvers_raise():
+    for name in ("osher", "es", "entropy-stable"):
+        with pytest.raises(NotImplementedError):
+            S.solver_enum(name)
+    with pytest.raises(ValueError):
+        S.solver_enum("roe")
+
+
+@pytest.mark.parametrize("name,want,stages", [("euler", N.EULER, 1), ("rk4", N.RK4, 4), ("ssprk(2,2)", N.SSPRK22, 2), ("ssprk22", N.SSPRK22, 2),
+                                              ("ssprk(3,3)", N.SSPRK33, 3), ("ssprk(4,3)", N.SSPRK43, 4), ("ssprk(5,3)", N.SSPRK53, 5),
+                                              ("ssprk(5,4)", N.SSPRK54, 5), ("ssprk(10,4)", N.SSPRK104, 11), ("ssprk104", N.SSPRK104, 11)])
+def test_integrator(name, want, stages):
+    assert S.integrator_enum(name) == want
+    assert S.stages_of(want) == stages
+    names = ["euler", "rk4", "ssprk22", "ssprk33", "ssprk43", "ssprk53", "ssprk54", "ssprk104"]
+    assert names.index(O.integrator_of(name)) == want
+
+
+def test_step_program_has_one_operator_per_stage(hostsim_lib):
+    for ts in ("euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"):
+        cfg = S.make_cfg(dimension=1, cells=32, boundary="edge", gamma=1.4, dx=1 / 32, cfl=.5, subgrid="plm", solver="lf", timestep=ts)
+        ctx = N.Context(cfg, lib=hostsim_lib)
+        prog = ctx.program()
+        assert prog[0] is True and prog[-1] is False
+        assert sum(prog) == S.stages_of(cfg.integrator)
+        ctx.close()
