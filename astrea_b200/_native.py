@@ -220,10 +220,10 @@ class Context:
         self._check(self.lib.astrea_profile(self._h, 1 if enable else 0))
 
     def profile_read(self):
-        """{class: (milliseconds, launches)} since the last read; classes: sweep, transpose, update, halo."""
-        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
+        """{class: (milliseconds, launches)} since the last read."""
+        ms, n = (C.c_double * 6)(), (C.c_int64 * 6)()
         self._check(self.lib.astrea_profile_read(self._h, ms, n))
-        return {name: (ms[k], n[k]) for k, name in enumerate(("sweep", "transpose", "update", "halo"))}
+        return {name: (ms[k], n[k]) for k, name in enumerate(("flux", "transpose", "update", "halo", "prim", "recon"))}
 
     @property
     def stream_handle(self):

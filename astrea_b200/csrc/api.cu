@@ -19,38 +19,6 @@
 
 namespace astrea {
 
-int launch_sweep1d(int scheme, int solver, const Sweep1DParams& p, int nthreads, Stream st) {
-    switch (scheme) {
-        case SCH_PCM: return launch_sweep1d_pcm(solver, p, nthreads, st);
-        case SCH_PLM: return launch_sweep1d_plm(solver, p, nthreads, st);
-        case SCH_PPM: return launch_sweep1d_ppm(solver, p, nthreads, st);
-        case SCH_WENO3: return launch_sweep1d_weno3(solver, p, nthreads, st);
-        case SCH_WENO5: return launch_sweep1d_weno5(solver, p, nthreads, st);
-        case SCH_WENO7: return launch_sweep1d_weno7(solver, p, nthreads, st);
-        default: return -1;
-    }
-}
-
-int launch_sweep2d(int scheme, int solver, int ax, int sax, Sweep2DParams p, int nthreads, Stream st) {
-    switch (scheme) {
-        case SCH_PCM: return launch_sweep2d_pcm(solver, ax, sax, p, nthreads, st);
-        case SCH_PLM: return launch_sweep2d_plm(solver, ax, sax, p, nthreads, st);
-        case SCH_PPM: return launch_sweep2d_ppm(solver, ax, sax, p, nthreads, st);
-        case SCH_WENO3: return launch_sweep2d_weno3(solver, ax, sax, p, nthreads, st);
-        case SCH_WENO5: return launch_sweep2d_weno5(solver, ax, sax, p, nthreads, st);
-        case SCH_WENO7: return launch_sweep2d_weno7(solver, ax, sax, p, nthreads, st);
-        default: return -1;
-    }
-}
-
-// shared-memory doubles per thread of the 2D sweep kernel (Sweep2D::smem_bytes / 8 / nthreads)
-static int sweep2d_doubles_per_thread(int scheme, int solver) {
-    const bool ho = scheme_high_order(scheme);
-    const int lag = (solver == SOL_LLF && scheme != SCH_PCM) ? 1 : 0;
-    const int nq = ho ? 3 : 2, nw = recon_lo(scheme) + recon_hi(scheme) + 1, ni = 1 + lag;
-    return NVAR * (nq + nw + 4 * ni + 1) + 2 * ni;
-}
-
 }  // namespace astrea
 
 using namespace astrea;
@@ -88,7 +56,8 @@ struct astrea_ctx {
     int ghost_r = 0;                  // ghost rows (0 in 1D)
     size_t plane_doubles = 0;
     std::vector<Reg> regs, rates;
-    Reg qT, d0, d1t;                  // transposed input of the y sweep; flux differences of the two sweeps
+    Reg qT, d0, d1t;                  // transposed input of the y sweep; interface fluxes of the x / y sweep (1D: flux difference)
+    Reg ws, wp, wm;                   // 2D scratch of the sweep in flight: primitive averages, interface states
     unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
     unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
     int* flag = nullptr;              // non-finite wave speed seen in any operator since the last read
@@ -117,7 +86,7 @@ int fail(astrea_ctx* c, int code, const std::string& msg) {
     return code;
 }
 
-enum { CLS_SWEEP = 0, CLS_TRANSPOSE = 1, CLS_UPDATE = 2, CLS_HALO = 3, CLS_COUNT = 4 };
+enum { CLS_SWEEP = 0, CLS_TRANSPOSE = 1, CLS_UPDATE = 2, CLS_HALO = 3, CLS_PRIM = 4, CLS_RECON = 5, CLS_COUNT = 6 };
 
 // Brackets one launch with CUDA events on the context's stream when profiling is on.
 struct Timed {
@@ -327,43 +296,66 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
             const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
             { Timed timed(c, CLS_TRANSPOSE); ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st)); }
         }
+        const bool ho = scheme_high_order(g.scheme), pcm = g.scheme == SCH_PCM;
+        const int kind = pcm ? 0 : (ho ? 2 : 1);
+        const int lo = recon_lo(g.scheme), hi = recon_hi(g.scheme);
+        const int ht = ho ? 2 : 1;                 // transverse reach of the flux stage
         for (int k = 0; k < 2; ++k) {
             const int ax = order[k], sax = k;
-            Sweep2DParams p{};
-            p.gamma = g.gamma; p.dx = g.dx; p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach;
-            p.flag = c->flag;
-            p.eigmax_bits = eig + ax;
-            int colblocks;
+            int64_t ns, nt, ns_glob, s_off, nt_glob, t_off;
+            Plane qf, ff;
             if (ax == 0) {
-                p.q = q; p.d = c->d0.plane;
-                p.ns = c->nrow; p.nt = c->ncol;
-                p.ns_glob = g.nx_global; p.s_off = g.x_offset; p.nt_glob = c->ncol; p.t_off = 0;
-                colblocks = c->colblocks_x;
+                qf = q; ff = c->d0.plane;
+                ns = c->nrow; nt = c->ncol; ns_glob = g.nx_global; s_off = g.x_offset; nt_glob = c->ncol; t_off = 0;
             } else {
-                p.q = c->qT.plane; p.d = c->d1t.plane;
-                p.ns = c->ncol; p.nt = c->nrow;
-                p.ns_glob = c->ncol; p.s_off = 0; p.nt_glob = g.nx_global; p.t_off = g.x_offset;
-                colblocks = c->colblocks_y;
+                qf = c->qT.plane; ff = c->d1t.plane;
+                ns = c->ncol; nt = c->nrow; ns_glob = c->ncol; s_off = 0; nt_glob = g.nx_global; t_off = g.x_offset;
             }
-            const int ht = scheme_high_order(g.scheme) ? 3 : 1;
-            p.tt = (int)((p.nt + colblocks - 1) / colblocks);
-            const int nthreads = p.tt + 2 * ht;
-            int seg = g.segment_2d;
-            if (seg <= 0) {
-                // enough blocks to fill 148 SMs in whole waves, while the start-up rows of a segment stay a small share
-                for (int waves = 1; waves <= 64; ++waves) {
-                    const int64_t nseg = std::max<int64_t>(1, (148 * waves + colblocks - 1) / colblocks);
-                    seg = (int)((p.ns + nseg - 1) / nseg);
-                    if (seg <= 512) break;
-                }
-                seg = std::max(seg, 32);
+            // scratch planes in the shape of this frame
+            const Plane ws = make_plane(c->ws.mem, nt, GHOST), wp = make_plane(c->wp.mem, nt, GHOST), wm = make_plane(c->wm.mem, nt, GHOST);
+            const bool edge = g.boundary == BC_EDGE;
+            const bool lo_phys = s_off == 0, hi_phys = s_off + ns == ns_glob;
+            // cells to reconstruct: one beyond each end (two at the upper end: LLF looks at interface j+1), except
+            // across a physical 'edge' boundary where the interface states are copies ("pad the derived array")
+            const int64_t i_lo = (edge && lo_phys) ? 0 : -1, i_hi = (edge && hi_phys) ? ns - 1 : ns + 1;
+            {
+                PrimStageParams pp{};
+                pp.q = qf; pp.w = ws; pp.gamma = g.gamma; pp.high_order = ho ? 1 : 0;
+                pp.r_lo = -(int64_t)(lo + 1); pp.r_hi = ns + hi + 2; pp.c_lo = -(int64_t)ht; pp.c_hi = nt + ht;
+                pp.r_min = -(int64_t)GHOST; pp.r_max = ns + GHOST - 1; pp.c_min = -(int64_t)GHOST; pp.c_max = nt + GHOST - 1;
+                const int gx = (int)((pp.c_hi - pp.c_lo + PrimStage::TX - 1) / PrimStage::TX);
+                const int gy = (int)((pp.r_hi - pp.r_lo + PrimStage::TY - 1) / PrimStage::TY);
+                Timed timed(c, CLS_PRIM);
+                ASTREA_TRY(launch<PrimStage>(pp, gx, gy, 256, PrimStage::smem_bytes(pp.high_order), c->st));
             }
-            p.seg = (int)std::min<int64_t>(seg, p.ns);
-            { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep2d(g.scheme, g.solver, ax, sax, p, nthreads, c->st)); }
+            if (!pcm) {
+                ReconStageParams rp{};
+                rp.w = ws; rp.wp = wp; rp.wm = wm; rp.wf = Plane{nullptr, 0, 0};
+                rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = -(int64_t)ht; rp.c_hi = nt + ht;
+                rp.i_lo = i_lo; rp.i_hi = i_hi; rp.bc = g.boundary; rp.limiter = g.limiter;
+                rp.seg = g.segment_2d > 0 ? g.segment_2d : 64;
+                const int nthreads = 128;
+                const int gx = (int)((rp.c_hi - rp.c_lo + nthreads - 1) / nthreads);
+                const int nseg = (int)((i_hi - i_lo + 1 + rp.seg - 1) / rp.seg);
+                Timed timed(c, CLS_RECON);
+                ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * NVAR, nthreads, c->st));
+            }
+            {
+                FluxStageParams fp{};
+                fp.wp = wp; fp.wm = wm; fp.ws = ws; fp.q = qf; fp.f = ff;
+                fp.ns = ns; fp.nt = nt; fp.ns_glob = ns_glob; fp.s_off = s_off; fp.nt_glob = nt_glob; fp.t_off = t_off;
+                fp.gamma = g.gamma; fp.bc = g.boundary; fp.low_mach = g.low_mach;
+                fp.eigmax_bits = eig + ax; fp.flag = c->flag;
+                const int nthreads = (g.threads_2d >= 32 && g.threads_2d <= 128) ? g.threads_2d / 32 * 32 : 128;
+                const int own = 32 - 2 * ht, nwarp = nthreads / 32;
+                const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
+                Timed timed(c, CLS_SWEEP);
+                ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, fp, gx, gy, nthreads, c->st));
+            }
         }
     }
     RateParams r{};
-    r.d0 = c->d0.plane; r.d1t = c->d1t.plane; r.out = c->rates[ins.rate_out].plane;
+    r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane; r.out = c->rates[ins.rate_out].plane;
     r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = nullptr; r.emf_pitch = 0; r.dx = g.dx; r.bc = g.boundary;
     {
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
@@ -450,6 +442,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     ok = ok && alloc_reg(c, c->d0, c->ncol);
     if (g.dimension == 2) {
         ok = ok && alloc_reg(c, c->qT, c->nrow) && alloc_reg(c, c->d1t, c->nrow);
+        ok = ok && alloc_reg(c, c->ws, c->ncol) && alloc_reg(c, c->wp, c->ncol) && alloc_reg(c, c->wm, c->ncol);
     } else {
         ok = ok && alloc_reg(c, c->qT, c->ncol);   // scratch for primitive downloads
     }
@@ -475,15 +468,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
         c->tile1d = tile;
         c->threads1d = tile + lo + hi;
     } else {
-        const int per_thread = sweep2d_doubles_per_thread(g.scheme, g.solver);
-        int tmax = (int)(SMEM_LIMIT / (sizeof(double) * per_thread));
-        tmax = std::min(256, tmax / 32 * 32);
-        if (g.threads_2d > 0) tmax = std::max(32, std::min(tmax, g.threads_2d));
-        const int ht = scheme_high_order(g.scheme) ? 3 : 1;
-        c->threads2d = tmax;
-        c->tt2d = tmax - 2 * ht;
-        c->colblocks_x = (int)((c->ncol + c->tt2d - 1) / c->tt2d);   // x sweep: columns are y
-        c->colblocks_y = (int)((c->nrow + c->tt2d - 1) / c->tt2d);   // y sweep: columns are x
+        c->threads2d = 128;
     }
     return c;
 }
@@ -494,6 +479,7 @@ void astrea_destroy(astrea_ctx* c) {
     for (auto& r : c->regs) dev_free(r.mem);
     for (auto& r : c->rates) dev_free(r.mem);
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
+    dev_free(c->ws.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->stream_owned) cudaStreamDestroy(c->st.s);

@@ -109,9 +109,10 @@ struct TransposeKernel {
 
 // ------------------------------------------------------------------------------------------------ assemble L
 struct RateParams {
-    Plane d0;             // (F[i+1]-F[i])/dx of the x sweep, [x][v][y]
-    Plane d1t;            // same of the y sweep in its own (transposed) frame, [y][v][x]; unused in 1D
-    Plane out;            // L = -(d0 + d1)
+    Plane f0;             // Riemann flux of the x sweep at interface rows 0..nrow, [x][v][y]  (1D: unused, see d0)
+    Plane f1t;            // same of the y sweep in its own (transposed) frame, [y][v][x]
+    Plane d0;             // 1D only: (F[i+1]-F[i])/dx written by the fused 1D sweep kernel
+    Plane out;            // L = -(dF_x/dx + dF_y/dx)   (evolvers.py:41-60)
     int64_t nrow, ncol;
     int dimension;
     // constrained transport (evolvers.py:52-58): overwrite the in-plane field rates with emf differences
@@ -131,11 +132,12 @@ struct RateKernel {
         const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
         for (int v = 0; v < NVAR; ++v) {
             if (p.dimension == 2) {
-                ex.phase([&](int tid) {     // read the y-sweep tile coalesced along its own columns (= x)
+                ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
                     const int tx = tid % TILE;
                     for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                         const int64_t yr = c0 + ty, xc = r0 + tx;
-                        if (yr < p.ncol && xc < p.nrow) tile[ty * (TILE + 1) + tx] = *p.d1t.at(yr, v, xc);
+                        if (yr < p.ncol && xc < p.nrow)
+                            tile[ty * (TILE + 1) + tx] = (*p.f1t.at(yr + 1, v, xc) - *p.f1t.at(yr, v, xc)) / p.dx;
                     }
                 });
             }
@@ -144,8 +146,15 @@ struct RateKernel {
                 for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                     const int64_t r = r0 + ty, c = c0 + tx;
                     if (r >= p.nrow || c >= p.ncol) continue;
-                    double total = *p.d0.at(r, v, c);
-                    if (p.dimension == 2) total = total + tile[tx * (TILE + 1) + ty];
+                    double total;
+                    if (p.dimension == 2) {
+                        // compute_L sums the sweeps in iteration order (evolvers.py:45-49); the sum of two terms
+                        // does not depend on that order
+                        total = (*p.f0.at(r + 1, v, c) - *p.f0.at(r, v, c)) / p.dx;
+                        total = total + tile[tx * (TILE + 1) + ty];
+                    } else {
+                        total = *p.d0.at(r, v, c);
+                    }
                     if (p.emf != nullptr && (v == 5 || v == 6)) {
                         const double* e = p.emf + r * p.emf_pitch + c;
                         if (v == 5) total = (e[1] - e[0]) / p.dx;                       // +dE/dy

@@ -40,6 +40,19 @@ struct DeviceExec {
         f((int)threadIdx.x);
         __syncthreads();
     }
+    // warp-scope phase: the threads of a warp run f, then re-converge (no block barrier)
+    template <class F>
+    __device__ __forceinline__ void wphase(F&& f) {
+        f((int)threadIdx.x);
+        __syncwarp();
+    }
+    // Value that lane (lane + delta) mod 32 of the same warp produced in an EARLIER phase: ``get(t)`` returns the
+    // value held by thread t.  On the device every lane evaluates get() on itself and the value moves by shuffle.
+    template <class G>
+    __device__ __forceinline__ double lane(int tid, int delta, G&& get) {
+        const double own = get(tid);
+        return __shfl_sync(0xffffffffu, own, ((tid & 31) + delta) & 31);
+    }
     // Block-wide max of a non-negative per-thread value -> atomicMax on the bit pattern of *dst; ``bad``
     // (non-finite seen) is OR-ed into *flag.  Call from block scope (not inside a phase): get(tid, val, bad).
     template <class G>
@@ -117,6 +130,14 @@ struct HostExec {
     template <class F>
     void phase(F&& f) {
         for (int t = 0; t < nthr; ++t) f(t);
+    }
+    template <class F>
+    void wphase(F&& f) {
+        for (int t = 0; t < nthr; ++t) f(t);
+    }
+    template <class G>
+    double lane(int tid, int delta, G&& get) {
+        return get((tid & ~31) + (((tid & 31) + delta) & 31));
     }
     template <class G>
     void publish_max(G&& get, unsigned long long* dst, int* flag) {

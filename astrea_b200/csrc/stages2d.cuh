@@ -1,0 +1,360 @@
+// 2D spatial operator for one sweep direction as three small, high-occupancy kernels.
+//
+// Frame: rows of every plane run along the sweep direction (s), columns along the transverse direction (t); the
+// x sweep reads the state as stored, the y sweep its transposed copy (the reference's ``grid.transpose(axes)``).
+//
+//   PrimStage   q  -> wS       primitive cell averages: pointwise (PCM/PLM, fv.py:97-101) or 4th-order
+//                              (PPM/WENO, fv.py:126-143).  Thread per cell, 34x10 shared-memory tile so that each
+//                              pointwise conversion is evaluated once.
+//   ReconStage  wS -> w+, w-   reconstruction + limiter (schemes/*.py, limiters.py).  Thread per (column, variable)
+//                              marching along the sweep with the stencil in registers: one load and two stores
+//                              per cell and variable, no shared memory, no barrier.
+//   FluxStage   w+- -> F       face conversion (fv.py:105-122 'face'), physical fluxes (constructor.py:113-125),
+//                              averaged-state wave speed (fv.py:157-169), Riemann flux of the face averages and of
+//                              the face-centred states, F = F_c - d2_t(F_avg)/24 (solvers.py:44-57, fv.py:147-153).
+//                              One warp per 32 transverse points of one interface row; transverse neighbours are
+//                              exchanged by warp shuffle, everything else lives in registers.
+//
+// The flux difference and the Runge-Kutta update follow in aux_kernels.cuh.  HBM traffic per cell and sweep:
+// 64 B (q) + 64 B (wS) + 64 B + 128 B (w+-) + 128 B + 64 B (F); see DESIGN.md for the roofline discussion (the
+// path is bound by the fp64 pipe, not by HBM).
+#pragma once
+#include "physics.cuh"
+#include "recon.cuh"
+#include "riemann.cuh"
+#include "runtime.cuh"
+
+namespace astrea {
+
+// ------------------------------------------------------------------------------------------------ PrimStage
+struct PrimStageParams {
+    Plane q, w;
+    int64_t r_lo, r_hi, c_lo, c_hi;   // half-open output range (may reach into the ghost region)
+    int64_t r_min, r_max, c_min, c_max;   // allocated index range of the planes (inclusive) for clamped halo loads
+    double gamma;
+    int high_order;
+};
+struct PrimStage {
+    using Params = PrimStageParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TX = 32, TY = 8, SX = TX + 2, SY = TY + 2;
+    static size_t smem_bytes(int high_order) { return high_order ? sizeof(double) * 2 * NVAR * SX * SY : 0; }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int64_t c0 = p.c_lo + (int64_t)bx * TX, r0 = p.r_lo + (int64_t)by * TY;
+        const double gamma = p.gamma;
+        if (!p.high_order) {
+            ex.phase([&](int tid) {
+                const int64_t c = c0 + tid % TX, r = r0 + tid / TX;
+                if (c >= p.c_hi || r >= p.r_hi) return;
+                double q[NVAR], w[NVAR];
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) q[v] = *p.q.at(r, v, c);
+                prim_of_cons(q, w, gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) *p.w.at(r, v, c) = w[v];
+            });
+            return;
+        }
+        double* Q = ex.smem();                 // [NVAR][SY][SX] conservative averages of the tile + 1 halo
+        double* W = Q + NVAR * SX * SY;        // pointwise primitives of the same cells
+        ex.phase([&](int tid) {
+            for (int e = tid; e < SX * SY; e += MAX_THREADS) {
+                const int x = e % SX, y = e / SX;
+                const int64_t c = clamp_index(c0 - 1 + x, p.c_min, p.c_max), r = clamp_index(r0 - 1 + y, p.r_min, p.r_max);
+                double q[NVAR], w[NVAR];
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) q[v] = *p.q.at(r, v, c);
+                prim_of_cons(q, w, gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) { Q[(v * SY + y) * SX + x] = q[v]; W[(v * SY + y) * SX + x] = w[v]; }
+            }
+        });
+        ex.phase([&](int tid) {
+            const int x = tid % TX + 1, y = tid / TX + 1;
+            const int64_t c = c0 + x - 1, r = r0 + y - 1;
+            if (c >= p.c_hi || r >= p.r_hi) return;
+            const double c24 = 1.0 / 24.0;
+            double qa[NVAR], w[NVAR], ws[NVAR];
+            // fv.py:134-142: axis 0 of the sweep frame first, then the transverse axis
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                const double* q = Q + v * SY * SX;
+                const double* w0 = W + v * SY * SX;
+                const double qc = q[y * SX + x], wc = w0[y * SX + x];
+                double a = qc - c24 * ((q[(y + 1) * SX + x] - qc) - (qc - q[(y - 1) * SX + x]));
+                double s = c24 * ((w0[(y + 1) * SX + x] - wc) - (wc - w0[(y - 1) * SX + x]));
+                a = a - c24 * ((q[y * SX + x + 1] - qc) - (qc - q[y * SX + x - 1]));
+                s = s + c24 * ((w0[y * SX + x + 1] - wc) - (wc - w0[y * SX + x - 1]));
+                qa[v] = a;
+                ws[v] = s;
+            }
+            prim_of_cons(qa, w, gamma);
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) *p.w.at(r, v, c) = w[v] + ws[v];
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ ReconStage
+struct ReconStageParams {
+    Plane w;                   // primitive cell averages, valid on rows [-(LO+2) .. ns+HI+1] where data are genuine
+    Plane wp, wm;              // out: state on the right / left of interface j (rows 0 .. ns [+1])
+    Plane wf;                  // out (optional, base == nullptr to skip): face state handed to constrained transport
+    int64_t ns;                // local cells along the sweep
+    int64_t ns_glob, s_off;    // global extent and offset of local row 0 (for the 'edge' clamp)
+    int64_t c_lo, c_hi;        // half-open column range to process
+    int64_t i_lo, i_hi;        // inclusive range of cells to reconstruct (local indices)
+    int bc, limiter, seg;
+};
+
+// accessor over the register stencil: logical offset k relative to the cell, identity boundary map
+template <int LO>
+struct StencilAccessor {
+    const double* r;
+    HD double s(int64_t k) const { return r[k + LO]; }
+    HD int64_t b(int64_t k) const { return k; }
+};
+// accessor over a plane column with the clamp of an 'edge' boundary (rows near the physical boundary only)
+struct ColumnAccessor {
+    const double* col;         // address of (row 0, var, column)
+    int64_t row_pitch, lo_glob, hi_glob, off;
+    HD double s(int64_t k) const { return col[k * row_pitch]; }
+    HD int64_t b(int64_t k) const { return clamp_index(k + off, lo_glob, hi_glob) - off; }
+};
+
+template <int SCHEME>
+struct ReconStage {
+    using Params = ReconStageParams;
+    static constexpr int MAX_THREADS = 128;
+    static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
+    // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
+    static constexpr int REACH = HI + 2;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t t = p.c_lo + (int64_t)bx * NT + tid;
+            if (t >= p.c_hi) return;
+            const int v = by % NVAR;
+            const int64_t first = p.i_lo + (int64_t)(by / NVAR) * p.seg;
+            int64_t last = first + p.seg - 1;
+            if (last > p.i_hi) last = p.i_hi;
+            if (first > last) return;
+            const double* col = p.w.at(0, v, t);
+            const int64_t rp = p.w.row_pitch;
+            const bool edge = p.bc == BC_EDGE;
+            double r[NW];
+#pragma unroll
+            for (int k = 0; k < NW - 1; ++k) r[k + 1] = col[(first - LO + k) * rp];
+            for (int64_t i = first; i <= last; ++i) {
+#pragma unroll
+                for (int k = 0; k < NW - 1; ++k) r[k] = r[k + 1];
+                r[NW - 1] = col[(i + HI) * rp];
+                const int64_t ig = i + p.s_off;
+                double wl, wr, wf;
+                if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
+                    if (ig < 0 || ig > p.ns_glob - 1) continue;          // no such cell
+                    ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
+                    cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf);
+                } else {
+                    StencilAccessor<LO> acc{r};
+                    cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf);
+                }
+                // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
+                *p.wp.at(i, v, t) = wl;
+                *p.wm.at(i + 1, v, t) = wr;
+                if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
+                if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
+                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ FluxStage
+struct FluxStageParams {
+    Plane wp, wm;              // interface states from ReconStage (unused for PCM)
+    Plane ws, q;               // primitive / conservative cell averages (PCM faces, HLLD normal field)
+    Plane f;                   // out: Riemann flux at interface rows 0 .. ns
+    int64_t ns, nt;
+    int64_t ns_glob, s_off, nt_glob, t_off;
+    double gamma;
+    int bc, low_mach;
+    unsigned long long* eigmax_bits;
+    int* flag;
+};
+
+// KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)
+// MEAN: arithmetic mean (PLM) instead of the Roe average for the wave-speed state.  AX = physical sweep axis,
+// SAX = the solver's axis argument.
+template <int KIND, int SOLVER, int AX, int SAX>
+struct FluxStage {
+    using Params = FluxStageParams;
+    static constexpr int MAX_THREADS = 128;
+    static constexpr bool HO = KIND == 2, PCM = KIND == 0;
+    static constexpr int H = HO ? 2 : 1;            // halo lanes on each side of a warp
+    static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
+    static constexpr bool LLF = SOLVER == SOL_LLF;
+
+    // Per-thread values; a member read by the neighbouring lanes in phase n is never written in phase n.
+    struct Tls {
+        double wp[NVAR], wm[NVAR];     // face-averaged primitive states            (A)
+        double qp[NVAR], qm[NVAR];     // conservative states of wp / wm, pointwise  (A)
+        double fp[NVAR], fm[NVAR];     // physical flux of wp / wm                   (A)
+        double xp[NVAR], xm[NVAR];     // w - d2_t(w)/24: face-centred primitives    (B)
+        double ap[NVAR], am[NVAR];     // face-averaged conservative states          (B)
+        double fa[NVAR];               // Riemann flux of the face averages          (B)
+        double fc[NVAR];               // Riemann flux of the face-centred states    (C)
+        double lam, bn, lam_max;
+        int64_t j, t;
+        bool live, bad;
+    };
+
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        const int nwarp = NT / 32;
+        const double gamma = p.gamma, c24 = 1.0 / 24.0;
+        const bool edge = p.bc == BC_EDGE;
+        typename Ex::template Local<Tls> tls(ex);
+        auto smap = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.s_off, 0, p.ns_glob - 1) - p.s_off : r; };
+        auto solve = [&](const Tls& st, const double* wp, const double* wm, const double* qp, const double* qm, const double* fp,
+                         const double* fm, double* out) {
+            if (SOLVER == SOL_HLLC) hllc_flux<SAX>(gamma, p.low_mach != 0, wp, wm, qp, qm, fp, fm, out);
+            else if (SOLVER == SOL_HLLD) hlld_flux<SAX>(gamma, st.bn, wp, wm, qp, qm, fp, fm, out);
+            else llf_flux(st.lam, qp, qm, fp, fm, out);
+        };
+        // transverse second difference of a per-thread array member produced in an earlier phase; the neighbour of
+        // a point on a physical 'edge' boundary is the point itself ("pad the derived array")
+        auto d2t = [&](int tid, const Tls& st, double own, auto get) -> double {
+            double a = ex.lane(tid, -1, get), b = ex.lane(tid, 1, get);
+            if (edge) {
+                const int64_t tg = st.t + p.t_off;
+                if (tg - 1 < 0) a = own;
+                if (tg + 1 > p.nt_glob - 1) b = own;
+            }
+            return (b - own) - (own - a);
+        };
+        // averaged-state wave speed of interface row jj at this thread's column (fv.py:157-169)
+        auto speed_at = [&](int64_t jj, int64_t tc) -> double {
+            double a[NVAR], x[NVAR], y[NVAR];
+            if (PCM) {
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) a[v] = *p.ws.at(jj, v, tc);
+            } else {
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) { x[v] = *p.wp.at(jj, v, tc); y[v] = *p.wm.at(jj, v, tc); }
+                if (KIND == 1) mean_state(x, y, a); else roe_state(x, y, a);
+            }
+            return spectral_radius<AX>(a, gamma);
+        };
+
+        // A: load the interface states, pointwise conversions, wave speed
+        ex.wphase([&](int tid) {
+            Tls& st = tls[tid];
+            const int lane_id = tid & 31, w = tid >> 5;
+            st.j = (int64_t)by * nwarp + w;
+            st.t = (int64_t)bx * OWN - H + lane_id;
+            st.live = st.j <= p.ns;
+            st.lam = 0.0; st.bn = 0.0; st.lam_max = 0.0; st.bad = false;
+            if (!st.live) return;
+            const int64_t j = st.j;
+            const int64_t tc = clamp_index(st.t, -(int64_t)GHOST, p.nt + GHOST - 1);
+            if (PCM) {
+                const int64_t rp_ = smap(j), rm_ = smap(j - 1);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) {
+                    st.wp[v] = *p.ws.at(rp_, v, tc); st.wm[v] = *p.ws.at(rm_, v, tc);
+                    st.qp[v] = *p.q.at(rp_, v, tc);  st.qm[v] = *p.q.at(rm_, v, tc);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) { st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
+                cons_of_prim(st.wp, st.qp, gamma);
+                cons_of_prim(st.wm, st.qm, gamma);
+            }
+            physical_flux<AX>(st.wp, st.fp, gamma);
+            physical_flux<AX>(st.wm, st.fm, gamma);
+            if (SOLVER == SOL_HLLD) st.bn = *p.ws.at(smap(j), 5 + SAX, tc);
+            // wave speeds: the per-interface estimate feeds the CFL reduction, LLF also uses it as its dissipation
+            const int64_t jg = j + p.s_off;
+            double lam_here;
+            bool counts;
+            if (PCM) {
+                // pcm.py:30: Jacobian at the padded cells; interface j sees cells b(j-1) and b(j)
+                const double lp = spectral_radius<AX>(st.wp, gamma);
+                lam_here = lp;
+                counts = jg >= 0 && jg < p.ns_glob && j < p.ns;
+                if (LLF) st.lam = npmax(spectral_radius<AX>(st.wm, gamma), lp);
+            } else {
+                double a[NVAR];
+                if (KIND == 1) mean_state(st.wp, st.wm, a); else roe_state(st.wp, st.wm, a);
+                lam_here = spectral_radius<AX>(a, gamma);
+                counts = jg >= 1 && jg <= p.ns_glob && j >= 1;
+                if (LLF) {
+                    // entries j and j+1 of the pad-1 array of interface speeds (solvers.py:73-74)
+                    const int64_t ja = edge ? clamp_index(jg, 1, p.ns_glob) - p.s_off : j;
+                    const int64_t jb = edge ? clamp_index(jg + 1, 1, p.ns_glob) - p.s_off : j + 1;
+                    const double la = (ja == j) ? lam_here : speed_at(ja, tc);
+                    const double lb = (jb == j) ? lam_here : speed_at(jb, tc);
+                    st.lam = npmax(la, lb);
+                }
+            }
+            const bool owned = lane_id >= H && lane_id < 32 - H && st.t >= 0 && st.t < p.nt;
+            if (counts && owned) {
+                if (lam_here == lam_here && lam_here <= 1.7976931348623157e308) st.lam_max = lam_here; else st.bad = true;
+            }
+        });
+        ex.publish_max([&](int k, double& val, bool& bad) { val = tls[k].lam_max; bad = tls[k].bad; }, p.eigmax_bits, p.flag);
+
+        // B: w - d2_t(w)/24, face conversion of q (fv.py:105-122), Riemann flux of the face averages
+        ex.wphase([&](int tid) {
+            Tls& st = tls[tid];
+            double qx[NVAR];
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                st.xp[v] = st.wp[v] - c24 * d2t(tid, st, st.wp[v], [&](int k) { return tls[k].wp[v]; });
+                st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], [&](int k) { return tls[k].wm[v]; });
+            }
+            if (HO) {
+                cons_of_prim(st.xp, qx, gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], [&](int k) { return tls[k].qp[v]; });
+                cons_of_prim(st.xm, qx, gamma);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], [&](int k) { return tls[k].qm[v]; });
+            } else {
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) { st.ap[v] = st.qp[v]; st.am[v] = st.qm[v]; }
+            }
+            if (st.live) solve(st, st.wp, st.wm, st.ap, st.am, st.fp, st.fm, st.fa);
+        });
+        // C: face-centred q and physical flux (solvers.py:47-52), Riemann flux of the centred states
+        ex.wphase([&](int tid) {
+            Tls& st = tls[tid];
+            double cqp[NVAR], cqm[NVAR], cfp[NVAR], cfm[NVAR];
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                cqp[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], [&](int k) { return tls[k].ap[v]; });
+                cqm[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], [&](int k) { return tls[k].am[v]; });
+                cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], [&](int k) { return tls[k].fp[v]; });
+                cfm[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], [&](int k) { return tls[k].fm[v]; });
+            }
+            if (st.live) solve(st, st.xp, st.xm, cqp, cqm, cfp, cfm, st.fc);
+        });
+        // D: F = F_c - d2_t(F_avg)/24 (fv.py:147-153)
+        ex.wphase([&](int tid) {
+            Tls& st = tls[tid];
+            const int lane_id = tid & 31;
+            const bool owned = st.live && lane_id >= H && lane_id < 32 - H && st.t >= 0 && st.t < p.nt;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                const double f = st.fc[v] - c24 * d2t(tid, st, st.fa[v], [&](int k) { return tls[k].fa[v]; });
+                if (owned) *p.f.at(st.j, v, st.t) = f;
+            }
+        });
+    }
+};
+
+}  // namespace astrea

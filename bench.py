@@ -251,19 +251,27 @@ def run_ours(a):
     prof = ctx.profile_read()
     ctx.profile(False)
     total_ms = sum(v[0] for v in prof.values())
-    sweep_ms, sweep_n = prof["sweep"]
     peak, peak_src = load_peaks()
     alg = alg_bytes_per_cell_update(stages)
     sweeps_per_step = stages * dim
-    bytes_per_sweep_launch = cells_per_rank * alg / sweeps_per_step
+    # One sweep = primitive stage + reconstruction stage + flux stage (2D) or the fused sweep kernel (1D); its share
+    # of the algorithmic bytes of a cell-update is 1 / (stages * dimension) (DESIGN.md "Roofline accounting").
+    sweep_ms = prof["flux"][0] + prof["prim"][0] + prof["recon"][0]
+    sweep_n = prof["flux"][1]
+    bytes_per_sweep = cells_per_rank * alg / sweeps_per_step
     sweep_avg_ms = sweep_ms / max(1, sweep_n)
-    achieved = bytes_per_sweep_launch / (sweep_avg_ms * 1e-3) / 1e9
+    achieved = bytes_per_sweep / (sweep_avg_ms * 1e-3) / 1e9
+    flux_avg_ms = prof["flux"][0] / max(1, prof["flux"][1])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "Sweep2D" if dim == 2 else "Sweep1D",
-                "alg_bytes_per_cell_update": alg, "alg_bytes_per_launch": bytes_per_sweep_launch,
+                "peak_source": peak_src,
+                "kernel": "one sweep = PrimStage + ReconStage + FluxStage" if dim == 2 else "Sweep1D",
+                "alg_bytes_per_cell_update": alg, "alg_bytes_per_launch": bytes_per_sweep,
                 "kernel_avg_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
+                "dominant_kernel": {"name": "FluxStage" if dim == 2 else "Sweep1D", "avg_ms": flux_avg_ms,
+                                    "share_of_step": prof["flux"][0] / total_ms if total_ms else None},
                 "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
-                "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak}
+                "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak,
+                "note": "fp64-pipe bound, not HBM bound: see DESIGN.md"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:

@@ -125,8 +125,9 @@ int astrea_save_state(astrea_ctx* ctx);
 int astrea_restore_state(astrea_ctx* ctx);
 
 /* Per-launch timing with CUDA events on the context's stream, summed per kernel class:
- * 0 = sweep kernels, 1 = transpose, 2 = rate assembly + Runge-Kutta update, 3 = halo fill / pack / unpack.
- * astrea_profile_read synchronises, returns the sums since the last read (arrays of 4) and clears them. */
+ * 0 = flux stage (2D) / fused sweep (1D), 1 = transpose, 2 = rate assembly + Runge-Kutta update,
+ * 3 = halo fill / pack / unpack, 4 = primitive stage, 5 = reconstruction stage.
+ * astrea_profile_read synchronises, returns the sums since the last read (arrays of 6) and clears them. */
 int astrea_profile(astrea_ctx* ctx, int enable);
 int astrea_profile_read(astrea_ctx* ctx, double* ms_by_class, int64_t* launches_by_class);
 
