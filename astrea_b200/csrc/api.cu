@@ -10,6 +10,7 @@
 // (evolvers.py:79-206).
 #include "../../include/astrea_b200.h"
 #include "aux_kernels.cuh"
+#include "ct_kernels.cuh"
 #include "dispatch.cuh"
 
 #include <algorithm>
@@ -34,12 +35,15 @@ struct Reg {
 
 // one term of a register update: a state register or a rate buffer, with its literal coefficient
 struct Term { int is_rate; int index; double coef; };
+enum { SP_NONE = 0, SP_FACE_FIELD = 1, SP_REFINE = 2 };
 struct Instr {
-    int is_operator;            // 1: rate[rate_out] = L(reg[src]);   0: reg[out] = combination of terms
+    int is_operator;            // 1: rate[rate_out] = L(reg[src]);   0: reg[out] = combination of terms (or a special)
     int src, rate_out;
     int out, bracket;
     double scale;
     std::vector<Term> terms;
+    int refine = 0;             // magnetic_2d: refine_grid (mag_field.inverse_reconstruct) wraps this update
+    int special = SP_NONE;      // SP_FACE_FIELD: evolvers.py:73-76;  SP_REFINE: refine_grid applied to reg[out]
 };
 
 thread_local std::string g_create_error;
@@ -58,6 +62,8 @@ struct astrea_ctx {
     std::vector<Reg> regs, rates;
     Reg qT, d0, d1t;                  // transposed input of the y sweep; interface fluxes of the x / y sweep (1D: flux difference)
     Reg ws, wp, wm;                   // 2D scratch of the sweep in flight: primitive averages, interface states
+    Reg wfx, wfy, ct0;                // magnetic_2d: face states of the two sweeps (each in its frame), one more scratch
+    double* emf = nullptr;            // magnetic_2d: corner electric field [nrow][ncol]
     unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
     unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
     int* flag = nullptr;              // non-finite wave speed seen in any operator since the last read
@@ -143,29 +149,42 @@ bool alloc_reg(astrea_ctx* c, Reg& r, int64_t ncol) {
 // ---------------------------------------------------------------------------------------- step programs
 // Registers: 0 = u (the grid).  Rates: 0 = L of the most recent operator unless a formula re-uses older ones.
 void add_op(std::vector<Instr>& p, int src, int rate_out) { p.push_back(Instr{1, src, rate_out, 0, 0, 1.0, {}}); }
-void add_comb(std::vector<Instr>& p, int out, double scale, std::vector<Term> t, int bracket = 0) {
-    p.push_back(Instr{0, 0, 0, out, bracket, scale, std::move(t)});
+void add_comb(std::vector<Instr>& p, int out, double scale, std::vector<Term> t, int bracket = 0, int refine = 1) {
+    Instr ins{0, 0, 0, out, bracket, scale, std::move(t)};
+    ins.refine = refine;
+    p.push_back(std::move(ins));
 }
+void add_copy(std::vector<Instr>& p, int out, int src) { add_comb(p, out, 1.0, {Term{0, src, 1.0}}, 0, 0); }
 Term R(int reg, double coef) { return Term{0, reg, coef}; }
 Term L(int rate, double coef) { return Term{1, rate, coef}; }
 
 // evolvers.py:79-206, literal coefficients and evaluation order.  Returns (#registers, #rates).
-void build_program(int integrator, std::vector<Instr>& p, int& nregs, int& nrates, int& final_reg) {
+void build_program(int integrator, bool mhd, std::vector<Instr>& p, int& nregs, int& nrates, int& final_reg) {
     p.clear();
     add_op(p, 0, 0);   // evolve_space on the grid (astrea.py:67)
     switch (integrator) {
-        case INT_SSPRK104: {   // evolvers.py:84-103; u = reg0, k = reg1, k5 = reg2, _k = reg3
-            nregs = 4; nrates = 1;
-            add_comb(p, 1, 1.0, {R(0, 1.0)});                                  // k = copy(grid)
+        case INT_SSPRK104: {   // evolvers.py:84-103; u = reg0, k = reg1, k5 = reg2, _k = reg3, (increment = reg4)
+            nregs = mhd ? 5 : 4; nrates = 1;
+            // k += refine_grid(1/6*dt*L): the refinement acts on the increment, so with magnetic_2d the increment
+            // is formed in its own register first
+            auto increment = [&](int k) {
+                if (mhd) {
+                    add_comb(p, 4, 1.0, {L(0, 1.0 / 6)}, 0, 1);
+                    add_comb(p, k, 1.0, {R(k, 1.0), R(4, 1.0)}, 0, 0);
+                } else {
+                    add_comb(p, k, 1.0, {R(k, 1.0), L(0, 1.0 / 6)});
+                }
+            };
+            add_copy(p, 1, 0);                                                 // k = copy(grid)
             for (int s = 0; s < 5; ++s) {
-                add_comb(p, 1, 1.0, {R(1, 1.0), L(0, 1.0 / 6)});
+                increment(1);
                 add_op(p, 1, 0);
             }
             add_comb(p, 2, 1.0, {R(0, 3.0 / 5), R(1, 6.0 / 15), L(0, 1.0 / 15)});
             add_op(p, 2, 0);
-            add_comb(p, 3, 1.0, {R(2, 1.0)});
+            add_copy(p, 3, 2);
             for (int s = 0; s < 4; ++s) {
-                add_comb(p, 3, 1.0, {R(3, 1.0), L(0, 1.0 / 6)});
+                increment(3);
                 add_op(p, 3, 0);
             }
             add_comb(p, 0, 1.0, {R(0, -11.0 / 35), R(2, 5.0 / 7), R(3, 3.0 / 5), L(0, 1.0 / 10)});
@@ -252,6 +271,23 @@ void build_program(int integrator, std::vector<Instr>& p, int& nregs, int& nrate
             break;
         }
     }
+    if (!mhd) return;
+    // magnetic_2d: the B slots of the grid become face averages before the stages (evolvers.py:73-76) and every
+    // register update is followed by refine_grid (evolvers.py:63-67)
+    std::vector<Instr> q;
+    for (size_t i = 0; i < p.size(); ++i) {
+        q.push_back(p[i]);
+        if (i == 0) {
+            Instr f{0, 0, 0, 0, 0, 1.0, {}};
+            f.special = SP_FACE_FIELD;
+            q.push_back(f);
+        } else if (!p[i].is_operator && p[i].refine) {
+            Instr r{0, 0, 0, p[i].out, 0, 1.0, {}};
+            r.special = SP_REFINE;
+            q.push_back(r);
+        }
+    }
+    p.swap(q);
 }
 
 // ---------------------------------------------------------------------------------------- launches
@@ -272,6 +308,80 @@ int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
             { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st)); }
         }
     }
+    return 0;
+}
+
+int transpose_plane(astrea_ctx* c, Plane src, Plane dst, int64_t src_rows, int64_t src_cols) {
+    TransposeParams t{src, dst, -(int64_t)GHOST, src_rows + GHOST, -(int64_t)GHOST, src_cols + GHOST};
+    const int gx = (int)((src_cols + 2 * GHOST + 31) / 32), gy = (int)((src_rows + 2 * GHOST + 31) / 32);
+    Timed timed(c, CLS_TRANSPOSE);
+    ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st));
+    return 0;
+}
+
+int fill_plane_halo(astrea_ctx* c, Plane pl, int64_t rows, int64_t cols) {
+    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)rows, 64, 0, c->st)); }
+    h.phase = 1;
+    const int gx = (int)((cols + 2 * GHOST + 255) / 256);
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st)); }
+    return 0;
+}
+
+// mag_field.compute_corner (mag_field.py:125-187) from the face states of the two sweeps -> c->emf
+int corner_field(astrea_ctx* c) {
+    const astrea_cfg& g = c->cfg;
+    const int64_t nx = c->nrow, ny = c->ncol;
+    const bool edge = g.boundary == BC_EDGE;
+    // "pad the derived array": ghost cells of the face-state arrays are copies, not reconstructions
+    if (int e = fill_plane_halo(c, c->wfx.plane, nx, ny)) return e;
+    if (int e = fill_plane_halo(c, c->wfy.plane, ny, nx)) return e;
+    auto transverse_ppm = [&](Plane face_t, Plane d, Plane u, int64_t ns, int64_t ns_glob, int64_t s_off, int64_t nt) -> int {
+        ReconStageParams rp{};
+        rp.w = face_t; rp.wp = d; rp.wm = u; rp.wf = Plane{nullptr, 0, 0};
+        rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = 0; rp.c_hi = nt;
+        rp.i_lo = 0; rp.i_hi = edge ? ns - 1 : ns;          // pad(wD)[1:] needs cell ns when periodic
+        rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
+        const int nthreads = 128;
+        const int gx = (int)((nt + nthreads - 1) / nthreads);
+        const int nseg = (int)((rp.i_hi - rp.i_lo + 1 + rp.seg - 1) / rp.seg);
+        Timed timed(c, CLS_RECON);
+        ASTREA_TRY(launch_recon(SCH_PPM, rp, gx, nseg * NVAR, nthreads, c->st));
+        return 0;
+    };
+    // bundle 1: face states of the x sweep, reconstructed along y (in the y frame), then brought to the x frame
+    const Plane t1 = make_plane(c->ws.mem, nx, GHOST), d1y = make_plane(c->wp.mem, nx, GHOST), u1y = make_plane(c->wm.mem, nx, GHOST);
+    if (int e = transpose_plane(c, c->wfx.plane, t1, nx, ny)) return e;
+    if (int e = transverse_ppm(t1, d1y, u1y, ny, ny, 0, nx)) return e;
+    const Plane d1 = make_plane(c->qT.mem, ny, GHOST), u1 = make_plane(c->ws.mem, ny, GHOST);
+    if (int e = transpose_plane(c, d1y, d1, ny, nx)) return e;
+    if (int e = transpose_plane(c, u1y, u1, ny, nx)) return e;
+    // bundle 0: face states of the y sweep, reconstructed along x (x frame)
+    const Plane t0 = make_plane(c->wp.mem, ny, GHOST), d0 = make_plane(c->wm.mem, ny, GHOST), u0 = make_plane(c->ct0.mem, ny, GHOST);
+    if (int e = transpose_plane(c, c->wfy.plane, t0, ny, nx)) return e;
+    if (int e = transverse_ppm(t0, d0, u0, nx, g.nx_global, g.x_offset, ny)) return e;
+    CornerEmfParams ep{d0, u0, d1, u1, c->emf, nx, ny, g.nx_global, g.x_offset, g.gamma, g.boundary, c->parity};
+    Timed timed(c, CLS_UPDATE);
+    ASTREA_TRY(launch<CornerEmfKernel>(ep, (int)((ny + 127) / 128), (int)nx, 128, 0, c->st));
+    return 0;
+}
+
+int run_special(astrea_ctx* c, const Instr& ins) {
+    const astrea_cfg& g = c->cfg;
+    if (ins.special == SP_FACE_FIELD) {
+        FaceFieldParams fp{c->regs[c->grid_reg].plane, c->wfx.plane, c->wfy.plane, c->nrow, c->ncol};
+        Timed timed(c, CLS_UPDATE);
+        ASTREA_TRY(launch<FaceFieldKernel>(fp, (int)((c->ncol + 31) / 32), (int)((c->nrow + 31) / 32), 256, FaceFieldKernel::smem_bytes(), c->st));
+        return 0;
+    }
+    // refine_grid = mag_field.inverse_reconstruct on register `out`
+    Plane reg = c->regs[ins.out].plane;
+    if (int e = fill_halo(c, reg, 0)) return e;
+    RefineFieldParams rp{reg, make_plane(c->ws.mem, c->ncol, GHOST), c->nrow, c->ncol, g.nx_global, g.x_offset, g.boundary, 0};
+    const int gx = (int)((c->ncol + 127) / 128);
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, (int)c->nrow, 128, 0, c->st)); }
+    rp.copy_back = 1;
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, (int)c->nrow, 128, 0, c->st)); }
     return 0;
 }
 
@@ -328,9 +438,12 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 Timed timed(c, CLS_PRIM);
                 ASTREA_TRY(launch<PrimStage>(pp, gx, gy, 256, PrimStage::smem_bytes(pp.high_order), c->st));
             }
+            if (pcm && g.magnetic_2d)      // pcm.py:35: the face state is the cell average
+                ASTREA_TRY(copy_d2d(ax == 0 ? c->wfx.mem : c->wfy.mem, c->ws.mem, c->plane_doubles * sizeof(double), c->st));
             if (!pcm) {
                 ReconStageParams rp{};
                 rp.w = ws; rp.wp = wp; rp.wm = wm; rp.wf = Plane{nullptr, 0, 0};
+                if (g.magnetic_2d) rp.wf = (ax == 0) ? c->wfx.plane : c->wfy.plane;       // data[axes]['wF'] (plm.py:57, ppm.py:101, weno.py:184)
                 rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = -(int64_t)ht; rp.c_hi = nt + ht;
                 rp.i_lo = i_lo; rp.i_hi = i_hi; rp.bc = g.boundary; rp.limiter = g.limiter;
                 rp.seg = g.segment_2d > 0 ? g.segment_2d : 64;
@@ -354,9 +467,12 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
             }
         }
     }
+    if (g.magnetic_2d) {
+        if (int e = corner_field(c)) return e;
+    }
     RateParams r{};
     r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane; r.out = c->rates[ins.rate_out].plane;
-    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = nullptr; r.emf_pitch = 0; r.dx = g.dx; r.bc = g.boundary;
+    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr; r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
     {
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
         { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st)); }
@@ -395,7 +511,14 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
         return -1;
     }
     if (g->integrator < ASTREA_EULER || g->integrator > ASTREA_SSPRK104) { why = "unknown integrator"; return -1; }
-    if (g->magnetic_2d) { why = "magnetic_2d (constrained transport) is not available in this build"; return -1; }
+    if (g->magnetic_2d) {
+        if (g->dimension != 2) { why = "magnetic_2d needs dimension == 2"; return -1; }
+        if (g->solver != ASTREA_HLLC && g->solver != ASTREA_HLLD) {
+            why = "magnetic_2d with a Lax-type solver takes corner speeds from np.linalg.eigvals (mag_field.py:152-159): not on the device path";
+            return -1;
+        }
+        if (g->nx != g->nx_global) { why = "magnetic_2d grids are not decomposed in this build"; return -1; }
+    }
     if (g->dimension == 1) {
         if (g->nx < 1 || g->ny != 1) { why = "1D: nx >= 1 cells, ny == 1"; return -1; }
         if (g->nx_global != g->nx || g->x_offset != 0) { why = "1D grids are not decomposed"; return -1; }
@@ -433,7 +556,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     if (g.dimension == 2) c->plane_doubles = std::max(c->plane_doubles, (size_t)(c->ncol + 2 * GHOST) * NVAR * (size_t)(c->nrow + 2 * GHOST));
 
     int nregs = 1, nrates = 1;
-    build_program(g.integrator, c->prog, nregs, nrates, c->final_reg);
+    build_program(g.integrator, g.magnetic_2d != 0, c->prog, nregs, nrates, c->final_reg);
     bool ok = true;
     c->regs.resize(nregs);
     c->rates.resize(nrates);
@@ -443,6 +566,11 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     if (g.dimension == 2) {
         ok = ok && alloc_reg(c, c->qT, c->nrow) && alloc_reg(c, c->d1t, c->nrow);
         ok = ok && alloc_reg(c, c->ws, c->ncol) && alloc_reg(c, c->wp, c->ncol) && alloc_reg(c, c->wm, c->ncol);
+        if (g.magnetic_2d) {
+            ok = ok && alloc_reg(c, c->wfx, c->ncol) && alloc_reg(c, c->wfy, c->nrow) && alloc_reg(c, c->ct0, c->ncol);
+            c->emf = (double*)dev_alloc(sizeof(double) * (size_t)c->nrow * c->ncol);
+            ok = ok && c->emf;
+        }
     } else {
         ok = ok && alloc_reg(c, c->qT, c->ncol);   // scratch for primitive downloads
     }
@@ -480,6 +608,7 @@ void astrea_destroy(astrea_ctx* c) {
     for (auto& r : c->rates) dev_free(r.mem);
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
     dev_free(c->ws.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
+    dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->stream_owned) cudaStreamDestroy(c->st.s);
@@ -539,7 +668,8 @@ int astrea_run_instr(astrea_ctx* c, int i, int external_rows) {
     if (!c || i < 0 || i >= (int)c->prog.size()) return fail(c, ASTREA_E_ARG, "astrea_run_instr: bad instruction index");
     if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_instr: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
     const Instr& ins = c->prog[i];
-    const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0) : run_combine(c, ins);
+    const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0)
+                                  : (ins.special != SP_NONE ? run_special(c, ins) : run_combine(c, ins));
     if (e) return e;
     c->next_instr = i + 1;
     return 0;
@@ -610,7 +740,23 @@ int astrea_step(astrea_ctx* c, double t, double t_stop, double* dt_out) {
 int astrea_get_parity(const astrea_ctx* c) { return c ? c->parity : ASTREA_E_ARG; }
 int astrea_set_parity(astrea_ctx* c, int p) { if (!c) return ASTREA_E_ARG; c->parity = p & 1; return 0; }
 
-int astrea_download_face_field(astrea_ctx* c, double*) { return fail(c, ASTREA_E_ARG, "magnetic_2d is not available in this build"); }
+int astrea_download_face_field(astrea_ctx* c, double* bxy_aos) {
+    if (!c || !bxy_aos) return fail(c, ASTREA_E_ARG, "astrea_download_face_field: NULL argument");
+    if (!c->cfg.magnetic_2d) return fail(c, ASTREA_E_ARG, "astrea_download_face_field: magnetic_2d is off");
+    // face averages of the last operator, assembled in a scratch plane and unpacked on the host
+    Plane tmp = make_plane(c->ws.mem, c->ncol, GHOST);
+    FaceFieldParams fp{tmp, c->wfx.plane, c->wfy.plane, c->nrow, c->ncol};
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<FaceFieldKernel>(fp, (int)((c->ncol + 31) / 32), (int)((c->nrow + 31) / 32), 256, FaceFieldKernel::smem_bytes(), c->st)); }
+    const size_t n = (size_t)c->nrow * c->ncol;
+    std::vector<double> host(n * NVAR);
+    double* staging = c->wp.mem;
+    PackParams p{tmp, staging, c->nrow, c->ncol, 0};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    ASTREA_TRY(copy_d2h(host.data(), staging, n * NVAR * sizeof(double), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_download_face_field: stream sync failed");
+    for (size_t k = 0; k < n; ++k) { bxy_aos[2 * k] = host[NVAR * k + 5]; bxy_aos[2 * k + 1] = host[NVAR * k + 6]; }
+    return 0;
+}
 
 int astrea_halo_info(const astrea_ctx* c, int64_t* ghost_rows, int64_t* doubles_per_block) {
     if (!c) return ASTREA_E_ARG;

@@ -116,8 +116,8 @@ struct RateParams {
     int64_t nrow, ncol;
     int dimension;
     // constrained transport (evolvers.py:52-58): overwrite the in-plane field rates with emf differences
-    const double* emf;    // corner field [x][y] with ghost ring, or nullptr
-    int64_t emf_pitch;
+    const double* emf;    // corner field [x][y] (pitch ncol), or nullptr
+    int64_t nx_glob, x_off;
     double dx;
     int bc;
 };
@@ -156,9 +156,16 @@ struct RateKernel {
                         total = *p.d0.at(r, v, c);
                     }
                     if (p.emf != nullptr && (v == 5 || v == 6)) {
-                        const double* e = p.emf + r * p.emf_pitch + c;
-                        if (v == 5) total = (e[1] - e[0]) / p.dx;                       // +dE/dy
-                        else total = (-1.0 * (e[p.emf_pitch] - e[0])) / p.dx;           // -dE/dx
+                        // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
+                        const bool wrap = p.bc == BC_WRAP;
+                        const double e0 = p.emf[r * p.ncol + c];
+                        if (v == 5) {
+                            const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
+                            total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
+                        } else {
+                            const int64_t rn = r + 1 < p.nrow ? r + 1 : (wrap ? 0 : p.nrow - 1);
+                            total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
+                        }
                     }
                     *p.out.at(r, v, c) = -total;
                 }

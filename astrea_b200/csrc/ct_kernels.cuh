@@ -1,0 +1,182 @@
+// Constrained transport of the in-plane magnetic field (num_methods/mag_field.py, evolvers.py:26-32,52-58,73-76).
+//
+//   face states (ReconStage ``wf``)  --halo fill = "pad the derived array"-->
+//   transpose --> PPM-mc along the transverse direction (ReconStage<PPM>, cell aligned)   mag_field.py:11-82
+//   CornerEmfKernel: Roe-averaged HLL wave speeds across each corner + upwinded E_z        mag_field.py:125-187
+//   RateKernel (aux_kernels.cuh): dBx/dt = -dE_z/dy, dBy/dt = +dE_z/dx                      evolvers.py:52-58
+//   FaceFieldKernel: B slots of the grid <- face averages, once per step        evolvers.py:73-76
+//   RefineFieldKernel: face-averaged B -> cell-averaged B after every register update        mag_field.py:191-211
+//
+// All kernels here work in the x frame ([x][var][y] planes); arrays produced in the y frame are transposed first.
+#pragma once
+#include "physics.cuh"
+#include "runtime.cuh"
+
+namespace astrea {
+
+// ------------------------------------------------------------------------------------------------ corner E_z
+struct CornerEmfParams {
+    // (wD, wU) of mag_field.reconstruct_transverse, both bundles in the x frame:
+    //   bundle 0: face states of the y sweep reconstructed along x  (swapped_permutations key 0, wave speeds along x)
+    //   bundle 1: face states of the x sweep reconstructed along y  (key 1, wave speeds along y)
+    Plane d0, u0, d1, u1;
+    double* emf;               // out: [nrow][ncol], pitch ncol
+    int64_t nrow, ncol;
+    int64_t nx_glob, x_off;    // 'edge' clamp of the +1 neighbour along x
+    double gamma;
+    int bc, parity;
+};
+struct CornerEmfKernel {
+    using Params = CornerEmfParams;
+    static constexpr int MAX_THREADS = 128;
+    // mag_field.py:128-149 ('hll' branch): a+ = max(0, v_n + c_f), a- = -min(0, v_n - c_f) at the Roe average
+    template <int AXIS>
+    static HD void speeds(const double* plus, const double* minus, double gamma, double& ap, double& am) {
+        double avg[NVAR];
+        roe_state(plus, minus, avg);
+        const double rho = avg[0], P = avg[4];
+        const double vn = avg[1 + AXIS], Bn = avg[5 + AXIS];
+        const double a = sqrt(gamma * sdiv(P, rho));
+        const double sr = sqrt(rho);
+        const double b = sdiv(norm3(avg[5], avg[6], avg[7]), sr);
+        const double bn = sdiv(Bn, sr);
+        const double cf = sqrt(0.5 * (a * a + b * b + sqrt(sq(a * a + b * b) - (4.0 * (a * a) * (bn * bn)))));
+        ap = npmax(0.0, vn + cf);
+        am = -npmin(0.0, vn - cf);
+    }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t j = (int64_t)bx * NT + tid, i = by;
+            if (j >= p.ncol) return;
+            const bool edge = p.bc == BC_EDGE;
+            // pad(wD)[1:]: the +1 neighbour along the reconstruction direction (ghost data when periodic / interior)
+            const int64_t in = edge ? clamp_index(i + 1 + p.x_off, 0, p.nx_glob - 1) - p.x_off : i + 1;
+            const int64_t jn = edge ? clamp_index(j + 1, 0, p.ncol - 1) : j + 1;
+            double D0[NVAR], U0[NVAR], D1[NVAR], U1[NVAR], nb[NVAR];
+            double ap0, am0, ap1, am1;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) { U0[v] = *p.u0.at(i, v, j); nb[v] = *p.d0.at(in, v, j); }
+            speeds<0>(nb, U0, p.gamma, ap0, am0);
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) { U1[v] = *p.u1.at(i, v, j); nb[v] = *p.d1.at(i, v, jn); }
+            speeds<1>(nb, U1, p.gamma, ap1, am1);
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) { D0[v] = *p.d0.at(i, v, j); D1[v] = *p.d1.at(i, v, j); }
+            // mag_field.py:164-185 unpacks by iteration order of the (reversed every step) permutations
+            const double* north = p.parity ? D1 : D0;
+            const double* south = p.parity ? U1 : U0;
+            const double* east = p.parity ? D0 : D1;
+            const double* west = p.parity ? U0 : U1;
+            const double ap_y = p.parity ? ap1 : ap0, am_y = p.parity ? am1 : am0;
+            const double ap_x = p.parity ? ap0 : ap1, am_x = p.parity ? am0 : am1;
+            const double NE = 0.5 * (west[2] + south[2]) * south[5] - 0.5 * (west[1] + south[1]) * west[6];
+            const double NW = 0.5 * (east[2] + south[2]) * south[5] - 0.5 * (east[1] + south[1]) * east[6];
+            const double SE = 0.5 * (west[2] + north[2]) * north[5] - 0.5 * (west[1] + north[1]) * west[6];
+            const double SW = 0.5 * (east[2] + north[2]) * north[5] - 0.5 * (east[1] + north[1]) * east[6];
+            const double e = sdiv(ap_x * ap_y * SW + am_x * ap_y * SE + ap_x * am_y * NW + am_x * am_y * NE, (ap_x + am_x) * (ap_y + am_y))
+                           - sdiv(ap_y * am_y, ap_y + am_y) * (north[5] - south[5])
+                           + sdiv(ap_x * am_x, ap_x + am_x) * (east[6] - west[6]);
+            p.emf[i * p.ncol + j] = e;
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ face field
+struct FaceFieldParams {
+    Plane grid;        // in/out: components 5 and 6 are overwritten
+    Plane wfx;         // face states of the x sweep, x frame
+    Plane wfy;         // face states of the y sweep, y frame
+    int64_t nrow, ncol;
+};
+struct FaceFieldKernel {
+    using Params = FaceFieldParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TILE = 32;
+    static size_t smem_bytes() { return sizeof(double) * TILE * (TILE + 1); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        double* tile = ex.smem();
+        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        ex.phase([&](int tid) {
+            const int tx = tid % TILE;
+            for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                const int64_t yr = c0 + ty, xc = r0 + tx;
+                if (yr < p.ncol && xc < p.nrow) tile[ty * (TILE + 1) + tx] = *p.wfy.at(yr, 6, xc);
+            }
+        });
+        ex.phase([&](int tid) {
+            const int tx = tid % TILE;
+            for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                const int64_t r = r0 + ty, c = c0 + tx;
+                if (r >= p.nrow || c >= p.ncol) continue;
+                *p.grid.at(r, 5, c) = *p.wfx.at(r, 5, c);
+                *p.grid.at(r, 6, c) = tile[tx * (TILE + 1) + ty];
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ refine (inverse reconstruct)
+struct RefineFieldParams {
+    Plane in;          // register with face-averaged Bx, By in components 5, 6 (ghost filled)
+    Plane out;         // components 5, 6 receive the cell averages (a scratch plane; copied back by CopyFieldKernel)
+    int64_t nrow, ncol;
+    int64_t nx_glob, x_off;
+    int bc;
+    int copy_back;     // 1: this launch copies out -> in instead
+};
+struct RefineFieldKernel {
+    using Params = RefineFieldParams;
+    static constexpr int MAX_THREADS = 128;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t j = (int64_t)bx * NT + tid, i = by;
+            if (j >= p.ncol) return;
+            if (p.copy_back) {
+                *p.in.at(i, 5, j) = *p.out.at(i, 5, j);
+                *p.in.at(i, 6, j) = *p.out.at(i, 6, j);
+                return;
+            }
+            const bool edge = p.bc == BC_EDGE;
+            const double c24 = 1.0 / 24.0;
+            auto mx = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.x_off, 0, p.nx_glob - 1) - p.x_off : r; };
+            auto my = [&](int64_t c) -> int64_t { return edge ? clamp_index(c, 0, p.ncol - 1) : c; };
+            // Bx: sweep direction x (rows), transverse y.  mag_field.py:199-207 in the x frame.
+            {
+                auto g = [&](int64_t r, int64_t c) { return *p.in.at(r, 5, c); };
+                auto fc = [&](int64_t r, int64_t c) {      // fv.high_order_convert('avg', ., 'face'): x - d2_y/24
+                    const double a = g(r, c);
+                    return a - c24 * ((g(r, my(c + 1)) - a) - (a - g(r, my(c - 1))));
+                };
+                auto cc = [&](int64_t r, int64_t c) {      // 4-point face -> centre interpolation along x
+                    return -1.0 / 16.0 * (fc(mx(r - 1), c) + fc(mx(r + 2), c)) + 9.0 / 16.0 * (fc(r, c) + fc(mx(r + 1), c));
+                };
+                const double a = cc(i, j);
+                double ca = a + c24 * ((cc(mx(i + 1), j) - a) - (a - cc(mx(i - 1), j)));
+                ca = ca + c24 * ((cc(i, my(j + 1)) - a) - (a - cc(i, my(j - 1))));
+                *p.out.at(i, 5, j) = ca;
+            }
+            // By: sweep direction y (columns), transverse x: the same in the transposed frame (axis 0 = y first)
+            {
+                auto g = [&](int64_t r, int64_t c) { return *p.in.at(r, 6, c); };
+                auto fc = [&](int64_t r, int64_t c) {
+                    const double a = g(r, c);
+                    return a - c24 * ((g(mx(r + 1), c) - a) - (a - g(mx(r - 1), c)));
+                };
+                auto cc = [&](int64_t r, int64_t c) {
+                    return -1.0 / 16.0 * (fc(r, my(c - 1)) + fc(r, my(c + 2))) + 9.0 / 16.0 * (fc(r, c) + fc(r, my(c + 1)));
+                };
+                const double a = cc(i, j);
+                double ca = a + c24 * ((cc(i, my(j + 1)) - a) - (a - cc(i, my(j - 1))));
+                ca = ca + c24 * ((cc(mx(i + 1), j) - a) - (a - cc(mx(i - 1), j)));
+                *p.out.at(i, 6, j) = ca;
+            }
+        });
+    }
+};
+
+}  // namespace astrea

@@ -106,6 +106,7 @@ struct ReconStageParams {
     int64_t c_lo, c_hi;        // half-open column range to process
     int64_t i_lo, i_hi;        // inclusive range of cells to reconstruct (local indices)
     int bc, limiter, seg;
+    int cell_aligned;          // 1: wp / wm receive wL / wR of cell i at row i (transverse reconstruction of mag_field.py)
 };
 
 // accessor over the register stencil: logical offset k relative to the cell, identity boundary map
@@ -160,6 +161,11 @@ struct ReconStage {
                 } else {
                     StencilAccessor<LO> acc{r};
                     cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf);
+                }
+                if (p.cell_aligned) {
+                    *p.wp.at(i, v, t) = wl;
+                    *p.wm.at(i, v, t) = wr;
+                    continue;
                 }
                 // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
                 *p.wp.at(i, v, t) = wl;

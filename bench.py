@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the per-timestep finite-volume update (BASELINE.json metric: cell-updates/s, fp64, per RK step).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
 
 A "step" is one full Runge-Kutta step (all stages) of every cell of the workload.  Default workload (N=1) is
 BASELINE config 2: Lax-Liu 3, 2048^2, PPM + HLLC, SSPRK(3,3), periodic.  With N > 1 (torchrun, one rank per GPU)
@@ -36,6 +36,7 @@ WORKLOADS = {
     "c1": ("sod", 1024, 1, "plm", "lf", "ssprk(2,2)", "1D Sod 1024 PLM+minmod+LLF SSPRK(2,2) edge"),
     "c2": ("ll3", 2048, 2, "ppm", "hllc", "ssprk(3,3)", "2D Lax-Liu 3 2048^2 PPM+HLLC SSPRK(3,3) periodic"),
     "c3": ("khi", 4096, 2, "weno5", "hllc", "ssprk(3,3)", "2D Kelvin-Helmholtz 4096^2 WENO5+HLLC SSPRK(3,3) periodic"),
+    "c4": ("orszag-tang", 4096, 2, "plm", "hlld", "ssprk(3,3)", "2D MHD Orszag-Tang 4096^2 PLM+HLLD + constrained transport SSPRK(3,3) periodic"),
     "c5": ("ll6", 8192, 2, "ppm", "hllc", "ssprk(3,3)", "2D Lax-Liu 6 8192^2 per GPU PPM+HLLC SSPRK(3,3) periodic"),
 }
 MAX_HORIZON = 8
@@ -106,8 +107,9 @@ def _oracle_sample(args):
     from astrea_b200.initial import initial_state, problem
     from oracle import OracleConfig, advance
     prob = problem(config, cells, 1.4)
+    from astrea_b200.selectors import MAGNETIC_2D
     cfg = OracleConfig(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
-                       boundary=prob["boundary"], dx=prob["dx"], eigen=eigen)
+                       boundary=prob["boundary"], dx=prob["dx"], eigen=eigen, magnetic_2d=config in MAGNETIC_2D)
     g0 = initial_state(config, cells, dim, 1.4, cfg.high_order)
     t0 = time.perf_counter()
     g, dts = advance(g0, cfg, steps)
@@ -336,7 +338,7 @@ def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
         cells = a.cells or cells
         perms = {0: (0, 1)} if dim == 1 else {0: (0, 1, 2), 1: (1, 0, 2)}
         sv0 = SV(dim, cells, sim.boundary, sim.gamma, sim.dx, sim.cfl, subgrid, solver, "hll" if solver.startswith("hll") else "lax",
-                 timestep, False, perms)
+                 timestep, sim.magnetic_2d, perms)
 
         def one_pass():
             sv, grid = sv0, ic_np

@@ -12,7 +12,7 @@ from cases import run_native, run_oracle
 from astrea_b200.initial import initial_state, problem
 
 pytestmark = pytest.mark.gpu
-HYDRO = sorted(c for c, m in golden_index().items() if not m["magnetic_2d"])
+HYDRO = sorted(golden_index())      # every golden case, constrained-transport MHD included
 
 
 @pytest.fixture(scope="module")
@@ -51,10 +51,10 @@ def test_golden_all_steps_bit_exact_vs_oracle(lib, cid):
     assert used == dts and np.array_equal(got, want, equal_nan=True), "within tolerance but not bit-identical"
 
 
-def _meta(config, cells, dim, subgrid, solver, timestep, bc):
+def _meta(config, cells, dim, subgrid, solver, timestep, bc, mhd=False):
     prob = problem(config, cells, 1.4)
     return dict(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
-                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=False)
+                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=mhd)
 
 
 MATRIX = [(cfg, sub, sol, bc, dim)
@@ -75,6 +75,41 @@ def test_scheme_solver_matrix(lib, config, subgrid, solver, bc, dim):
     got, used, _ = run_native(lib, meta, g0, 2, segment_2d=37)
     assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
     assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+MHD = [("orszag-tang", "plm", "hlld", "ssprk(3,3)", "wrap"), ("orszag-tang", "ppm", "hlld", "ssprk(3,3)", "wrap"),
+       ("orszag-tang", "weno5", "hllc", "ssprk(2,2)", "wrap"), ("orszag-tang", "pcm", "hlld", "euler", "wrap"),
+       ("mhd rotor", "plm", "hlld", "ssprk(3,3)", "wrap"), ("orszag-tang", "plm", "hlld", "ssprk(10,4)", "wrap"),
+       ("orszag-tang", "weno3", "hlld", "ssprk(5,3)", "edge"), ("orszag-tang", "weno7", "hlld", "ssprk(5,4)", "wrap"),
+       ("orszag-tang", "plm", "hllc", "rk4", "edge"), ("orszag-tang", "ppm", "hlld", "ssprk(4,3)", "edge")]
+
+
+@pytest.mark.parametrize("config,subgrid,solver,timestep,bc", MHD, ids=["-".join(m) for m in MHD])
+def test_constrained_transport(lib, config, subgrid, solver, timestep, bc):
+    """BASELINE config 4 family (magnetic_2d): 150^2 (ragged against every tile), 3 steps (odd-step role swap, Q1b)."""
+    cells = 150
+    meta = _meta(config, cells, 2, subgrid, solver, timestep, bc, mhd=True)
+    high = subgrid.startswith("w") or subgrid == "ppm"
+    g0 = initial_state(config, cells, 2, 1.4, high, boundary=bc)
+    want, dts = run_oracle(meta, g0, 3)
+    got, used, _ = run_native(lib, meta, g0, 3)
+    assert np.isfinite(want).all()
+    assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
+    assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+def test_orszag_tang_full_size_properties(lib):
+    """BASELINE config 4 at 4096^2 is beyond the oracle: (a) div B of the face field stays at round-off, (b) the
+    result is independent of the launch geometry, (c) mass, momentum and energy totals are conserved to round-off."""
+    cells = 1024
+    meta = _meta("orszag-tang", cells, 2, "plm", "hlld", "ssprk(3,3)", None, mhd=True)
+    g0 = initial_state("orszag-tang", cells, 2, 1.4, False)
+    a, dts, _ = run_native(lib, meta, g0, 2)
+    b, _, _ = run_native(lib, meta, g0, 2, segment_2d=100, threads_2d=64)
+    assert np.array_equal(a, b)
+    scale = np.abs(g0).sum(axis=(0, 1))
+    drift = np.abs(a.sum(axis=(0, 1)) - g0.sum(axis=(0, 1)))
+    assert np.all(drift[[0, 1, 2, 4]] <= 1e-11 * np.where(scale > 0, scale, 1)[[0, 1, 2, 4]])
 
 
 @pytest.mark.parametrize("timestep", ["euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"])

@@ -12,7 +12,7 @@ from conftest import golden_case, golden_index, rel_l1
 from cases import run_native, run_oracle
 from astrea_b200.initial import initial_state, problem
 
-HYDRO = sorted(c for c, m in golden_index().items() if not m["magnetic_2d"])
+HYDRO = sorted(golden_index())      # every golden case, constrained-transport MHD included
 
 
 @pytest.mark.parametrize("cid", HYDRO)
@@ -38,10 +38,10 @@ def test_golden_cases_vs_reference(hostsim_lib, cid):
         assert np.allclose(e, ref, rtol=1e-11, atol=0)
 
 
-def _meta(config, cells, dim, subgrid, solver, timestep, bc):
+def _meta(config, cells, dim, subgrid, solver, timestep, bc, mhd=False):
     prob = problem(config, cells, 1.4)
     return dict(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep,
-                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=False)
+                boundary=bc or prob["boundary"], dx=prob["dx"], gamma=1.4, cfl=.5, magnetic_2d=mhd)
 
 
 # every scheme x solver, both boundary modes, odd sizes, with the grid cut into many blocks
@@ -62,6 +62,67 @@ def test_scheme_solver_matrix_multiblock(hostsim_lib, config, subgrid, solver, b
     got, used, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=32, segment_2d=11, tile_1d=13)
     assert used == dts
     assert np.array_equal(got, want, equal_nan=True)
+
+
+# constrained transport (magnetic_2d): every scheme, both HLL solvers, both boundary modes, every integrator family
+MHD = [("orszag-tang", "plm", "hlld", "ssprk(3,3)", "wrap"), ("orszag-tang", "ppm", "hlld", "ssprk(3,3)", "wrap"),
+       ("orszag-tang", "weno5", "hllc", "ssprk(2,2)", "wrap"), ("orszag-tang", "pcm", "hlld", "euler", "wrap"),
+       ("mhd rotor", "plm", "hlld", "ssprk(3,3)", "wrap"), ("orszag-tang", "plm", "hlld", "ssprk(10,4)", "wrap"),
+       ("orszag-tang", "weno3", "hlld", "ssprk(5,3)", "edge"), ("orszag-tang", "weno7", "hlld", "ssprk(5,4)", "wrap"),
+       ("orszag-tang", "plm", "hllc", "rk4", "edge"), ("orszag-tang", "ppm", "hlld", "ssprk(4,3)", "edge")]
+
+
+@pytest.mark.parametrize("config,subgrid,solver,timestep,bc", MHD, ids=["-".join(m) for m in MHD])
+def test_constrained_transport(hostsim_lib, config, subgrid, solver, timestep, bc):
+    """mag_field.py: transverse PPM to the corners, upwinded corner E_z, induction update, face-average overwrite
+    (Q14) and inverse reconstruction after every register update — two steps, so that the odd-step role swap of
+    SURVEY Q1b is exercised."""
+    cells = 26
+    meta = _meta(config, cells, 2, subgrid, solver, timestep, bc, mhd=True)
+    high = subgrid.startswith("w") or subgrid == "ppm"
+    g0 = initial_state(config, cells, 2, 1.4, high, boundary=bc)
+    want, dts = run_oracle(meta, g0, 2)
+    got, used, _ = run_native(hostsim_lib, meta, g0, 2, segment_2d=9)
+    assert np.isfinite(want).all()
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_mhd_blast_raises_like_the_reference(hostsim_lib):
+    """The reference's MHD blast run dies of LinAlgError in its first step (negative pressure -> NaN wave speed)."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle import advance
+    meta = _meta("mhd blast", 24, 2, "plm", "hlld", "ssprk(2,2)", None, mhd=True)
+    g0 = initial_state("mhd blast", 24, 2, 1.4, False)
+    with pytest.raises(np.linalg.LinAlgError):
+        advance(np.copy(g0), oracle_cfg(meta), 2)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.step()
+        ctx.step()
+        ctx.read_eigmax()
+    ctx.close()
+
+
+def test_face_field_download(hostsim_lib):
+    """evolve_time overwrites Bx, By of the caller's grid with the face averages of the stage-1 operator (Q14)."""
+    import ctypes
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle import space_operator
+    meta = _meta("orszag-tang", 20, 2, "plm", "hlld", "ssprk(3,3)", None, mhd=True)
+    g0 = initial_state("orszag-tang", 20, 2, 1.4, False)
+    fl = space_operator(np.copy(g0), oracle_cfg(meta))
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    ctx.evolve_space(0)
+    out = np.empty((20, 20, 2))
+    ctx._check(ctx.lib.astrea_download_face_field(ctx._h, out.ctypes.data))
+    ctx.close()
+    assert np.array_equal(out[..., 0], fl[0]["face_avg"][..., 5])
+    assert np.array_equal(out[..., 1], fl[1]["face_avg"].transpose(1, 0, 2)[..., 6])
 
 
 INTEGRATORS = ["euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"]
