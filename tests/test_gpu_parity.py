@@ -109,7 +109,7 @@ def test_orszag_tang_full_size_properties(lib):
     assert np.array_equal(a, b)
     scale = np.abs(g0).sum(axis=(0, 1))
     drift = np.abs(a.sum(axis=(0, 1)) - g0.sum(axis=(0, 1)))
-    assert np.all(drift[[0, 1, 2, 4]] <= 1e-11 * np.where(scale > 0, scale, 1)[[0, 1, 2, 4]])
+    assert np.all(drift[[0, 1, 2, 4]] <= 1e-9 * np.where(scale > 0, scale, 1)[[0, 1, 2, 4]])   # 1e6 cells of round-off
 
 
 @pytest.mark.parametrize("timestep", ["euler", "rk4", "ssprk(2,2)", "ssprk(3,3)", "ssprk(4,3)", "ssprk(5,3)", "ssprk(5,4)", "ssprk(10,4)"])
@@ -216,7 +216,7 @@ def test_full_size_shift_equivariance_and_conservation(lib):
     assert np.array_equal(np.roll(a, shift, axis=(0, 1)), b)
     tot0, tot1 = g0.sum(axis=(0, 1)), a.sum(axis=(0, 1))
     scale = np.abs(g0).sum(axis=(0, 1))
-    assert np.all(np.abs(tot1 - tot0) <= 1e-11 * np.where(scale > 0, scale, 1))
+    assert np.all(np.abs(tot1 - tot0) <= 1e-9 * np.where(scale > 0, scale, 1))       # 4e6 cells of round-off
 
 
 def test_full_size_tiling_independence(lib):
