@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEVICE_LIB = os.path.join(_HERE, "lib", "libastrea_b200.so")
+# ASTREA_B200_LIB: path of an alternative *device* build (kernel-tuning experiments); still refused unless sm_100a
+DEVICE_LIB = os.environ.get("ASTREA_B200_LIB") or os.path.join(_HERE, "lib", "libastrea_b200.so")
 
 # enums of include/astrea_b200.h
 PCM, PLM, PPM, WENO3, WENO5, WENO7 = range(6)
@@ -28,7 +29,7 @@ class Cfg(C.Structure):
         ("scheme", C.c_int32), ("ppm_author", C.c_int32), ("limiter", C.c_int32), ("solver", C.c_int32),
         ("low_mach", C.c_int32), ("integrator", C.c_int32), ("magnetic_2d", C.c_int32), ("device", C.c_int32),
         ("nx_global", C.c_int64), ("x_offset", C.c_int64),
-        ("threads_2d", C.c_int32), ("segment_2d", C.c_int32), ("tile_1d", C.c_int32), ("reserved", C.c_int32),
+        ("threads_2d", C.c_int32), ("segment_2d", C.c_int32), ("tile_1d", C.c_int32), ("flags", C.c_int32),
     ]
 
 

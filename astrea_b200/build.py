@@ -46,15 +46,19 @@ def _run(cmd, verbose):
     return res.stdout + res.stderr
 
 
-def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None):
-    """Compile every translation unit (in parallel) and link the shared library.  Returns its path."""
+def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None, variant=None, defines=()):
+    """Compile every translation unit (in parallel) and link the shared library.  Returns its path.
+    ``variant`` / ``defines``: a tuning build with extra -D flags, written to astrea_b200/lib/variants/<variant>.so."""
     lib = HOSTSIM_LIB if hostsim else DEVICE_LIB
     objdir = os.path.join(ROOT, "build", "hostsim" if hostsim else "sm_100a")
+    if variant:
+        lib = os.path.join(ROOT, "astrea_b200", "lib", "variants", variant + ".so")
+        objdir = os.path.join(ROOT, "build", "variant_" + variant)
     os.makedirs(objdir, exist_ok=True)
     os.makedirs(os.path.dirname(lib), exist_ok=True)
     heads = _headers()
     compiler = "g++" if hostsim else os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = list(GXX_FLAGS if hostsim else NVCC_FLAGS)
+    flags = list(GXX_FLAGS if hostsim else NVCC_FLAGS) + ["-D" + d for d in defines]
     if ptxas_info and not hostsim:
         flags += ["-Xptxas", "-v"]
     objs, todo = [], []
@@ -84,6 +88,8 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--ptxas-info", action="store_true")
+    ap.add_argument("--variant", default=None)
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build(a.hostsim, a.force, a.verbose, a.ptxas_info))
+    print(build(a.hostsim, a.force, a.verbose, a.ptxas_info, variant=a.variant, defines=a.defines))
     sys.exit(0)

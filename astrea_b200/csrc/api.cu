@@ -64,6 +64,10 @@ struct astrea_ctx {
     Reg ws, wp, wm;                   // 2D scratch of the sweep in flight: primitive averages, interface states
     Reg wfx, wfy, ct0;                // magnetic_2d: face states of the two sweeps (each in its frame), one more scratch
     double* emf = nullptr;            // magnetic_2d: corner electric field [nrow][ncol]
+    // hydro specialisation (physics.cuh): the uploaded grid has no v_z / B, so only [rho, m_x, m_y, E] are processed
+    bool hydro = false, saved_hydro = false;
+    int* mhd_flag = nullptr;          // device: set by the upload when a v_z / B component is non-zero
+    VarList vars() const { return hydro ? hydro_vars() : all_vars(); }
     unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
     unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
     int* flag = nullptr;              // non-finite wave speed seen in any operator since the last read
@@ -292,7 +296,7 @@ void build_program(int integrator, bool mhd, std::vector<Instr>& p, int& nregs, 
 
 // ---------------------------------------------------------------------------------------- launches
 int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
-    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1};
+    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, c->vars()};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     if (c->ghost_r > 0) {
         h.phase = 1;
@@ -312,7 +316,7 @@ int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
 }
 
 int transpose_plane(astrea_ctx* c, Plane src, Plane dst, int64_t src_rows, int64_t src_cols) {
-    TransposeParams t{src, dst, -(int64_t)GHOST, src_rows + GHOST, -(int64_t)GHOST, src_cols + GHOST};
+    TransposeParams t{src, dst, -(int64_t)GHOST, src_rows + GHOST, -(int64_t)GHOST, src_cols + GHOST, all_vars()};
     const int gx = (int)((src_cols + 2 * GHOST + 31) / 32), gy = (int)((src_rows + 2 * GHOST + 31) / 32);
     Timed timed(c, CLS_TRANSPOSE);
     ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st));
@@ -320,7 +324,7 @@ int transpose_plane(astrea_ctx* c, Plane src, Plane dst, int64_t src_rows, int64
 }
 
 int fill_plane_halo(astrea_ctx* c, Plane pl, int64_t rows, int64_t cols) {
-    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1};
+    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1, all_vars()};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)rows, 64, 0, c->st)); }
     h.phase = 1;
     const int gx = (int)((cols + 2 * GHOST + 255) / 256);
@@ -342,6 +346,8 @@ int corner_field(astrea_ctx* c) {
         rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = 0; rp.c_hi = nt;
         rp.i_lo = 0; rp.i_hi = edge ? ns - 1 : ns;          // pad(wD)[1:] needs cell ns when periodic
         rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
+        rp.nvar = NVAR;
+        for (int k = 0; k < NVAR; ++k) rp.vars[k] = k;
         const int nthreads = 128;
         const int gx = (int)((nt + nthreads - 1) / nthreads);
         const int nseg = (int)((rp.i_hi - rp.i_lo + 1 + rp.seg - 1) / rp.seg);
@@ -401,7 +407,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
         // sweep order and the solver's private axis counter (solvers.py:34-36,63; astrea.py:85)
         const int order[2] = {c->parity ? 1 : 0, c->parity ? 0 : 1};
         // the y sweep works on the transposed copy of the (ghost-filled) register
-        TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST};
+        TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST, c->vars()};
         {
             const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
             { Timed timed(c, CLS_TRANSPOSE); ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st)); }
@@ -433,10 +439,11 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 pp.q = qf; pp.w = ws; pp.gamma = g.gamma; pp.high_order = ho ? 1 : 0;
                 pp.r_lo = -(int64_t)(lo + 1); pp.r_hi = ns + hi + 2; pp.c_lo = -(int64_t)ht; pp.c_hi = nt + ht;
                 pp.r_min = -(int64_t)GHOST; pp.r_max = ns + GHOST - 1; pp.c_min = -(int64_t)GHOST; pp.c_max = nt + GHOST - 1;
-                const int gx = (int)((pp.c_hi - pp.c_lo + PrimStage::TX - 1) / PrimStage::TX);
-                const int gy = (int)((pp.r_hi - pp.r_lo + PrimStage::TY - 1) / PrimStage::TY);
+                const int gx = (int)((pp.c_hi - pp.c_lo + PrimStage<false>::TX - 1) / PrimStage<false>::TX);
+                const int gy = (int)((pp.r_hi - pp.r_lo + PrimStage<false>::TY - 1) / PrimStage<false>::TY);
                 Timed timed(c, CLS_PRIM);
-                ASTREA_TRY(launch<PrimStage>(pp, gx, gy, 256, PrimStage::smem_bytes(pp.high_order), c->st));
+                if (c->hydro) ASTREA_TRY(launch<PrimStage<true>>(pp, gx, gy, 256, PrimStage<true>::smem_bytes(pp.high_order), c->st));
+                else ASTREA_TRY(launch<PrimStage<false>>(pp, gx, gy, 256, PrimStage<false>::smem_bytes(pp.high_order), c->st));
             }
             if (pcm && g.magnetic_2d)      // pcm.py:35: the face state is the cell average
                 ASTREA_TRY(copy_d2d(ax == 0 ? c->wfx.mem : c->wfy.mem, c->ws.mem, c->plane_doubles * sizeof(double), c->st));
@@ -447,11 +454,14 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = -(int64_t)ht; rp.c_hi = nt + ht;
                 rp.i_lo = i_lo; rp.i_hi = i_hi; rp.bc = g.boundary; rp.limiter = g.limiter;
                 rp.seg = g.segment_2d > 0 ? g.segment_2d : 64;
+                const VarList vl = c->vars();
+                rp.nvar = vl.n;
+                for (int k = 0; k < NVAR; ++k) rp.vars[k] = vl.v[k];
                 const int nthreads = 128;
                 const int gx = (int)((rp.c_hi - rp.c_lo + nthreads - 1) / nthreads);
                 const int nseg = (int)((i_hi - i_lo + 1 + rp.seg - 1) / rp.seg);
                 Timed timed(c, CLS_RECON);
-                ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * NVAR, nthreads, c->st));
+                ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * rp.nvar, nthreads, c->st));
             }
             {
                 FluxStageParams fp{};
@@ -463,7 +473,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 const int own = 32 - 2 * ht, nwarp = nthreads / 32;
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
                 Timed timed(c, CLS_SWEEP);
-                ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, fp, gx, gy, nthreads, c->st));
+                ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, c->hydro ? 1 : 0, fp, gx, gy, nthreads, c->st));
             }
         }
     }
@@ -473,6 +483,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     RateParams r{};
     r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane; r.out = c->rates[ins.rate_out].plane;
     r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr; r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
+    r.vars = c->vars();
     {
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
         { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st)); }
@@ -494,6 +505,7 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
     p.scale = ins.scale;
     p.dt = c->dt_dev;
     p.nrow = c->nrow; p.ncol = c->ncol;
+    p.vars = c->vars();
     const int gx = (int)((c->ncol + 255) / 256);
     { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st)); }
     return 0;
@@ -574,6 +586,8 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     } else {
         ok = ok && alloc_reg(c, c->qT, c->ncol);   // scratch for primitive downloads
     }
+    c->mhd_flag = (int*)dev_alloc(sizeof(int));
+    ok = ok && c->mhd_flag;
     c->eig_bits = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
     c->flag = (int*)dev_alloc(sizeof(int));
     c->dt_dev = (double*)dev_alloc(sizeof(double));
@@ -609,7 +623,7 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
     dev_free(c->ws.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
-    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem);
+    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->stream_owned) cudaStreamDestroy(c->st.s);
 #endif
@@ -623,10 +637,16 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
     double* staging = c->d0.mem;     // d0 is scratch between operator evaluations
     ASTREA_TRY(copy_h2d(staging, grid_aos, bytes, c->st));
-    PackParams p{c->regs[c->grid_reg].plane, staging, c->nrow, c->ncol, 1};
+    ASTREA_TRY(dev_zero(c->mhd_flag, sizeof(int), c->st));
+    PackParams p{c->regs[c->grid_reg].plane, staging, c->nrow, c->ncol, 1, c->mhd_flag};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     c->next_instr = 0;
-    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_upload: stream sync failed");
+    int has_field = 1;
+    ASTREA_TRY(copy_d2h(&has_field, c->mhd_flag, sizeof(int), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_upload: stream sync failed");
+    // 2D hydro with LLF / HLLC: v_z and B stay identically zero, the kernels skip them (bit-identical results)
+    c->hydro = !has_field && c->cfg.dimension == 2 && !c->cfg.magnetic_2d && c->cfg.solver != SOL_HLLD && !(c->cfg.flags & 1);
+    return 0;
 }
 
 int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
@@ -644,7 +664,7 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     }
     const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
     double* staging = c->d0.mem;
-    PackParams p{src, staging, c->nrow, c->ncol, 0};
+    PackParams p{src, staging, c->nrow, c->ncol, 0, nullptr};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     ASTREA_TRY(copy_d2h(grid_aos, staging, bytes, c->st));
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_download: stream sync failed");
@@ -750,7 +770,7 @@ int astrea_download_face_field(astrea_ctx* c, double* bxy_aos) {
     const size_t n = (size_t)c->nrow * c->ncol;
     std::vector<double> host(n * NVAR);
     double* staging = c->wp.mem;
-    PackParams p{tmp, staging, c->nrow, c->ncol, 0};
+    PackParams p{tmp, staging, c->nrow, c->ncol, 0, nullptr};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     ASTREA_TRY(copy_d2h(host.data(), staging, n * NVAR * sizeof(double), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_download_face_field: stream sync failed");
@@ -780,7 +800,7 @@ int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, d
 
 int astrea_halo_prepare(astrea_ctx* c, int i) {
     if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: not an operator instruction");
-    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0};
+    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars()};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     return 0;
 }
@@ -813,6 +833,7 @@ int astrea_save_state(astrea_ctx* c) {
     if (!c->saved.mem && !alloc_reg(c, c->saved, c->ncol)) return fail(c, ASTREA_E_CUDA, "astrea_save_state: device allocation failed");
     ASTREA_TRY(copy_d2d(c->saved.mem, c->regs[c->grid_reg].mem, c->plane_doubles * sizeof(double), c->st));
     c->saved_parity = c->parity;
+    c->saved_hydro = c->hydro;
     return 0;
 }
 
@@ -822,6 +843,7 @@ int astrea_restore_state(astrea_ctx* c) {
     ASTREA_TRY(copy_d2d(c->regs[c->grid_reg].mem, c->saved.mem, c->plane_doubles * sizeof(double), c->st));
     ASTREA_TRY(dev_zero(c->flag, sizeof(int), c->st));
     c->parity = c->saved_parity;
+    c->hydro = c->saved_hydro;
     c->next_instr = 0;
     return 0;
 }

@@ -17,6 +17,7 @@ struct PackParams {
     double* aos;          // device staging buffer, (nrow, ncol, 8) C-order
     int64_t nrow, ncol;
     int to_plane;         // 1: aos -> plane, 0: plane -> aos
+    int* mhd_flag;        // to_plane: set to 1 if any v_z / B component is non-zero (nullptr: do not check)
 };
 struct PackKernel {
     using Params = PackParams;
@@ -32,6 +33,7 @@ struct PackKernel {
             for (int v = 0; v < NVAR; ++v) {
                 if (p.to_plane) *p.plane.at(r, v, c) = a[v]; else a[v] = *p.plane.at(r, v, c);
             }
+            if (p.to_plane && p.mhd_flag != nullptr && (a[3] != 0.0 || a[5] != 0.0 || a[6] != 0.0 || a[7] != 0.0)) *p.mhd_flag = 1;
         });
     }
 };
@@ -43,6 +45,7 @@ struct HaloParams {
     int bc;
     int phase;            // 0: ghost columns of interior rows, 1: ghost rows (full padded width, corners included)
     int fill_lo, fill_hi; // phase 1: which row ghosts to fill locally (0 when a neighbour rank provides them)
+    VarList vars;
 };
 struct HaloKernel {
     using Params = HaloParams;
@@ -55,14 +58,16 @@ struct HaloKernel {
             if (p.phase == 0) {
                 // by = row, threads over the 2*GHOST ghost columns x NVAR
                 const int64_t r = by;
-                for (int e = tid; e < 2 * GHOST * NVAR; e += NT) {
-                    const int v = e / (2 * GHOST), g = e % (2 * GHOST);
+                for (int e = tid; e < 2 * GHOST * p.vars.n; e += NT) {
+                    const int v = p.vars.v[e / (2 * GHOST)], g = e % (2 * GHOST);
                     const int64_t c = g < GHOST ? g - GHOST : p.ncol + (g - GHOST);
                     *p.plane.at(r, v, c) = *p.plane.at(r, v, src(c, p.ncol, p.bc));
                 }
             } else {
                 // by = ghost row id (0..2*GHOST-1) x var, threads over padded columns
-                const int g = by / NVAR, v = by % NVAR;
+                const int g = by / NVAR;
+                if (by % NVAR >= p.vars.n) return;
+                const int v = p.vars.v[by % NVAR];
                 const bool lo = g < GHOST;
                 if ((lo && !p.fill_lo) || (!lo && !p.fill_hi)) return;
                 const int64_t r = lo ? g - GHOST : p.nrow + (g - GHOST);
@@ -78,6 +83,7 @@ struct HaloKernel {
 struct TransposeParams {
     Plane src, dst;       // dst(row = c, col = r) = src(row = r, col = c), ghosts included
     int64_t r_lo, r_hi, c_lo, c_hi;   // half-open ranges of src rows / cols to move
+    VarList vars;
 };
 struct TransposeKernel {
     using Params = TransposeParams;
@@ -88,7 +94,8 @@ struct TransposeKernel {
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
         double* tile = ex.smem();
         const int64_t c0 = p.c_lo + (int64_t)bx * TILE, r0 = p.r_lo + (int64_t)by * TILE;
-        for (int v = 0; v < NVAR; ++v) {
+        for (int a = 0; a < p.vars.n; ++a) {
+            const int v = p.vars.v[a];
             ex.phase([&](int tid) {
                 const int tx = tid % TILE;
                 for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
@@ -120,6 +127,7 @@ struct RateParams {
     int64_t nx_glob, x_off;
     double dx;
     int bc;
+    VarList vars;
 };
 struct RateKernel {
     using Params = RateParams;
@@ -130,7 +138,8 @@ struct RateKernel {
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
         double* tile = ex.smem();
         const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
-        for (int v = 0; v < NVAR; ++v) {
+        for (int a = 0; a < p.vars.n; ++a) {
+            const int v = p.vars.v[a];
             if (p.dimension == 2) {
                 ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
                     const int tx = tid % TILE;
@@ -190,6 +199,7 @@ struct CombineParams {
     double scale;         // 1.0 = no scaling
     const double* dt;     // device scalar
     int64_t nrow, ncol;
+    VarList vars;
 };
 struct CombineKernel {
     using Params = CombineParams;
@@ -202,8 +212,8 @@ struct CombineKernel {
             const int64_t r = by;
             if (c >= p.ncol) return;
             const double dt = *p.dt;
-#pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
+            for (int a = 0; a < p.vars.n; ++a) {
+                const int v = p.vars.v[a];
                 double acc = 0.0;
                 if (!p.bracket_rates) {
                     for (int k = 0; k < p.nterms; ++k) {

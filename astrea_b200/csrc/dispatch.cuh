@@ -10,36 +10,38 @@ namespace astrea {
 int launch_sweep1d(int scheme, int solver, const Sweep1DParams& p, int nthreads, Stream st);
 int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthreads, Stream st);
 // kind: 0 = PCM, 1 = pointwise face conversion (PLM), 2 = 4th-order face conversion (PPM / WENO)
-int launch_flux(int kind, int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
-int launch_flux_pcm(int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
-int launch_flux_plm(int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
-int launch_flux_ho(int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
+// hydro: 1 = the state has no v_z / B (LLF and HLLC only), see physics.cuh
+int launch_flux(int kind, int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
+int launch_flux_pcm(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
+int launch_flux_plm(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
+int launch_flux_ho(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
 
 // Body of one inst_flux_*.cu
 #define ASTREA_DEFINE_FLUX(NAME, KIND)                                                                               \
     template <int SOL, int AX, int SAX>                                                                              \
-    static int runflux_##NAME(const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {                   \
-        return launch<FluxStage<KIND, SOL, AX, SAX>>(p, gx, gy, nthreads, 0, st);                                    \
+    static int runflux_##NAME(int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {        \
+        if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD>>(p, gx, gy, nthreads, 0, st);        \
+        return launch<FluxStage<KIND, SOL, AX, SAX, false>>(p, gx, gy, nthreads, 0, st);                             \
     }                                                                                                                \
-    int launch_flux_##NAME(int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
+    int launch_flux_##NAME(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
         const int key = ax * 2 + sax;                                                                                \
         switch (solver) {                                                                                            \
             case SOL_LLF: /* LLF ignores the solver axis (solvers.py:69) */                                          \
-                return ax == 0 ? runflux_##NAME<SOL_LLF, 0, 0>(p, gx, gy, nthreads, st)                              \
-                               : runflux_##NAME<SOL_LLF, 1, 1>(p, gx, gy, nthreads, st);                             \
+                return ax == 0 ? runflux_##NAME<SOL_LLF, 0, 0>(hydro, p, gx, gy, nthreads, st)                       \
+                               : runflux_##NAME<SOL_LLF, 1, 1>(hydro, p, gx, gy, nthreads, st);                      \
             case SOL_HLLC:                                                                                           \
                 switch (key) {                                                                                       \
-                    case 0: return runflux_##NAME<SOL_HLLC, 0, 0>(p, gx, gy, nthreads, st);                          \
-                    case 1: return runflux_##NAME<SOL_HLLC, 0, 1>(p, gx, gy, nthreads, st);                          \
-                    case 2: return runflux_##NAME<SOL_HLLC, 1, 0>(p, gx, gy, nthreads, st);                          \
-                    default: return runflux_##NAME<SOL_HLLC, 1, 1>(p, gx, gy, nthreads, st);                         \
+                    case 0: return runflux_##NAME<SOL_HLLC, 0, 0>(hydro, p, gx, gy, nthreads, st);                   \
+                    case 1: return runflux_##NAME<SOL_HLLC, 0, 1>(hydro, p, gx, gy, nthreads, st);                   \
+                    case 2: return runflux_##NAME<SOL_HLLC, 1, 0>(hydro, p, gx, gy, nthreads, st);                   \
+                    default: return runflux_##NAME<SOL_HLLC, 1, 1>(hydro, p, gx, gy, nthreads, st);                  \
                 }                                                                                                    \
             case SOL_HLLD:                                                                                           \
                 switch (key) {                                                                                       \
-                    case 0: return runflux_##NAME<SOL_HLLD, 0, 0>(p, gx, gy, nthreads, st);                          \
-                    case 1: return runflux_##NAME<SOL_HLLD, 0, 1>(p, gx, gy, nthreads, st);                          \
-                    case 2: return runflux_##NAME<SOL_HLLD, 1, 0>(p, gx, gy, nthreads, st);                          \
-                    default: return runflux_##NAME<SOL_HLLD, 1, 1>(p, gx, gy, nthreads, st);                         \
+                    case 0: return runflux_##NAME<SOL_HLLD, 0, 0>(0, p, gx, gy, nthreads, st);                       \
+                    case 1: return runflux_##NAME<SOL_HLLD, 0, 1>(0, p, gx, gy, nthreads, st);                       \
+                    case 2: return runflux_##NAME<SOL_HLLD, 1, 0>(0, p, gx, gy, nthreads, st);                       \
+                    default: return runflux_##NAME<SOL_HLLD, 1, 1>(0, p, gx, gy, nthreads, st);                      \
                 }                                                                                                    \
             default: return -1;                                                                                      \
         }                                                                                                            \

@@ -11,11 +11,11 @@ int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthr
         default: return -1;
     }
 }
-int launch_flux(int kind, int solver, int ax, int sax, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {
+int launch_flux(int kind, int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {
     switch (kind) {
-        case 0: return launch_flux_pcm(solver, ax, sax, p, gx, gy, nthreads, st);
-        case 1: return launch_flux_plm(solver, ax, sax, p, gx, gy, nthreads, st);
-        default: return launch_flux_ho(solver, ax, sax, p, gx, gy, nthreads, st);
+        case 0: return launch_flux_pcm(solver, ax, sax, hydro, p, gx, gy, nthreads, st);
+        case 1: return launch_flux_plm(solver, ax, sax, hydro, p, gx, gy, nthreads, st);
+        default: return launch_flux_ho(solver, ax, sax, hydro, p, gx, gy, nthreads, st);
     }
 }
 }

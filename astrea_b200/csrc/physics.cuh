@@ -57,6 +57,62 @@ HD void mean_state(const double* a, const double* b, double* out) {   // plm.py:
     for (int v = 0; v < NVAR; ++v) out[v] = 0.5 * (a[v] + b[v]);
 }
 
+// ---------------------------------------------------------------------------------------------- hydro specialisation
+// A state whose v_z and B are identically zero keeps them zero under every operation of the path (each such term is
+// a product with an exact zero), and dropping those terms does not change a bit of the other components: x + 0 and
+// x - 0 are exact.  The H = true variants below touch only [rho, v_x|m_x, v_y|m_y, P|E]; the context selects them
+// when the uploaded grid has no v_z / B (api.cu), which is the case for every hydrodynamic 2D configuration.
+template <bool H> struct VarSet;
+template <> struct VarSet<false> { static constexpr int N = 8; static HD constexpr int at(int a) { return a; } };
+template <> struct VarSet<true> { static constexpr int N = 4; static HD constexpr int at(int a) { return a < 3 ? a : 4; } };
+
+HD double norm2sq(double a, double b) { double n = sqrt(a * a + b * b); return n * n; }
+
+template <bool H>
+HD void prim_of_cons_t(const double* q, double* w, double gamma) {
+    if (!H) { prim_of_cons(q, w, gamma); return; }
+    const double rho = q[0];
+    const double vx = sdiv(q[1], rho), vy = sdiv(q[2], rho);
+    w[0] = rho; w[1] = vx; w[2] = vy;
+    w[4] = (gamma - 1.0) * (q[4] - 0.5 * (rho * norm2sq(vx, vy)));
+}
+
+template <bool H>
+HD void cons_of_prim_t(const double* w, double* q, double gamma) {
+    if (!H) { cons_of_prim(w, q, gamma); return; }
+    const double rho = w[0];
+    q[0] = rho; q[1] = w[1] * rho; q[2] = w[2] * rho;
+    q[4] = w[4] / (gamma - 1.0) + 0.5 * (rho * norm2sq(w[1], w[2]));
+}
+
+template <int AX, bool H>
+HD void physical_flux_t(const double* w, double* f, double gamma) {
+    if (!H) { physical_flux<AX>(w, f, gamma); return; }
+    constexpr int n = AX, t = 1 - AX;          // in-plane normal / transverse component
+    const double rho = w[0], p = w[4], vn = w[1 + n];
+    f[0] = rho * vn;
+    f[1 + n] = rho * (vn * vn) + p;
+    f[1 + t] = rho * vn * w[1 + t];
+    f[4] = vn * (0.5 * rho * norm2sq(w[1], w[2]) + (gamma * p) / (gamma - 1.0));
+}
+
+template <bool H>
+HD void roe_state_t(const double* first, const double* second, double* out) {
+    if (!H) { roe_state(first, second, out); return; }
+    const double s2 = sqrt(second[0]), s1 = sqrt(first[0]);
+    const double den = s2 + s1;
+    out[0] = s2 * s1;
+    out[1] = sdiv(first[1] * s1 + second[1] * s2, den);
+    out[2] = sdiv(first[2] * s1 + second[2] * s2, den);
+    out[4] = sdiv(s1 * first[4] + s2 * second[4], den);
+}
+
+template <bool H>
+HD void mean_state_t(const double* a, const double* b, double* out) {
+#pragma unroll
+    for (int k = 0; k < VarSet<H>::N; ++k) { const int v = VarSet<H>::at(k); out[v] = 0.5 * (a[v] + b[v]); }
+}
+
 // max |lambda| of the primitive Jacobian (constructor.py:129-163) at state w along AX, in closed form.
 // The spectrum is {0, v, v +- sqrt(x)} for x in {c_a^2, c_f^2, c_s^2}, with c_a^2 = Bn^2/rho and c_f^2, c_s^2 the
 // roots of x^2 - (a^2 + b^2) x + a^2 c_a^2.  For a physical state all x >= 0 and the maximum is |v| + c_f.  The
@@ -87,6 +143,17 @@ HD double spectral_radius(const double* w, double gamma) {
         return npmax(sqrt((vn + al) * (vn + al) + be * be), wave_modulus(vn, bn2));
     }
     return disc;        // NaN
+}
+
+// B == 0: a^2 = gamma P / rho is the only non-zero root (c_f^2 = a^2 if a^2 >= 0, else c_s^2 = a^2 < 0)
+template <int AX, bool H>
+HD double spectral_radius_t(const double* w, double gamma) {
+    if (!H) return spectral_radius<AX>(w, gamma);
+    const double a2 = gamma * w[4] / w[0];
+    const double vn = fabs(w[1 + AX]);
+    if (a2 >= 0.0) return vn + sqrt(a2);
+    if (a2 < 0.0) return npmax(vn, sqrt(vn * vn + (-a2)));
+    return a2;          // NaN
 }
 
 }  // namespace astrea

@@ -3,7 +3,7 @@
 // ``plus`` = state on the right of the interface, ``minus`` = state on its left.  SAX is the *solver* axis, the
 // reference's private 0,1 counter (solvers.py:34-36,63), which is not the sweep axis on odd steps.
 #pragma once
-#include "common.cuh"
+#include "physics.cuh"
 
 namespace astrea {
 
@@ -11,10 +11,16 @@ HD void llf_flux(double lam, const double* qp, const double* qm, const double* f
 #pragma unroll
     for (int v = 0; v < NVAR; ++v) out[v] = 0.5 * (fm[v] + fp[v]) - 0.5 * ((qp[v] - qm[v]) * lam);
 }
+template <bool H>
+HD void llf_flux_t(double lam, const double* qp, const double* qm, const double* fp, const double* fm, double* out) {
+#pragma unroll
+    for (int k = 0; k < VarSet<H>::N; ++k) { const int v = VarSet<H>::at(k); out[v] = 0.5 * (fm[v] + fp[v]) - 0.5 * ((qp[v] - qm[v]) * lam); }
+}
 
-template <int SAX>
+template <int SAX, bool H = false>
 HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* wm, const double* qp, const double* qm,
                   const double* fp, const double* fm, double* out) {
+    constexpr int NV = VarSet<H>::N;
     const double rL = wm[0], uL = wm[1 + SAX], pL = wm[4];
     const double rR = wp[0], uR = wp[1 + SAX], pR = wp[4];
     const double cL = sqrt(gamma * sdiv(pL, rL)), cR = sqrt(gamma * sdiv(pR, rR));
@@ -37,12 +43,13 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
     // later masks override earlier ones (solvers.py:135-137)
     if (sup || !(useL || useR)) {
 #pragma unroll
-        for (int v = 0; v < NVAR; ++v) out[v] = fp[v];
+        for (int k = 0; k < NV; ++k) { const int v = VarSet<H>::at(k); out[v] = fp[v]; }
         return;
     }
     if (useR) {
 #pragma unroll
-        for (int v = 0; v < NVAR; ++v) {
+        for (int k = 0; k < NV; ++k) {
+            const int v = VarSet<H>::at(k);
             double qs = qp[v] * kR;
             if (v == 1) qs = rR * kR * sM;
             if (v == 4) qs = qs + kR * (sM - uR) * (rR * sM + sdiv(pR, sR - uR));
@@ -51,7 +58,8 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
         return;
     }
 #pragma unroll
-    for (int v = 0; v < NVAR; ++v) {
+    for (int k = 0; k < NV; ++k) {
+        const int v = VarSet<H>::at(k);
         double qs = qm[v] * kL;
         if (v == 1) qs = rL * kL * sM;
         if (v == 4) qs = qs + kL * (sM - uL) * (rL * sM + sdiv(pL, sL - uL));

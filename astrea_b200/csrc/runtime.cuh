@@ -85,8 +85,14 @@ struct DeviceExec {
     }
 };
 
+// resident blocks per SM the register allocation should allow: K::MIN_BLOCKS when the kernel declares it, else 1
+template <class K, class = void>
+struct min_blocks_of { static constexpr int value = 0; };   // 0 = let ptxas choose (same as omitting the argument)
 template <class K>
-__global__ void __launch_bounds__(K::MAX_THREADS) kernel_entry(const typename K::Params p) {
+struct min_blocks_of<K, decltype((void)K::MIN_BLOCKS)> { static constexpr int value = K::MIN_BLOCKS; };
+
+template <class K>
+__global__ void __launch_bounds__(K::MAX_THREADS, min_blocks_of<K>::value) kernel_entry(const typename K::Params p) {
     DeviceExec ex;
     K::block(p, (int)blockIdx.x, (int)blockIdx.y, ex);
 }

@@ -34,8 +34,10 @@ struct PrimStageParams {
     double gamma;
     int high_order;
 };
+template <bool HYDRO>
 struct PrimStage {
     using Params = PrimStageParams;
+    using VS = VarSet<HYDRO>;
     static constexpr int MAX_THREADS = 256;
     static constexpr int TX = 32, TY = 8, SX = TX + 2, SY = TY + 2;
     static size_t smem_bytes(int high_order) { return high_order ? sizeof(double) * 2 * NVAR * SX * SY : 0; }
@@ -49,10 +51,10 @@ struct PrimStage {
                 if (c >= p.c_hi || r >= p.r_hi) return;
                 double q[NVAR], w[NVAR];
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) q[v] = *p.q.at(r, v, c);
-                prim_of_cons(q, w, gamma);
+                for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); q[v] = *p.q.at(r, v, c); }
+                prim_of_cons_t<HYDRO>(q, w, gamma);
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) *p.w.at(r, v, c) = w[v];
+                for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); *p.w.at(r, v, c) = w[v]; }
             });
             return;
         }
@@ -64,10 +66,10 @@ struct PrimStage {
                 const int64_t c = clamp_index(c0 - 1 + x, p.c_min, p.c_max), r = clamp_index(r0 - 1 + y, p.r_min, p.r_max);
                 double q[NVAR], w[NVAR];
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) q[v] = *p.q.at(r, v, c);
-                prim_of_cons(q, w, gamma);
+                for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); q[v] = *p.q.at(r, v, c); }
+                prim_of_cons_t<HYDRO>(q, w, gamma);
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) { Q[(v * SY + y) * SX + x] = q[v]; W[(v * SY + y) * SX + x] = w[v]; }
+                for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); Q[(v * SY + y) * SX + x] = q[v]; W[(v * SY + y) * SX + x] = w[v]; }
             }
         });
         ex.phase([&](int tid) {
@@ -78,7 +80,8 @@ struct PrimStage {
             double qa[NVAR], w[NVAR], ws[NVAR];
             // fv.py:134-142: axis 0 of the sweep frame first, then the transverse axis
 #pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
+            for (int k = 0; k < VS::N; ++k) {
+                const int v = VS::at(k);
                 const double* q = Q + v * SY * SX;
                 const double* w0 = W + v * SY * SX;
                 const double qc = q[y * SX + x], wc = w0[y * SX + x];
@@ -89,9 +92,9 @@ struct PrimStage {
                 qa[v] = a;
                 ws[v] = s;
             }
-            prim_of_cons(qa, w, gamma);
+            prim_of_cons_t<HYDRO>(qa, w, gamma);
 #pragma unroll
-            for (int v = 0; v < NVAR; ++v) *p.w.at(r, v, c) = w[v] + ws[v];
+            for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); *p.w.at(r, v, c) = w[v] + ws[v]; }
         });
     }
 };
@@ -107,6 +110,8 @@ struct ReconStageParams {
     int64_t i_lo, i_hi;        // inclusive range of cells to reconstruct (local indices)
     int bc, limiter, seg;
     int cell_aligned;          // 1: wp / wm receive wL / wR of cell i at row i (transverse reconstruction of mag_field.py)
+    int nvar;                  // variables to reconstruct (8, or 4 for a hydro state) and their indices
+    int vars[NVAR];
 };
 
 // accessor over the register stencil: logical offset k relative to the cell, identity boundary map
@@ -128,6 +133,9 @@ template <int SCHEME>
 struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
+#ifdef ASTREA_RECON_MIN_BLOCKS
+    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;
+#endif
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
@@ -137,8 +145,8 @@ struct ReconStage {
         ex.phase([&](int tid) {
             const int64_t t = p.c_lo + (int64_t)bx * NT + tid;
             if (t >= p.c_hi) return;
-            const int v = by % NVAR;
-            const int64_t first = p.i_lo + (int64_t)(by / NVAR) * p.seg;
+            const int v = p.vars[by % p.nvar];
+            const int64_t first = p.i_lo + (int64_t)(by / p.nvar) * p.seg;
             int64_t last = first + p.seg - 1;
             if (last > p.i_hi) last = p.i_hi;
             if (first > last) return;
@@ -148,10 +156,12 @@ struct ReconStage {
             double r[NW];
 #pragma unroll
             for (int k = 0; k < NW - 1; ++k) r[k + 1] = col[(first - LO + k) * rp];
+            double ahead = col[(first + HI) * rp];           // row i + HI, requested one iteration early
             for (int64_t i = first; i <= last; ++i) {
 #pragma unroll
                 for (int k = 0; k < NW - 1; ++k) r[k] = r[k + 1];
-                r[NW - 1] = col[(i + HI) * rp];
+                r[NW - 1] = ahead;
+                if (i < last) ahead = col[(i + 1 + HI) * rp];
                 const int64_t ig = i + p.s_off;
                 double wl, wr, wf;
                 if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
@@ -194,10 +204,16 @@ struct FluxStageParams {
 // KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)
 // MEAN: arithmetic mean (PLM) instead of the Roe average for the wave-speed state.  AX = physical sweep axis,
 // SAX = the solver's axis argument.
-template <int KIND, int SOLVER, int AX, int SAX>
+// HYDRO: v_z and B are identically zero, only [rho, v_x, v_y, P] are processed (physics.cuh).
+template <int KIND, int SOLVER, int AX, int SAX, bool HYDRO = false>
 struct FluxStage {
     using Params = FluxStageParams;
+    using VS = VarSet<HYDRO>;
     static constexpr int MAX_THREADS = 128;
+#ifndef ASTREA_FLUX_MIN_BLOCKS
+#define ASTREA_FLUX_MIN_BLOCKS 4
+#endif
+    static constexpr int MIN_BLOCKS = ASTREA_FLUX_MIN_BLOCKS;      // 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5)
     static constexpr bool HO = KIND == 2, PCM = KIND == 0;
     static constexpr int H = HO ? 2 : 1;            // halo lanes on each side of a warp
     static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
@@ -227,9 +243,9 @@ struct FluxStage {
         auto smap = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.s_off, 0, p.ns_glob - 1) - p.s_off : r; };
         auto solve = [&](const Tls& st, const double* wp, const double* wm, const double* qp, const double* qm, const double* fp,
                          const double* fm, double* out) {
-            if (SOLVER == SOL_HLLC) hllc_flux<SAX>(gamma, p.low_mach != 0, wp, wm, qp, qm, fp, fm, out);
+            if (SOLVER == SOL_HLLC) hllc_flux<SAX, HYDRO>(gamma, p.low_mach != 0, wp, wm, qp, qm, fp, fm, out);
             else if (SOLVER == SOL_HLLD) hlld_flux<SAX>(gamma, st.bn, wp, wm, qp, qm, fp, fm, out);
-            else llf_flux(st.lam, qp, qm, fp, fm, out);
+            else llf_flux_t<HYDRO>(st.lam, qp, qm, fp, fm, out);
         };
         // transverse second difference of a per-thread array member produced in an earlier phase; the neighbour of
         // a point on a physical 'edge' boundary is the point itself ("pad the derived array")
@@ -247,13 +263,14 @@ struct FluxStage {
             double a[NVAR], x[NVAR], y[NVAR];
             if (PCM) {
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) a[v] = *p.ws.at(jj, v, tc);
+                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); a[v] = *p.ws.at(jj, v, tc); }
             } else {
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) { x[v] = *p.wp.at(jj, v, tc); y[v] = *p.wm.at(jj, v, tc); }
-                if (KIND == 1) mean_state(x, y, a); else roe_state(x, y, a);
+                for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv); x[v] = *p.wp.at(jj, v, tc); y[v] = *p.wm.at(jj, v, tc); }
+                if (KIND == 1) mean_state_t<HYDRO>(x, y, a); else roe_state_t<HYDRO>(x, y, a);
             }
-            return spectral_radius<AX>(a, gamma);
+            return spectral_radius_t<AX, HYDRO>(a, gamma);
         };
 
         // A: load the interface states, pointwise conversions, wave speed
@@ -270,18 +287,20 @@ struct FluxStage {
             if (PCM) {
                 const int64_t rp_ = smap(j), rm_ = smap(j - 1);
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) {
+                for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
                     st.wp[v] = *p.ws.at(rp_, v, tc); st.wm[v] = *p.ws.at(rm_, v, tc);
                     st.qp[v] = *p.q.at(rp_, v, tc);  st.qm[v] = *p.q.at(rm_, v, tc);
                 }
             } else {
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) { st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
-                cons_of_prim(st.wp, st.qp, gamma);
-                cons_of_prim(st.wm, st.qm, gamma);
+                for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv); st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
+                cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma);
+                cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma);
             }
-            physical_flux<AX>(st.wp, st.fp, gamma);
-            physical_flux<AX>(st.wm, st.fm, gamma);
+            physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma);
+            physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma);
             if (SOLVER == SOL_HLLD) st.bn = *p.ws.at(smap(j), 5 + SAX, tc);
             // wave speeds: the per-interface estimate feeds the CFL reduction, LLF also uses it as its dissipation
             const int64_t jg = j + p.s_off;
@@ -289,14 +308,14 @@ struct FluxStage {
             bool counts;
             if (PCM) {
                 // pcm.py:30: Jacobian at the padded cells; interface j sees cells b(j-1) and b(j)
-                const double lp = spectral_radius<AX>(st.wp, gamma);
+                const double lp = spectral_radius_t<AX, HYDRO>(st.wp, gamma);
                 lam_here = lp;
                 counts = jg >= 0 && jg < p.ns_glob && j < p.ns;
-                if (LLF) st.lam = npmax(spectral_radius<AX>(st.wm, gamma), lp);
+                if (LLF) st.lam = npmax(spectral_radius_t<AX, HYDRO>(st.wm, gamma), lp);
             } else {
                 double a[NVAR];
-                if (KIND == 1) mean_state(st.wp, st.wm, a); else roe_state(st.wp, st.wm, a);
-                lam_here = spectral_radius<AX>(a, gamma);
+                if (KIND == 1) mean_state_t<HYDRO>(st.wp, st.wm, a); else roe_state_t<HYDRO>(st.wp, st.wm, a);
+                lam_here = spectral_radius_t<AX, HYDRO>(a, gamma);
                 counts = jg >= 1 && jg <= p.ns_glob && j >= 1;
                 if (LLF) {
                     // entries j and j+1 of the pad-1 array of interface speeds (solvers.py:73-74)
@@ -319,20 +338,22 @@ struct FluxStage {
             Tls& st = tls[tid];
             double qx[NVAR];
 #pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
                 st.xp[v] = st.wp[v] - c24 * d2t(tid, st, st.wp[v], [&](int k) { return tls[k].wp[v]; });
                 st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], [&](int k) { return tls[k].wm[v]; });
             }
             if (HO) {
-                cons_of_prim(st.xp, qx, gamma);
+                cons_of_prim_t<HYDRO>(st.xp, qx, gamma);
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], [&](int k) { return tls[k].qp[v]; });
-                cons_of_prim(st.xm, qx, gamma);
+                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], [&](int k) { return tls[k].qp[v]; }); }
+                cons_of_prim_t<HYDRO>(st.xm, qx, gamma);
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], [&](int k) { return tls[k].qm[v]; });
+                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], [&](int k) { return tls[k].qm[v]; }); }
             } else {
 #pragma unroll
-                for (int v = 0; v < NVAR; ++v) { st.ap[v] = st.qp[v]; st.am[v] = st.qm[v]; }
+                for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv); st.ap[v] = st.qp[v]; st.am[v] = st.qm[v]; }
             }
             if (st.live) solve(st, st.wp, st.wm, st.ap, st.am, st.fp, st.fm, st.fa);
         });
@@ -341,7 +362,8 @@ struct FluxStage {
             Tls& st = tls[tid];
             double cqp[NVAR], cqm[NVAR], cfp[NVAR], cfm[NVAR];
 #pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
                 cqp[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], [&](int k) { return tls[k].ap[v]; });
                 cqm[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], [&](int k) { return tls[k].am[v]; });
                 cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], [&](int k) { return tls[k].fp[v]; });
@@ -355,7 +377,8 @@ struct FluxStage {
             const int lane_id = tid & 31;
             const bool owned = st.live && lane_id >= H && lane_id < 32 - H && st.t >= 0 && st.t < p.nt;
 #pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
                 const double f = st.fc[v] - c24 * d2t(tid, st, st.fa[v], [&](int k) { return tls[k].fa[v]; });
                 if (owned) *p.f.at(st.j, v, st.t) = f;
             }

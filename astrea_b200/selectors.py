@@ -85,7 +85,7 @@ def stages_of(integrator):
 
 def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cfl, subgrid, solver, timestep,
              solver_category_name=None, magnetic_2d=False, limiter="minmod", low_mach=False, device=0,
-             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0):
+             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False):
     cfg = N.Cfg()
     cfg.dimension = int(dimension)
     cfg.boundary = boundary_enum(boundary)
@@ -103,6 +103,7 @@ def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cf
     cfg.nx_global = int(nx_global if nx_global is not None else cfg.nx)
     cfg.x_offset = int(x_offset)
     cfg.threads_2d, cfg.segment_2d, cfg.tile_1d = int(threads_2d), int(segment_2d), int(tile_1d)
+    cfg.flags = 1 if general_path else 0      # keep the 8-variable kernels for a grid without v_z / B (testing)
     return cfg
 
 

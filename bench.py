@@ -157,7 +157,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -307,7 +307,7 @@ def run_ours(a):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        OUT.emit(json.dumps(line))
     sim.close()
     evolvers.release()
     if world > 1:
@@ -380,7 +380,31 @@ def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
             else "Context.upload + Simulation.step + Context.download per rank", "timer": "host wall clock around synchronised calls"}
 
 
+class StdoutToStderr:
+    """Libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout.  Everything but
+    the final line goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -392,10 +416,11 @@ def main():
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     a = ap.parse_args()
-    if a.impl == "reference":
-        run_reference_arm(a)
-    else:
-        run_ours(a)
+    with StdoutToStderr() as OUT:
+        if a.impl == "reference":
+            run_reference_arm(a)
+        else:
+            run_ours(a)
 
 
 if __name__ == "__main__":

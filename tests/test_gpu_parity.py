@@ -75,6 +75,10 @@ def test_scheme_solver_matrix(lib, config, subgrid, solver, bc, dim):
     got, used, _ = run_native(lib, meta, g0, 2, segment_2d=37)
     assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
     assert np.allclose(used, dts, rtol=1e-13, atol=0)
+    if dim == 2:
+        # the same through the general 8-variable kernels (a grid without v_z / B normally takes the hydro variants)
+        gen, used, _ = run_native(lib, meta, g0, 2, segment_2d=37, general_path=True)
+        assert np.array_equal(gen, got, equal_nan=True)
 
 
 MHD = [("orszag-tang", "plm", "hlld", "ssprk(3,3)", "wrap"), ("orszag-tang", "ppm", "hlld", "ssprk(3,3)", "wrap"),

@@ -62,6 +62,11 @@ def test_scheme_solver_matrix_multiblock(hostsim_lib, config, subgrid, solver, b
     got, used, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=32, segment_2d=11, tile_1d=13)
     assert used == dts
     assert np.array_equal(got, want, equal_nan=True)
+    if dim == 2:
+        # the same through the general 8-variable kernels (a grid without v_z / B normally takes the hydro variants)
+        got, used, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=32, segment_2d=11, general_path=True)
+        assert used == dts
+        assert np.array_equal(got, want, equal_nan=True)
 
 
 # constrained transport (magnetic_2d): every scheme, both HLL solvers, both boundary modes, every integrator family
