@@ -53,6 +53,11 @@ _SIGNATURES = {
     "astrea_evolve_space": (C.c_int, [C.c_void_p, C.c_int, _PD]),
     "astrea_evolve_time": (C.c_int, [C.c_void_p, C.c_double]),
     "astrea_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _PD]),
+    "astrea_set_time": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "astrea_step_async": (C.c_int, [C.c_void_p]),
+    "astrea_get_time": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64), _PD]),
+    "astrea_dt_history": (C.c_int, [C.c_void_p, _PD, C.c_int]),
+    "astrea_dt_async": (C.c_int, [C.c_void_p]),
     "astrea_get_parity": (C.c_int, [C.c_void_p]),
     "astrea_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -162,6 +167,27 @@ class Context:
         dt = C.c_double()
         self._check(self.lib.astrea_step(self._h, float(t), float(t_stop), C.byref(dt)))
         return dt.value
+
+    # -- the same without host round trips (device-side dt and clock)
+    def set_time(self, t=0.0, t_stop=0.0):
+        self._check(self.lib.astrea_set_time(self._h, float(t), float(t_stop)))
+
+    def step_async(self):
+        self._check(self.lib.astrea_step_async(self._h))
+
+    def dt_async(self):
+        self._check(self.lib.astrea_dt_async(self._h))
+
+    def get_time(self):
+        """(t, steps, last dt) after synchronising; raises NonFiniteError if a step since the last check went bad."""
+        t, n, dt = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self.lib.astrea_get_time(self._h, C.byref(t), C.byref(n), C.byref(dt)))
+        return t.value, n.value, dt.value
+
+    def dt_history(self, n):
+        out = (C.c_double * n)()
+        self._check(self.lib.astrea_dt_history(self._h, out, n))
+        return list(out)
 
     @property
     def parity(self):

@@ -26,7 +26,7 @@ using namespace astrea;
 
 namespace {
 
-constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr int DT_HISTORY = 1024;
 
 struct Reg {
     double* mem = nullptr;
@@ -42,6 +42,9 @@ struct Instr {
     int out, bracket;
     double scale;
     std::vector<Term> terms;
+    int defer_rate = 0;         // operator: do not assemble L, the next register update does it on the fly
+    int fused_rate = -1;        // update: index of the rate buffer assembled on the fly from the flux planes (-1: none)
+    int store_rate = 0;         // update with fused_rate: also store that rate (a later formula re-uses it)
     int refine = 0;             // magnetic_2d: refine_grid (mag_field.inverse_reconstruct) wraps this update
     int special = SP_NONE;      // SP_FACE_FIELD: evolvers.py:73-76;  SP_REFINE: refine_grid applied to reg[out]
 };
@@ -70,7 +73,9 @@ struct astrea_ctx {
     VarList vars() const { return hydro ? hydro_vars() : all_vars(); }
     unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
     unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
-    int* flag = nullptr;              // non-finite wave speed seen in any operator since the last read
+    unsigned long long* flag = nullptr;   // eig_bits[2]: 1.0 once a non-finite wave speed was seen (sticky until read)
+    double* clock = nullptr;          // device: t, t_stop, steps, last dt (ClockKernel)
+    double* dt_history = nullptr;     // device: dt of the last DT_HISTORY steps
     double* dt_dev = nullptr;
     std::vector<Instr> prog;
     int grid_reg = 0;                 // register holding the current grid
@@ -275,6 +280,23 @@ void build_program(int integrator, bool mhd, std::vector<Instr>& p, int& nregs, 
             break;
         }
     }
+    // Fuse the rate assembly into the register update that follows an operator when that update is the first reader
+    // of the operator's rate buffer; the rate is stored only if a later formula reads it again.
+    for (size_t i = 0; i + 1 < p.size(); ++i) {
+        if (!p[i].is_operator || p[i + 1].is_operator) continue;
+        const int r = p[i].rate_out;
+        bool used_next = false;
+        for (const Term& t : p[i + 1].terms) used_next = used_next || (t.is_rate && t.index == r);
+        if (!used_next) continue;
+        bool used_later = false;
+        for (size_t k = i + 2; k < p.size(); ++k) {
+            if (p[k].is_operator) { if (p[k].rate_out == r) break; else continue; }
+            for (const Term& t : p[k].terms) used_later = used_later || (t.is_rate && t.index == r);
+        }
+        p[i].defer_rate = 1;
+        p[i + 1].fused_rate = r;
+        p[i + 1].store_rate = used_later ? 1 : 0;
+    }
     if (!mhd) return;
     // magnetic_2d: the B slots of the grid become face averages before the stages (evolvers.py:73-76) and every
     // register update is followed by refine_grid (evolvers.py:63-67)
@@ -391,6 +413,16 @@ int run_special(astrea_ctx* c, const Instr& ins) {
     return 0;
 }
 
+RateParams rate_params(astrea_ctx* c) {
+    const astrea_cfg& g = c->cfg;
+    RateParams r{};
+    r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane;
+    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr;
+    r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
+    r.vars = c->vars();
+    return r;
+}
+
 int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first) {
     const astrea_cfg& g = c->cfg;
     Plane q = c->regs[ins.src].plane;
@@ -480,10 +512,9 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     if (g.magnetic_2d) {
         if (int e = corner_field(c)) return e;
     }
-    RateParams r{};
-    r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane; r.out = c->rates[ins.rate_out].plane;
-    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr; r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
-    r.vars = c->vars();
+    if (ins.defer_rate) return 0;      // the register update that follows assembles L on the fly (UpdateKernel)
+    RateParams r = rate_params(c);
+    r.out = c->rates[ins.rate_out].plane;
     {
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
         { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RateKernel>(r, gx, gy, 256, RateKernel::smem_bytes(), c->st)); }
@@ -499,13 +530,20 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
         const Term& t = ins.terms[k];
         p.term[k] = t.is_rate ? c->rates[t.index].plane : c->regs[t.index].plane;
         p.coef[k] = t.coef;
-        p.is_rate[k] = t.is_rate;
+        p.is_rate[k] = (t.is_rate && t.index == ins.fused_rate) ? 2 : t.is_rate;
     }
     p.bracket_rates = ins.bracket;
     p.scale = ins.scale;
     p.dt = c->dt_dev;
     p.nrow = c->nrow; p.ncol = c->ncol;
     p.vars = c->vars();
+    if (ins.fused_rate >= 0) {
+        UpdateParams u{rate_params(c), p, ins.store_rate ? c->rates[ins.fused_rate].plane : Plane{nullptr, 0, 0}};
+        const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
+        Timed timed(c, CLS_UPDATE);
+        ASTREA_TRY(launch<UpdateKernel>(u, gx, gy, 256, UpdateKernel::smem_bytes(), c->st));
+        return 0;
+    }
     const int gx = (int)((c->ncol + 255) / 256);
     { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st)); }
     return 0;
@@ -588,18 +626,20 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     }
     c->mhd_flag = (int*)dev_alloc(sizeof(int));
     ok = ok && c->mhd_flag;
-    c->eig_bits = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
-    c->flag = (int*)dev_alloc(sizeof(int));
+    c->eig_bits = (unsigned long long*)dev_alloc(8 * sizeof(unsigned long long));
+    c->clock = (double*)dev_alloc((4 + DT_HISTORY) * sizeof(double));
     c->dt_dev = (double*)dev_alloc(sizeof(double));
-    ok = ok && c->eig_bits && c->flag && c->dt_dev;
+    ok = ok && c->eig_bits && c->clock && c->dt_dev;
     if (!ok) {
         g_create_error = "device allocation failed";
         astrea_destroy(c);
         return nullptr;
     }
-    c->eig_scratch = c->eig_bits + 2;
-    dev_zero(c->eig_bits, 4 * sizeof(unsigned long long), c->st);
-    dev_zero(c->flag, sizeof(int), c->st);
+    c->flag = c->eig_bits + 2;
+    c->eig_scratch = c->eig_bits + 4;
+    c->dt_history = c->clock + 4;
+    dev_zero(c->eig_bits, 8 * sizeof(unsigned long long), c->st);
+    dev_zero(c->clock, (4 + DT_HISTORY) * sizeof(double), c->st);
     dev_zero(c->dt_dev, sizeof(double), c->st);
 
     // launch geometry
@@ -623,7 +663,7 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
     dev_free(c->ws.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
-    dev_free(c->eig_bits); dev_free(c->flag); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
+    dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->stream_owned) cudaStreamDestroy(c->st.s);
 #endif
@@ -706,11 +746,10 @@ int astrea_finish_step(astrea_ctx* c) {
 
 int astrea_read_eigmax(astrea_ctx* c, double* eigmax) {
     if (!c || !eigmax) return fail(c, ASTREA_E_ARG, "astrea_read_eigmax: NULL argument");
-    unsigned long long bits[2] = {0, 0};
-    int flag = 0;
+    unsigned long long bits[3] = {0, 0, 0};
     ASTREA_TRY(copy_d2h(bits, c->eig_bits, sizeof(bits), c->st));
-    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(int), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_read_eigmax: stream sync failed");
+    const bool flag = bits[2] != 0;
     for (int a = 0; a < c->cfg.dimension; ++a) {
         const int slot = c->cfg.dimension == 1 ? 0 : a;
         std::memcpy(&eigmax[a], &bits[slot], sizeof(double));
@@ -736,8 +775,8 @@ int astrea_evolve_time(astrea_ctx* c, double dt) {
     // astrea.py:81 rebinds grid; the permutation reversal (astrea.py:85) is the caller's (astrea_step does both)
     c->grid_reg = c->final_reg;
     c->next_instr = 0;
-    int flag = 0;
-    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(int), c->st));
+    unsigned long long flag = 0;
+    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(flag), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_evolve_time: stream sync failed");
     if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a Runge-Kutta stage (fv.py:158 raises LinAlgError)");
     return 0;
@@ -755,6 +794,60 @@ int astrea_step(astrea_ctx* c, double t, double t_stop, double* dt_out) {
     for (int i = 1; i < (int)c->prog.size(); ++i)
         if (int e = astrea_run_instr(c, i, 0)) return e;
     return astrea_finish_step(c);
+}
+
+int astrea_set_time(astrea_ctx* c, double t, double t_stop) {
+    if (!c) return ASTREA_E_ARG;
+    ClockParams k{c->clock, c->dt_dev, c->eig_bits, c->dt_history, DT_HISTORY, 0, c->cfg.dimension, c->cfg.cfl, c->cfg.dx, t, t_stop};
+    Timed timed(c, CLS_HALO);
+    ASTREA_TRY(launch<ClockKernel>(k, 1, 1, 32, 0, c->st));
+    return 0;
+}
+
+int astrea_dt_async(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    if (c->next_instr != 1) return fail(c, ASTREA_E_STATE, "astrea_dt_async: run instruction 0 (the operator on the grid) first");
+    ClockParams k{c->clock, c->dt_dev, c->eig_bits, c->dt_history, DT_HISTORY, 1, c->cfg.dimension, c->cfg.cfl, c->cfg.dx, 0.0, 0.0};
+    Timed timed(c, CLS_HALO);
+    ASTREA_TRY(launch<ClockKernel>(k, 1, 1, 32, 0, c->st));
+    return 0;
+}
+
+int astrea_step_async(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+    c->next_instr = 0;
+    if (int e = astrea_run_instr(c, 0, 0)) return e;
+    if (int e = astrea_dt_async(c)) return e;
+    for (int i = 1; i < (int)c->prog.size(); ++i)
+        if (int e = astrea_run_instr(c, i, 0)) return e;
+    return astrea_finish_step(c);
+}
+
+int astrea_get_time(astrea_ctx* c, double* t, int64_t* steps, double* last_dt) {
+    if (!c) return ASTREA_E_ARG;
+    double clock[4] = {0, 0, 0, 0};
+    unsigned long long flag = 0;
+    ASTREA_TRY(copy_d2h(clock, c->clock, sizeof(clock), c->st));
+    ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(flag), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_get_time: stream sync failed");
+    if (t) *t = clock[0];
+    if (steps) *steps = (int64_t)clock[2];
+    if (last_dt) *last_dt = clock[3];
+    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a step since the last check (fv.py:158 raises LinAlgError)");
+    return 0;
+}
+
+int astrea_dt_history(astrea_ctx* c, double* out, int n) {
+    if (!c || !out || n < 0 || n > DT_HISTORY) return fail(c, ASTREA_E_ARG, "astrea_dt_history: n must be within 0..1024");
+    double clock[4];
+    std::vector<double> hist(DT_HISTORY);
+    ASTREA_TRY(copy_d2h(clock, c->clock, sizeof(clock), c->st));
+    ASTREA_TRY(copy_d2h(hist.data(), c->dt_history, DT_HISTORY * sizeof(double), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_dt_history: stream sync failed");
+    const long long steps = (long long)clock[2];
+    if (n > steps) return fail(c, ASTREA_E_ARG, "astrea_dt_history: fewer steps taken than requested");
+    for (int k = 0; k < n; ++k) out[k] = hist[(size_t)((steps - n + k) % DT_HISTORY)];
+    return 0;
 }
 
 int astrea_get_parity(const astrea_ctx* c) { return c ? c->parity : ASTREA_E_ARG; }
@@ -841,7 +934,7 @@ int astrea_restore_state(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
     if (!c->saved.mem) return fail(c, ASTREA_E_STATE, "astrea_restore_state: nothing saved");
     ASTREA_TRY(copy_d2d(c->regs[c->grid_reg].mem, c->saved.mem, c->plane_doubles * sizeof(double), c->st));
-    ASTREA_TRY(dev_zero(c->flag, sizeof(int), c->st));
+    ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));
     c->parity = c->saved_parity;
     c->hydro = c->saved_hydro;
     c->next_instr = 0;

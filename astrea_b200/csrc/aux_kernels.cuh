@@ -240,6 +240,133 @@ struct CombineKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ fused rate + RK update
+// A register update whose newest rate L is used nowhere else (SSPRK(2,2), (3,3), (4,3), (10,4), Euler, and the
+// last use in the others) does not need L in memory: it is assembled from the flux planes on the fly (term with
+// is_rate == 2) inside the update, which saves one plane write and one plane read per stage.
+struct UpdateParams {
+    RateParams rate;      // rate.out is unused
+    CombineParams comb;   // comb.term[k] with is_rate[k] == 2 is the rate assembled on the fly
+    Plane rate_store;     // base != nullptr: also store the assembled rate (it is re-used by a later formula)
+};
+struct UpdateKernel {
+    using Params = UpdateParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TILE = 32;
+    static size_t smem_bytes() { return sizeof(double) * TILE * (TILE + 1); }
+    template <class Ex>
+    static HD void block(const Params& pp, int bx, int by, Ex& ex) {
+        const RateParams& p = pp.rate;
+        const CombineParams& cb = pp.comb;
+        double* tile = ex.smem();
+        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        for (int a = 0; a < p.vars.n; ++a) {
+            const int v = p.vars.v[a];
+            if (p.dimension == 2) {
+                ex.phase([&](int tid) {
+                    const int tx = tid % TILE;
+                    for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                        const int64_t yr = c0 + ty, xc = r0 + tx;
+                        if (yr < p.ncol && xc < p.nrow)
+                            tile[ty * (TILE + 1) + tx] = (*p.f1t.at(yr + 1, v, xc) - *p.f1t.at(yr, v, xc)) / p.dx;
+                    }
+                });
+            }
+            ex.phase([&](int tid) {
+                const int tx = tid % TILE;
+                const double dt = *cb.dt;
+                for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                    const int64_t r = r0 + ty, c = c0 + tx;
+                    if (r >= p.nrow || c >= p.ncol) continue;
+                    double total;
+                    if (p.dimension == 2) {
+                        total = (*p.f0.at(r + 1, v, c) - *p.f0.at(r, v, c)) / p.dx;
+                        total = total + tile[tx * (TILE + 1) + ty];
+                    } else {
+                        total = *p.d0.at(r, v, c);
+                    }
+                    if (p.emf != nullptr && (v == 5 || v == 6)) {
+                        const bool wrap = p.bc == BC_WRAP;
+                        const double e0 = p.emf[r * p.ncol + c];
+                        if (v == 5) {
+                            const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
+                            total = (p.emf[r * p.ncol + cn] - e0) / p.dx;
+                        } else {
+                            const int64_t rn = r + 1 < p.nrow ? r + 1 : (wrap ? 0 : p.nrow - 1);
+                            total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;
+                        }
+                    }
+                    const double L = -total;
+                    if (pp.rate_store.base != nullptr) *pp.rate_store.at(r, v, c) = L;
+                    double acc = 0.0;
+                    if (!cb.bracket_rates) {
+                        for (int k = 0; k < cb.nterms; ++k) {
+                            const double x = cb.is_rate[k] == 2 ? L : *cb.term[k].at(r, v, c);
+                            const double t = cb.is_rate[k] ? (cb.coef[k] * dt) * x : cb.coef[k] * x;
+                            acc = (k == 0) ? t : acc + t;
+                        }
+                        if (cb.scale != 1.0) acc = cb.scale * acc;
+                    } else {
+                        double regs = 0.0, rates = 0.0;
+                        bool fr = true, fl = true;
+                        for (int k = 0; k < cb.nterms; ++k) {
+                            const double x = cb.is_rate[k] == 2 ? L : *cb.term[k].at(r, v, c);
+                            if (cb.is_rate[k]) { const double t = cb.coef[k] * x; rates = fl ? t : rates + t; fl = false; }
+                            else { const double t = cb.coef[k] * x; regs = fr ? t : regs + t; fr = false; }
+                        }
+                        double tail = dt * rates;
+                        if (cb.scale != 1.0) tail = cb.scale * tail;
+                        acc = regs + tail;
+                    }
+                    *cb.out.at(r, v, c) = acc;
+                }
+            });
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ device-side clock
+// astrea.py:70-78 without a host round trip: dt = cfl * min(dx / eigmax), clipped so that t + dt does not pass
+// t_stop, written where the register updates read it; t and the step count advance on the device.
+struct ClockParams {
+    double* clock;                       // [0] t, [1] t_stop, [2] steps taken, [3] last dt
+    double* dt;                          // the scalar the register updates read
+    const unsigned long long* eig_bits;  // [2] per-axis max wave speed of operator 0 (bit patterns)
+    double* history;                     // dt of step n at history[n % history_len]
+    int history_len;
+    int mode;                            // 0: set t, t_stop and reset the step count; 1: take dt from the wave speeds
+    int dimension;
+    double cfl, dx, t, t_stop;
+};
+struct ClockKernel {
+    using Params = ClockParams;
+    static constexpr int MAX_THREADS = 32;
+    template <class Ex>
+    static HD void block(const Params& p, int, int, Ex& ex) {
+        ex.phase([&](int tid) {
+            if (tid != 0) return;
+            if (p.mode == 0) {
+                p.clock[0] = p.t; p.clock[1] = p.t_stop; p.clock[2] = 0.0; p.clock[3] = 0.0;
+                return;
+            }
+            double e0, e1;
+            memcpy(&e0, &p.eig_bits[0], sizeof(double));
+            memcpy(&e1, &p.eig_bits[1], sizeof(double));
+            double m = p.dx / e0;
+            if (p.dimension == 2) { const double m1 = p.dx / e1; m = m1 < m ? m1 : m; }
+            double dt = p.cfl * m;
+            const double t = p.clock[0], t_stop = p.clock[1];
+            if (t_stop > t && t + dt >= t_stop) dt = t_stop - t;
+            *p.dt = dt;
+            const long long n = (long long)p.clock[2];
+            p.history[n % p.history_len] = dt;
+            p.clock[0] = t + dt;
+            p.clock[2] = (double)(n + 1);
+            p.clock[3] = dt;
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ cons -> prim for download
 struct PrimParams {
     Plane q, w;           // w may alias a scratch register; ghosts of q must be valid for the 4th-order conversion

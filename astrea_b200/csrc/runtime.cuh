@@ -54,9 +54,9 @@ struct DeviceExec {
         return __shfl_sync(0xffffffffu, own, ((tid & 31) + delta) & 31);
     }
     // Block-wide max of a non-negative per-thread value -> atomicMax on the bit pattern of *dst; ``bad``
-    // (non-finite seen) is OR-ed into *flag.  Call from block scope (not inside a phase): get(tid, val, bad).
+    // (non-finite seen) sets *flag to the bit pattern of 1.0.  Call from block scope (not inside a phase): get(tid, val, bad).
     template <class G>
-    __device__ void publish_max(G&& get, unsigned long long* dst, int* flag) {
+    __device__ void publish_max(G&& get, unsigned long long* dst, unsigned long long* flag) {
         __shared__ double red[32];
         __shared__ int redbad[32];
         double val = 0.0;
@@ -78,7 +78,7 @@ struct DeviceExec {
             }
             if (lane == 0) {
                 atomicMax(dst, (unsigned long long)__double_as_longlong(val));
-                if (bad) atomicOr(flag, 1);
+                if (bad) atomicMax(flag, 0x3FF0000000000000ull);      // bit pattern of 1.0: the flag is all-reduced (MAX) as a double
             }
         }
         __syncthreads();
@@ -146,14 +146,14 @@ struct HostExec {
         return get((tid & ~31) + (((tid & 31) + delta) & 31));
     }
     template <class G>
-    void publish_max(G&& get, unsigned long long* dst, int* flag) {
+    void publish_max(G&& get, unsigned long long* dst, unsigned long long* flag) {
         for (int t = 0; t < nthr; ++t) {
             double val = 0.0, cur;
             bool bad = false;
             get(t, val, bad);
             std::memcpy(&cur, dst, 8);
             if (val > cur) std::memcpy(dst, &val, 8);
-            if (bad) *flag |= 1;
+            if (bad) *flag = 0x3FF0000000000000ull;
         }
     }
 };

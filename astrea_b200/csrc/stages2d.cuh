@@ -198,7 +198,7 @@ struct FluxStageParams {
     double gamma;
     int bc, low_mach;
     unsigned long long* eigmax_bits;
-    int* flag;
+    unsigned long long* flag;
 };
 
 // KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)

@@ -23,7 +23,7 @@ struct Sweep1DParams {
     double gamma, dx;
     int bc, limiter, low_mach, tile;
     unsigned long long* eigmax_bits;   // [1]
-    int* flag;                         // non-finite wave speed seen
+    unsigned long long* flag;                         // non-finite wave speed seen
 };
 
 struct TileAccessor {

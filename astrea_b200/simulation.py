@@ -48,6 +48,7 @@ class SlabExchange:
         self.hi = (rank + 1) % world if (periodic or rank < world - 1) else None
         self._views = {}
         self.stream = torch.cuda.ExternalStream(ctx.stream_handle, device=device_index) if on_device else None
+        self._eig = _tensor_at(ctx.eigmax_device(), 3, on_device, device_index)
 
     def _blocks(self, instr):
         if instr not in self._views:
@@ -82,21 +83,21 @@ class SlabExchange:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
+    def reduce_eigmax(self):
+        """all-reduce(MAX), in place on the device, of the three doubles behind ``astrea_eigmax_device``: the two
+        per-axis wave speeds of operator 0 and the "non-finite seen" flag — so every rank takes the same dt and
+        raises together where the reference raises.  Stream-ordered, no host synchronisation."""
+        dist = self.dist
+        if self.on_device:
+            with self.torch.cuda.stream(self.stream):
+                dist.all_reduce(self._eig, op=dist.ReduceOp.MAX)
+        else:
+            self.ctx.sync()
+            dist.all_reduce(self._eig, op=dist.ReduceOp.MAX)
+
     def global_eigmax(self):
-        """The per-axis wave speeds of operator 0, maximised over the ranks, plus the "non-finite seen" flag OR-ed
-        over the ranks so that every rank raises together where the reference raises."""
-        torch, dist = self.torch, self.dist
-        try:
-            vals, bad = self.ctx.read_eigmax(), 0.0
-        except N.NonFiniteError:
-            vals, bad = [0.0, 0.0], 1.0
-        dev = torch.device("cuda", self.device_index) if self.on_device else torch.device("cpu")
-        t = torch.tensor(list(vals) + [bad], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e0, e1, bad = t.tolist()
-        if bad:
-            raise N.NonFiniteError(N.E_NONFINITE, "non-finite wave speed on some rank (the reference raises LinAlgError, fv.py:158)")
-        return [e0, e1]
+        self.reduce_eigmax()
+        return self.ctx.read_eigmax()      # synchronises; raises NonFiniteError on every rank if any rank saw one
 
 
 class Simulation:
@@ -163,6 +164,35 @@ class Simulation:
         self.t += dt
         self.steps_done += 1
         return dt
+
+    def step_async(self):
+        """One pass of astrea.py:67-85 enqueued without any host synchronisation: dt is computed on the device
+        (``astrea_dt_async``) and t advances there.  Call ``set_time`` first; read the clock with ``time()``."""
+        if self.exchange is None:
+            self.ctx.step_async()
+        else:
+            for i, is_operator in enumerate(self._program):
+                if is_operator:
+                    self.exchange.halo(i)
+                    self.ctx.run_instr(i, external_rows=True)
+                    if i == 0:
+                        self.exchange.reduce_eigmax()
+                        self.ctx.dt_async()
+                else:
+                    self.ctx.run_instr(i)
+            self.ctx.finish_step()
+        self.steps_done += 1
+
+    def set_time(self, t=0.0, t_stop=None):
+        self.t = t
+        self.ctx.set_time(t, t - 1.0 if t_stop is None else t_stop)
+
+    def time(self):
+        """(t, steps, last dt) from the device clock; synchronises and raises where the reference would have."""
+        if self.exchange is not None:
+            self.exchange.reduce_eigmax()        # make the non-finite flag global before reading it
+        self.t, steps, dt = self.ctx.get_time()
+        return self.t, steps, dt
 
     def check_finite(self):
         """Raise NonFiniteError (a LinAlgError) on every rank if any Runge-Kutta stage so far saw a non-finite wave

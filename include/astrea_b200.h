@@ -86,6 +86,19 @@ int astrea_evolve_time(astrea_ctx* ctx, double dt);
 /* One pass of the loop body astrea.py:67-85: evolve_space, dt = cfl*min(dx/eigmax) (:70-71), clip so that
  * t + dt does not pass t_stop (:74-75; pass t_stop <= t to disable), evolve_time, flip the parity. */
 int astrea_step(astrea_ctx* ctx, double t, double t_stop, double* dt_out);
+/* The same loop body without a host round trip: the time step is computed on the device from the wave speeds
+ * (astrea.py:70-71), clipped against t_stop (:74-75), and t / the step count advance on the device, so steps can be
+ * enqueued back to back.  astrea_set_time sets t and t_stop (t_stop <= t: no clipping) and resets the step count;
+ * astrea_get_time synchronises, returns t, the number of steps and the last dt, and reports ASTREA_E_NONFINITE if
+ * any operator since the last check saw a non-finite wave speed (the reference would have raised at that step);
+ * astrea_dt_history returns the dt of the last n steps (n <= 1024), oldest first. */
+int astrea_set_time(astrea_ctx* ctx, double t, double t_stop);
+int astrea_step_async(astrea_ctx* ctx);
+int astrea_get_time(astrea_ctx* ctx, double* t, int64_t* steps, double* last_dt);
+int astrea_dt_history(astrea_ctx* ctx, double* out, int n);
+/* multi-GPU hosts: after instruction 0 and the all-reduce(MAX) of the three doubles at astrea_eigmax_device
+ * (two wave speeds + the non-finite flag), enqueue the device-side dt computation */
+int astrea_dt_async(astrea_ctx* ctx);
 int astrea_get_parity(const astrea_ctx* ctx);
 int astrea_set_parity(astrea_ctx* ctx, int step_parity);
 
@@ -112,7 +125,8 @@ int astrea_halo_ptrs(astrea_ctx* ctx, int instr, double** send_lo, double** send
 /* fill the ghost columns of the interior rows of the register instruction `instr` reads, so that the rows handed to
  * the neighbours carry their corner cells; call before the exchange */
 int astrea_halo_prepare(astrea_ctx* ctx, int instr);
-/* device addresses of eigmax[2] (as written by the last operator 0) for an all-reduce(MAX) across ranks */
+/* device address of three doubles: eigmax[2] as written by the last operator 0 and the non-finite flag (0.0 / 1.0),
+ * for one all-reduce(MAX) across ranks */
 int astrea_eigmax_device(astrea_ctx* ctx, double** eigmax_dev);
 int astrea_read_eigmax(astrea_ctx* ctx, double* eigmax);        /* sync + copy to host, ASTREA_E_NONFINITE as above */
 int astrea_sync(astrea_ctx* ctx);

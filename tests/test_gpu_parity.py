@@ -239,3 +239,36 @@ def test_medium_size_vs_oracle(lib):
     got, used, _ = run_native(lib, meta, g0, 2)
     assert np.all(rel_l1(got, want) <= 1e-10)
     assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("spec", [("sod", 1, "plm", "lf", "ssprk(2,2)", 1024), ("ll6", 2, "ppm", "hllc", "ssprk(3,3)", 96),
+                                  ("orszag-tang", 2, "plm", "hlld", "ssprk(3,3)", 64)], ids=["sod1d", "ll6", "ot"])
+def test_async_stepping_with_device_clock(lib, spec):
+    """astrea_step_async: dt and the t_stop clip (astrea.py:70-78) evaluated on the device, steps enqueued back to back."""
+    from astrea_b200 import _native as N
+    from astrea_b200.selectors import MAGNETIC_2D
+    from cases import native_cfg, oracle_cfg
+    from oracle import advance
+    config, dim, subgrid, solver, timestep, cells = spec
+    meta = _meta(config, cells, dim, subgrid, solver, timestep, None, mhd=config in MAGNETIC_2D)
+    g0 = initial_state(config, cells, dim, 1.4, subgrid == "ppm")
+    ctx = N.Context(native_cfg(meta), lib=lib)
+    ctx.upload(g0)
+    want, dts = run_oracle(meta, g0, 4)
+    ctx.set_time(0.0, 0.0)
+    for _ in range(4):
+        ctx.step_async()
+    t, steps, last = ctx.get_time()
+    assert steps == 4 and np.allclose(ctx.dt_history(4), dts, rtol=1e-13, atol=0)
+    assert np.all(rel_l1(ctx.download(), want) <= 1e-10)
+    t_stop = dts[0] + 0.4 * dts[1]
+    want, used = advance(np.copy(g0), oracle_cfg(meta), 2, t=0.0, t_end=t_stop)
+    ctx.upload(g0)
+    ctx.parity = 0
+    ctx.set_time(0.0, t_stop)
+    ctx.step_async()
+    ctx.step_async()
+    t, steps, last = ctx.get_time()
+    assert steps == 2 and abs(t - t_stop) <= 1e-15 and np.allclose(ctx.dt_history(2), used, rtol=1e-12, atol=0)
+    assert np.all(rel_l1(ctx.download(), want) <= 1e-10)
+    ctx.close()

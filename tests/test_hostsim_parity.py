@@ -221,3 +221,43 @@ def test_unsupported_selectors_fail_loudly(hostsim_lib):
     meta = _meta("sod", 64, 1, "plm", "lw", "ssprk(2,2)", None)     # Lax-Wendroff: SURVEY Q11
     with pytest.raises(N.AstreaError):
         N.Context(native_cfg(meta), lib=hostsim_lib)
+
+
+@pytest.mark.parametrize("spec", [("sod", 1, "plm", "lf", "ssprk(2,2)", 96), ("ll6", 2, "ppm", "hllc", "ssprk(3,3)", 32),
+                                  ("orszag-tang", 2, "plm", "hlld", "ssprk(3,3)", 24)], ids=["sod1d", "ll6", "ot"])
+def test_async_stepping_with_device_clock(hostsim_lib, spec):
+    """astrea_step_async: dt = cfl*min(dx/eigmax) and the t_stop clip (astrea.py:70-78) evaluated on the device."""
+    from astrea_b200 import _native as N
+    from astrea_b200.selectors import MAGNETIC_2D
+    from cases import native_cfg, oracle_cfg
+    from oracle import advance
+    config, dim, subgrid, solver, timestep, cells = spec
+    meta = _meta(config, cells, dim, subgrid, solver, timestep, None, mhd=config in MAGNETIC_2D)
+    g0 = initial_state(config, cells, dim, 1.4, subgrid == "ppm")
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    # free-running steps
+    want, dts = run_oracle(meta, g0, 4)
+    ctx.set_time(0.0, 0.0)
+    for _ in range(4):
+        ctx.step_async()
+    t, steps, last = ctx.get_time()
+    assert steps == 4 and last == dts[-1] and ctx.dt_history(4) == dts
+    tt = 0.0
+    for d in dts:
+        tt += d
+    assert t == tt
+    assert np.array_equal(ctx.download(), want, equal_nan=True)
+    # clipped at t_stop: the last step lands exactly on it (astrea.py:74-75)
+    t_stop = dts[0] + 0.4 * dts[1]
+    cfg = oracle_cfg(meta)
+    want, used = advance(np.copy(g0), cfg, 2, t=0.0, t_end=t_stop)
+    ctx.upload(g0)
+    ctx.parity = 0
+    ctx.set_time(0.0, t_stop)
+    ctx.step_async()
+    ctx.step_async()
+    t, steps, last = ctx.get_time()
+    assert steps == 2 and ctx.dt_history(2) == used and t == used[0] + used[1]
+    assert np.array_equal(ctx.download(), want, equal_nan=True)
+    ctx.close()

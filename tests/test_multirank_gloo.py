@@ -26,6 +26,15 @@ def _worker(rank, world, rendezvous, spec, outdir):
     dts = sim.run(steps)
     np.save(os.path.join(outdir, f"slab{rank}.npy"), sim.state())
     np.save(os.path.join(outdir, f"dts{rank}.npy"), np.array(dts))
+    # the same steps again through the asynchronous path (device-side dt after an in-place all-reduce)
+    sim.ctx.upload(full[rank * rows:(rank + 1) * rows])
+    sim.ctx.parity = 0
+    sim.set_time(0.0)
+    for _ in range(steps):
+        sim.step_async()
+    t, n, last = sim.time()
+    assert n == steps and sim.ctx.dt_history(steps) == dts, (sim.ctx.dt_history(steps), dts)
+    np.save(os.path.join(outdir, f"aslab{rank}.npy"), sim.state())
     sim.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -58,6 +67,8 @@ def test_two_ranks_equal_one(hostsim_lib, spec, world):
         np.save(os.path.join(tmp, "g0.npy"), g0)
         mp.spawn(_worker, args=(world, os.path.join(tmp, "rdv"), spec, tmp), nprocs=world, join=True)
         got = np.concatenate([np.load(os.path.join(tmp, f"slab{r}.npy")) for r in range(world)], axis=0)
+        again = np.concatenate([np.load(os.path.join(tmp, f"aslab{r}.npy")) for r in range(world)], axis=0)
         for r in range(world):
             assert list(np.load(os.path.join(tmp, f"dts{r}.npy"))) == want_dts
+        assert np.array_equal(again, want, equal_nan=True)
     assert np.array_equal(got, want, equal_nan=True)
