@@ -20,8 +20,12 @@ int launch_flux_ho(int solver, int ax, int sax, int hydro, const FluxStageParams
 #define ASTREA_DEFINE_FLUX(NAME, KIND)                                                                               \
     template <int SOL, int AX, int SAX>                                                                              \
     static int runflux_##NAME(int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {        \
-        if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD>>(p, gx, gy, nthreads, 0, st);        \
-        return launch<FluxStage<KIND, SOL, AX, SAX, false>>(p, gx, gy, nthreads, 0, st);                             \
+        if (p.bc == BC_EDGE) {                                                                                       \
+            if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, true>>(p, gx, gy, nthreads, 0, st); \
+            return launch<FluxStage<KIND, SOL, AX, SAX, false, true>>(p, gx, gy, nthreads, 0, st);                   \
+        }                                                                                                            \
+        if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, false>>(p, gx, gy, nthreads, 0, st); \
+        return launch<FluxStage<KIND, SOL, AX, SAX, false, false>>(p, gx, gy, nthreads, 0, st);                      \
     }                                                                                                                \
     int launch_flux_##NAME(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
         const int key = ax * 2 + sax;                                                                                \

@@ -205,7 +205,8 @@ struct FluxStageParams {
 // MEAN: arithmetic mean (PLM) instead of the Roe average for the wave-speed state.  AX = physical sweep axis,
 // SAX = the solver's axis argument.
 // HYDRO: v_z and B are identically zero, only [rho, v_x, v_y, P] are processed (physics.cuh).
-template <int KIND, int SOLVER, int AX, int SAX, bool HYDRO = false>
+// EDGE: the boundary mode ('edge' needs index clamps and the "own value" rule, 'wrap' reads ghost data as is).
+template <int KIND, int SOLVER, int AX, int SAX, bool HYDRO = false, bool EDGE = true>
 struct FluxStage {
     using Params = FluxStageParams;
     using VS = VarSet<HYDRO>;
@@ -213,7 +214,14 @@ struct FluxStage {
 #ifndef ASTREA_FLUX_MIN_BLOCKS
 #define ASTREA_FLUX_MIN_BLOCKS 4
 #endif
-    static constexpr int MIN_BLOCKS = ASTREA_FLUX_MIN_BLOCKS;      // 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5)
+#ifndef ASTREA_FLUX_MIN_BLOCKS_HYDRO
+#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 6
+#endif
+    // 8-variable kernels: 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5);
+    // hydro kernels: 6 blocks = 24 warps at 80 registers (best of 3..6: the few spills cost less than the warps buy).
+    // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
+    // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
+    static constexpr int MIN_BLOCKS = HYDRO ? ASTREA_FLUX_MIN_BLOCKS_HYDRO : ASTREA_FLUX_MIN_BLOCKS;
     static constexpr bool HO = KIND == 2, PCM = KIND == 0;
     static constexpr int H = HO ? 2 : 1;            // halo lanes on each side of a warp
     static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
@@ -238,7 +246,7 @@ struct FluxStage {
         const int NT = ex.nthreads();
         const int nwarp = NT / 32;
         const double gamma = p.gamma, c24 = 1.0 / 24.0;
-        const bool edge = p.bc == BC_EDGE;
+        constexpr bool edge = EDGE;      // the launcher picks the instantiation from cfg.boundary
         typename Ex::template Local<Tls> tls(ex);
         auto smap = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.s_off, 0, p.ns_glob - 1) - p.s_off : r; };
         auto solve = [&](const Tls& st, const double* wp, const double* wm, const double* qp, const double* qm, const double* fp,
