@@ -64,7 +64,7 @@ struct astrea_ctx {
     size_t plane_doubles = 0;
     std::vector<Reg> regs, rates;
     Reg qT, d0, d1t;                  // transposed input of the y sweep; interface fluxes of the x / y sweep (1D: flux difference)
-    Reg ws, wp, wm;                   // 2D scratch of the sweep in flight: primitive averages, interface states
+    Reg ws, ws2, wp, wm;              // 2D scratch: primitive averages (x frame, y frame), interface states of the sweep in flight
     Reg wfx, wfy, ct0;                // magnetic_2d: face states of the two sweeps (each in its frame), one more scratch
     double* emf = nullptr;            // magnetic_2d: corner electric field [nrow][ncol]
     // hydro specialisation (physics.cuh): the uploaded grid has no v_z / B, so only [rho, m_x, m_y, E] are processed
@@ -438,16 +438,29 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     } else {
         // sweep order and the solver's private axis counter (solvers.py:34-36,63; astrea.py:85)
         const int order[2] = {c->parity ? 1 : 0, c->parity ? 0 : 1};
-        // the y sweep works on the transposed copy of the (ghost-filled) register
-        TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST, c->vars()};
-        {
-            const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
-            { Timed timed(c, CLS_TRANSPOSE); ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st)); }
-        }
         const bool ho = scheme_high_order(g.scheme), pcm = g.scheme == SCH_PCM;
         const int kind = pcm ? 0 : (ho ? 2 : 1);
         const int lo = recon_lo(g.scheme), hi = recon_hi(g.scheme);
         const int ht = ho ? 2 : 1;                 // transverse reach of the flux stage
+        if (pcm) {
+            // PCM's flux stage reads q itself (pcm.py:33-34): the y sweep needs the transposed copy of the register
+            TransposeParams t{q, c->qT.plane, -(int64_t)GHOST, c->nrow + GHOST, -(int64_t)GHOST, c->ncol + GHOST, c->vars()};
+            const int gx = (int)((c->ncol + 2 * GHOST + 31) / 32), gy = (int)((c->nrow + 2 * GHOST + 31) / 32);
+            Timed timed(c, CLS_TRANSPOSE);
+            ASTREA_TRY(launch<TransposeKernel>(t, gx, gy, 256, TransposeKernel::smem_bytes(), c->st));
+        } else {
+            // primitive averages of both sweep frames from one read of the register (PrimBothStage)
+            PrimBothParams pb{};
+            pb.q = q; pb.wx = make_plane(c->ws.mem, c->ncol, GHOST); pb.wy = make_plane(c->ws2.mem, c->nrow, GHOST);
+            pb.gamma = g.gamma; pb.high_order = ho ? 1 : 0;
+            pb.r_lo = -(int64_t)(lo + 1); pb.r_hi = c->nrow + hi + 2; pb.c_lo = -(int64_t)(lo + 1); pb.c_hi = c->ncol + hi + 2;
+            pb.r_min = -(int64_t)GHOST; pb.r_max = c->nrow + GHOST - 1; pb.c_min = -(int64_t)GHOST; pb.c_max = c->ncol + GHOST - 1;
+            const int gx = (int)((pb.c_hi - pb.c_lo + PrimBothStage<false>::TX - 1) / PrimBothStage<false>::TX);
+            const int gy = (int)((pb.r_hi - pb.r_lo + PrimBothStage<false>::TY - 1) / PrimBothStage<false>::TY);
+            Timed timed(c, CLS_PRIM);
+            if (c->hydro) ASTREA_TRY(launch<PrimBothStage<true>>(pb, gx, gy, 256, PrimBothStage<true>::smem_bytes(), c->st));
+            else ASTREA_TRY(launch<PrimBothStage<false>>(pb, gx, gy, 256, PrimBothStage<false>::smem_bytes(), c->st));
+        }
         for (int k = 0; k < 2; ++k) {
             const int ax = order[k], sax = k;
             int64_t ns, nt, ns_glob, s_off, nt_glob, t_off;
@@ -460,13 +473,14 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 ns = c->ncol; nt = c->nrow; ns_glob = c->ncol; s_off = 0; nt_glob = g.nx_global; t_off = g.x_offset;
             }
             // scratch planes in the shape of this frame
-            const Plane ws = make_plane(c->ws.mem, nt, GHOST), wp = make_plane(c->wp.mem, nt, GHOST), wm = make_plane(c->wm.mem, nt, GHOST);
+            const Plane ws = make_plane((ax == 1 && !pcm) ? c->ws2.mem : c->ws.mem, nt, GHOST);
+            const Plane wp = make_plane(c->wp.mem, nt, GHOST), wm = make_plane(c->wm.mem, nt, GHOST);
             const bool edge = g.boundary == BC_EDGE;
             const bool lo_phys = s_off == 0, hi_phys = s_off + ns == ns_glob;
             // cells to reconstruct: one beyond each end (two at the upper end: LLF looks at interface j+1), except
             // across a physical 'edge' boundary where the interface states are copies ("pad the derived array")
             const int64_t i_lo = (edge && lo_phys) ? 0 : -1, i_hi = (edge && hi_phys) ? ns - 1 : ns + 1;
-            {
+            if (pcm) {
                 PrimStageParams pp{};
                 pp.q = qf; pp.w = ws; pp.gamma = g.gamma; pp.high_order = ho ? 1 : 0;
                 pp.r_lo = -(int64_t)(lo + 1); pp.r_hi = ns + hi + 2; pp.c_lo = -(int64_t)ht; pp.c_hi = nt + ht;
@@ -615,7 +629,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     ok = ok && alloc_reg(c, c->d0, c->ncol);
     if (g.dimension == 2) {
         ok = ok && alloc_reg(c, c->qT, c->nrow) && alloc_reg(c, c->d1t, c->nrow);
-        ok = ok && alloc_reg(c, c->ws, c->ncol) && alloc_reg(c, c->wp, c->ncol) && alloc_reg(c, c->wm, c->ncol);
+        ok = ok && alloc_reg(c, c->ws, c->ncol) && alloc_reg(c, c->ws2, c->nrow) && alloc_reg(c, c->wp, c->ncol) && alloc_reg(c, c->wm, c->ncol);
         if (g.magnetic_2d) {
             ok = ok && alloc_reg(c, c->wfx, c->ncol) && alloc_reg(c, c->wfy, c->nrow) && alloc_reg(c, c->ct0, c->ncol);
             c->emf = (double*)dev_alloc(sizeof(double) * (size_t)c->nrow * c->ncol);
@@ -661,7 +675,7 @@ void astrea_destroy(astrea_ctx* c) {
     for (auto& r : c->regs) dev_free(r.mem);
     for (auto& r : c->rates) dev_free(r.mem);
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
-    dev_free(c->ws.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
+    dev_free(c->ws.mem); dev_free(c->ws2.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
 #ifdef ASTREA_DEVICE_BUILD

@@ -99,6 +99,96 @@ struct PrimStage {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ PrimBothStage
+// The primitive cell averages of BOTH sweep frames from one read of q: the pointwise conversions are shared, the
+// 4th-order correction is summed in each frame's own axis order (fv.py:134-142 sums axis 0 of the frame first, so
+// the two frames differ in the last bits), and the y-frame result is written transposed through shared memory.
+// Replaces transpose(q) + two PrimStage launches for every scheme whose flux stage does not read q itself (all but PCM).
+struct PrimBothParams {
+    Plane q;                           // x frame
+    Plane wx, wy;                      // out: primitive averages in the x frame / in the y frame (transposed)
+    int64_t r_lo, r_hi, c_lo, c_hi;    // half-open output range in x-frame coordinates (rows = x, cols = y)
+    int64_t r_min, r_max, c_min, c_max;
+    double gamma;
+    int high_order;
+};
+template <bool HYDRO>
+struct PrimBothStage {
+    using Params = PrimBothParams;
+    using VS = VarSet<HYDRO>;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TX = 32, TY = 16, SX = TX + 2, SY = TY + 2, PT = TY + 1;
+    static size_t smem_bytes() { return sizeof(double) * VS::N * (2 * SX * SY + TX * PT); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int64_t c0 = p.c_lo + (int64_t)bx * TX, r0 = p.r_lo + (int64_t)by * TY;
+        const double gamma = p.gamma, c24 = 1.0 / 24.0;
+        double* Q = ex.smem();                     // [N][SY][SX] conservative averages of the tile + 1 halo
+        double* W = Q + VS::N * SX * SY;           // pointwise primitives of the same cells
+        double* T = W + VS::N * SX * SY;           // [N][TX][PT] y-frame result, staged for the transposed write
+        ex.phase([&](int tid) {
+            for (int e = tid; e < SX * SY; e += MAX_THREADS) {
+                const int x = e % SX, y = e / SX;
+                const int64_t c = clamp_index(c0 - 1 + x, p.c_min, p.c_max), r = clamp_index(r0 - 1 + y, p.r_min, p.r_max);
+                double q[NVAR], w[NVAR];
+#pragma unroll
+                for (int k = 0; k < VS::N; ++k) q[VS::at(k)] = *p.q.at(r, VS::at(k), c);
+                prim_of_cons_t<HYDRO>(q, w, gamma);
+#pragma unroll
+                for (int k = 0; k < VS::N; ++k) { Q[(k * SY + y) * SX + x] = q[VS::at(k)]; W[(k * SY + y) * SX + x] = w[VS::at(k)]; }
+            }
+        });
+        ex.phase([&](int tid) {
+            const int x = tid % TX + 1;
+            for (int y = tid / TX + 1; y <= TY; y += MAX_THREADS / TX) {
+                const int64_t c = c0 + x - 1, r = r0 + y - 1;
+                const bool inside = c < p.c_hi && r < p.r_hi;
+                double wx[NVAR], wy[NVAR];
+                if (!p.high_order) {
+#pragma unroll
+                    for (int k = 0; k < VS::N; ++k) { wx[VS::at(k)] = W[(k * SY + y) * SX + x]; wy[VS::at(k)] = wx[VS::at(k)]; }
+                } else {
+                    double qx[NVAR], qy[NVAR], sx[NVAR], sy[NVAR];
+#pragma unroll
+                    for (int k = 0; k < VS::N; ++k) {
+                        const int v = VS::at(k);
+                        const double* q = Q + k * SY * SX;
+                        const double* w0 = W + k * SY * SX;
+                        const double qc = q[y * SX + x], wc = w0[y * SX + x];
+                        const double dq_r = (q[(y + 1) * SX + x] - qc) - (qc - q[(y - 1) * SX + x]);     // along x (rows)
+                        const double dq_c = (q[y * SX + x + 1] - qc) - (qc - q[y * SX + x - 1]);         // along y (cols)
+                        const double dw_r = (w0[(y + 1) * SX + x] - wc) - (wc - w0[(y - 1) * SX + x]);
+                        const double dw_c = (w0[y * SX + x + 1] - wc) - (wc - w0[y * SX + x - 1]);
+                        qx[v] = (qc - c24 * dq_r) - c24 * dq_c;       // x frame: axis 0 = x first
+                        sx[v] = c24 * dw_r + c24 * dw_c;
+                        qy[v] = (qc - c24 * dq_c) - c24 * dq_r;       // y frame: axis 0 = y first
+                        sy[v] = c24 * dw_c + c24 * dw_r;
+                    }
+                    prim_of_cons_t<HYDRO>(qx, wx, gamma);
+                    prim_of_cons_t<HYDRO>(qy, wy, gamma);
+#pragma unroll
+                    for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); wx[v] = wx[v] + sx[v]; wy[v] = wy[v] + sy[v]; }
+                }
+#pragma unroll
+                for (int k = 0; k < VS::N; ++k) {
+                    if (inside) *p.wx.at(r, VS::at(k), c) = wx[VS::at(k)];
+                    T[(k * TX + (x - 1)) * PT + (y - 1)] = wy[VS::at(k)];
+                }
+            }
+        });
+        ex.phase([&](int tid) {
+            // y frame: row = y (this tile's columns), col = x (this tile's rows): TY contiguous doubles per row
+            const int xx = tid % TY;
+            for (int yy = tid / TY; yy < TX; yy += MAX_THREADS / TY) {
+                const int64_t c = c0 + yy, r = r0 + xx;
+                if (c >= p.c_hi || r >= p.r_hi) continue;
+#pragma unroll
+                for (int k = 0; k < VS::N; ++k) *p.wy.at(c, VS::at(k), r) = T[(k * TX + yy) * PT + xx];
+            }
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ ReconStage
 struct ReconStageParams {
     Plane w;                   // primitive cell averages, valid on rows [-(LO+2) .. ns+HI+1] where data are genuine
