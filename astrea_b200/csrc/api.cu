@@ -27,6 +27,7 @@ using namespace astrea;
 namespace {
 
 constexpr int DT_HISTORY = 1024;
+constexpr int64_t GRAPH_MAX_CELLS = 1 << 18;     // astrea_step_async replays a CUDA graph up to 512^2 cells
 
 struct Reg {
     double* mem = nullptr;
@@ -91,6 +92,10 @@ struct astrea_ctx {
 #ifdef ASTREA_DEVICE_BUILD
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
+    // astrea_step_async on small grids replays a captured CUDA graph of the whole step: [step parity][hydro]
+    cudaGraphExec_t step_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int eager_steps[2][2] = {{0, 0}, {0, 0}};
+    int64_t graph_launches[2][2] = {{0, 0}, {0, 0}};      // kernels inside each captured step (for astrea_launch_count)
 #endif
 };
 
@@ -679,6 +684,9 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
 #ifdef ASTREA_DEVICE_BUILD
+    for (auto& row : c->step_graph)
+        for (auto& g : row)
+            if (g) cudaGraphExecDestroy(g);
     if (c->stream_owned) cudaStreamDestroy(c->st.s);
 #endif
     delete c;
@@ -827,13 +835,49 @@ int astrea_dt_async(astrea_ctx* c) {
     return 0;
 }
 
-int astrea_step_async(astrea_ctx* c) {
-    if (!c) return ASTREA_E_ARG;
+static int enqueue_step(astrea_ctx* c) {
     c->next_instr = 0;
     if (int e = astrea_run_instr(c, 0, 0)) return e;
     if (int e = astrea_dt_async(c)) return e;
     for (int i = 1; i < (int)c->prog.size(); ++i)
         if (int e = astrea_run_instr(c, i, 0)) return e;
+    return 0;
+}
+
+int astrea_step_async(astrea_ctx* c) {
+    if (!c) return ASTREA_E_ARG;
+#ifdef ASTREA_DEVICE_BUILD
+    // Launch-bound regime (the 1D configurations, small 2D grids): the ~10-40 launches of a step are captured once
+    // per (step parity, hydro) and replayed as one CUDA graph.  Large grids gain nothing and launch eagerly.
+    const bool small = (int64_t)c->nrow * c->ncol <= GRAPH_MAX_CELLS && !(c->cfg.flags & 2) && !c->profiling;
+    if (small) {
+        const int a = c->parity & 1, b = c->hydro ? 1 : 0;
+        if (c->step_graph[a][b] == nullptr && c->eager_steps[a][b] >= 1) {     // first step eager: sets kernel attributes
+            cudaGraph_t graph = nullptr;
+            cudaError_t err = cudaStreamBeginCapture(c->st.s, cudaStreamCaptureModeThreadLocal);
+            if (err != cudaSuccess) return fail(c, ASTREA_E_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(err));
+            const int64_t launches0 = c->launches;
+            const int e = enqueue_step(c);
+            err = cudaStreamEndCapture(c->st.s, &graph);
+            if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+            if (err != cudaSuccess) return fail(c, ASTREA_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(err));
+            err = cudaGraphInstantiate(&c->step_graph[a][b], graph, 0);
+            cudaGraphDestroy(graph);
+            if (err != cudaSuccess) return fail(c, ASTREA_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+            c->graph_launches[a][b] = c->launches - launches0;
+            c->launches = launches0;
+        }
+        if (c->step_graph[a][b] != nullptr) {
+            const cudaError_t err = cudaGraphLaunch(c->step_graph[a][b], c->st.s);
+            if (err != cudaSuccess) return fail(c, ASTREA_E_CUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(err));
+            c->launches += c->graph_launches[a][b];
+            c->next_instr = (int)c->prog.size();
+            return astrea_finish_step(c);
+        }
+        c->eager_steps[a][b]++;
+    }
+#endif
+    if (int e = enqueue_step(c)) return e;
     return astrea_finish_step(c);
 }
 

@@ -61,7 +61,8 @@ typedef struct astrea_cfg {
     int32_t threads_2d;    /* 0 = default; threads per block of the 2D sweep kernels */
     int32_t segment_2d;    /* 0 = default; cells marched per block along the sweep */
     int32_t tile_1d;       /* 0 = default; cells per block of the 1D sweep kernel */
-    int32_t flags;         /* bit 0: keep the general 8-variable kernels even when the grid has no v_z / B (testing) */
+    int32_t flags;         /* bit 0: keep the general 8-variable kernels even when the grid has no v_z / B (testing);
+                              bit 1: never replay astrea_step_async as a CUDA graph (small grids do by default) */
 } astrea_cfg;
 
 /* sim_variables -> device context.  Stands in for the namedtuple built at astrea.py:132-133. */
