@@ -560,7 +560,25 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
         UpdateParams u{rate_params(c), p, ins.store_rate ? c->rates[ins.fused_rate].plane : Plane{nullptr, 0, 0}};
         const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
         Timed timed(c, CLS_UPDATE);
-        ASTREA_TRY(launch<UpdateKernel>(u, gx, gy, 256, UpdateKernel::smem_bytes(), c->st));
+        const size_t sm = UpdateKernel<1, false>::smem_bytes();
+        int e = -1;
+        if (!p.bracket_rates) {
+            switch (p.nterms) {
+                case 1: e = launch<UpdateKernel<1, false>>(u, gx, gy, 256, sm, c->st); break;
+                case 2: e = launch<UpdateKernel<2, false>>(u, gx, gy, 256, sm, c->st); break;
+                case 3: e = launch<UpdateKernel<3, false>>(u, gx, gy, 256, sm, c->st); break;
+                case 4: e = launch<UpdateKernel<4, false>>(u, gx, gy, 256, sm, c->st); break;
+                case 5: e = launch<UpdateKernel<5, false>>(u, gx, gy, 256, sm, c->st); break;
+                default: break;
+            }
+        } else {
+            switch (p.nterms) {
+                case 5: e = launch<UpdateKernel<5, true>>(u, gx, gy, 256, sm, c->st); break;
+                case 7: e = launch<UpdateKernel<7, true>>(u, gx, gy, 256, sm, c->st); break;
+                default: break;
+            }
+        }
+        ASTREA_TRY(e);
         return 0;
     }
     const int gx = (int)((c->ncol + 255) / 256);

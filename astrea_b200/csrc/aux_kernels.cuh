@@ -249,6 +249,9 @@ struct UpdateParams {
     CombineParams comb;   // comb.term[k] with is_rate[k] == 2 is the rate assembled on the fly
     Plane rate_store;     // base != nullptr: also store the assembled rate (it is re-used by a later formula)
 };
+// NTERMS / BRACKET are compile-time so that the term loop unrolls and every pointer and coefficient stays in a
+// register (a run-time term count costs ~370 instructions per cell and variable, mostly 64-bit address arithmetic).
+template <int NTERMS, bool BRACKET>
 struct UpdateKernel {
     using Params = UpdateParams;
     static constexpr int MAX_THREADS = 256;
@@ -260,65 +263,85 @@ struct UpdateKernel {
         const CombineParams& cb = pp.comb;
         double* tile = ex.smem();
         const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        const bool two_d = p.dimension == 2;
+        // every plane of a context has the same geometry: one offset addresses them all
+        const int64_t rp = cb.out.row_pitch, cp = cb.out.col_pitch;
         for (int a = 0; a < p.vars.n; ++a) {
             const int v = p.vars.v[a];
-            if (p.dimension == 2) {
-                ex.phase([&](int tid) {
+            if (two_d) {
+                ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
                     const int tx = tid % TILE;
                     for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                         const int64_t yr = c0 + ty, xc = r0 + tx;
-                        if (yr < p.ncol && xc < p.nrow)
-                            tile[ty * (TILE + 1) + tx] = (*p.f1t.at(yr + 1, v, xc) - *p.f1t.at(yr, v, xc)) / p.dx;
+                        if (yr < p.ncol && xc < p.nrow) {
+                            const double* f = p.f1t.at(yr, v, xc);
+                            tile[ty * (TILE + 1) + tx] = (f[p.f1t.row_pitch] - f[0]) / p.dx;
+                        }
                     }
                 });
             }
             ex.phase([&](int tid) {
                 const int tx = tid % TILE;
                 const double dt = *cb.dt;
+                const double* tp[NTERMS];
+                double cf[NTERMS];
+                int kind[NTERMS];
+#pragma unroll
+                for (int k = 0; k < NTERMS; ++k) {
+                    tp[k] = cb.term[k].base + (int64_t)v * cp;
+                    kind[k] = cb.is_rate[k];
+                    cf[k] = (!BRACKET && kind[k]) ? cb.coef[k] * dt : cb.coef[k];
+                }
                 for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                     const int64_t r = r0 + ty, c = c0 + tx;
                     if (r >= p.nrow || c >= p.ncol) continue;
+                    const int64_t off = r * rp + c;
                     double total;
-                    if (p.dimension == 2) {
-                        total = (*p.f0.at(r + 1, v, c) - *p.f0.at(r, v, c)) / p.dx;
+                    if (two_d) {
+                        const double* f = p.f0.base + off + (int64_t)v * cp;
+                        total = (f[rp] - f[0]) / p.dx;
                         total = total + tile[tx * (TILE + 1) + ty];
                     } else {
-                        total = *p.d0.at(r, v, c);
+                        total = p.d0.base[off + (int64_t)v * cp];
                     }
                     if (p.emf != nullptr && (v == 5 || v == 6)) {
+                        // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
                         const bool wrap = p.bc == BC_WRAP;
                         const double e0 = p.emf[r * p.ncol + c];
                         if (v == 5) {
                             const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
-                            total = (p.emf[r * p.ncol + cn] - e0) / p.dx;
+                            total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
                         } else {
                             const int64_t rn = r + 1 < p.nrow ? r + 1 : (wrap ? 0 : p.nrow - 1);
-                            total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;
+                            total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
                         }
                     }
                     const double L = -total;
-                    if (pp.rate_store.base != nullptr) *pp.rate_store.at(r, v, c) = L;
+                    if (pp.rate_store.base != nullptr) pp.rate_store.base[off + (int64_t)v * cp] = L;
                     double acc = 0.0;
-                    if (!cb.bracket_rates) {
-                        for (int k = 0; k < cb.nterms; ++k) {
-                            const double x = cb.is_rate[k] == 2 ? L : *cb.term[k].at(r, v, c);
-                            const double t = cb.is_rate[k] ? (cb.coef[k] * dt) * x : cb.coef[k] * x;
+                    if (!BRACKET) {
+#pragma unroll
+                        for (int k = 0; k < NTERMS; ++k) {
+                            const double x = kind[k] == 2 ? L : tp[k][off];
+                            const double t = cf[k] * x;
                             acc = (k == 0) ? t : acc + t;
                         }
                         if (cb.scale != 1.0) acc = cb.scale * acc;
                     } else {
                         double regs = 0.0, rates = 0.0;
                         bool fr = true, fl = true;
-                        for (int k = 0; k < cb.nterms; ++k) {
-                            const double x = cb.is_rate[k] == 2 ? L : *cb.term[k].at(r, v, c);
-                            if (cb.is_rate[k]) { const double t = cb.coef[k] * x; rates = fl ? t : rates + t; fl = false; }
-                            else { const double t = cb.coef[k] * x; regs = fr ? t : regs + t; fr = false; }
+#pragma unroll
+                        for (int k = 0; k < NTERMS; ++k) {
+                            const double x = kind[k] == 2 ? L : tp[k][off];
+                            const double t = cf[k] * x;
+                            if (kind[k]) { rates = fl ? t : rates + t; fl = false; }
+                            else { regs = fr ? t : regs + t; fr = false; }
                         }
                         double tail = dt * rates;
                         if (cb.scale != 1.0) tail = cb.scale * tail;
                         acc = regs + tail;
                     }
-                    *cb.out.at(r, v, c) = acc;
+                    cb.out.base[off + (int64_t)v * cp] = acc;
                 }
             });
         }
