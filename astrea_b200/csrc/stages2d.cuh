@@ -223,9 +223,10 @@ template <int SCHEME>
 struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
-#ifdef ASTREA_RECON_MIN_BLOCKS
-    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;
+#ifndef ASTREA_RECON_MIN_BLOCKS
+#define ASTREA_RECON_MIN_BLOCKS 4
 #endif
+    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;     // up to 128 registers: the march is latency bound, registers beat warps
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
@@ -305,10 +306,10 @@ struct FluxStage {
 #define ASTREA_FLUX_MIN_BLOCKS 4
 #endif
 #ifndef ASTREA_FLUX_MIN_BLOCKS_HYDRO
-#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 6
+#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 7
 #endif
     // 8-variable kernels: 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5);
-    // hydro kernels: 6 blocks = 24 warps at 80 registers (best of 3..6: the few spills cost less than the warps buy).
+    // hydro kernels: 7 blocks = 28 warps at 72 registers (best of 3..8: the few spills cost less than the warps buy).
     // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
     // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
     static constexpr int MIN_BLOCKS = HYDRO ? ASTREA_FLUX_MIN_BLOCKS_HYDRO : ASTREA_FLUX_MIN_BLOCKS;
