@@ -278,12 +278,17 @@ def run_ours(a):
                 "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
                 "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak,
                 "note": "fp64-pipe bound, not HBM bound: see DESIGN.md"}
+    # DRAM bytes actually moved per sweep, from the committed `ncu --set full` capture (profiles/summarize.py)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
             tr = json.load(fh).get(a.workload)
-        if tr:
-            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        if tr and not a.cells:
+            per = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tr["kernels"].items()}
+            # one sweep = half a PrimBothStage launch (it serves both directions) + one ReconStage + one FluxStage
+            roofline["traffic"] = sum(b * (0.5 if "PrimBoth" in k else 1.0) for k, b in per.items()
+                                      if any(s in k for s in ("PrimBoth", "PrimStage", "ReconStage", "FluxStage", "Sweep1D")))
+            roofline["traffic_per_kernel_launch"] = per
             roofline["traffic_source"] = tr.get("source")
 
     # end to end through the reference-facing calls, host buffers in and out every step
