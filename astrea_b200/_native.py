@@ -63,6 +63,8 @@ _SIGNATURES = {
     "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
     "astrea_program_length": (C.c_int, [C.c_void_p]),
     "astrea_instr_is_operator": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_instr_is_update": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_run_update_part": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "astrea_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
     "astrea_run_instr": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "astrea_finish_step": (C.c_int, [C.c_void_p]),
@@ -201,6 +203,13 @@ class Context:
     def program(self):
         n = self.lib.astrea_program_length(self._h)
         return [bool(self.lib.astrea_instr_is_operator(self._h, i)) for i in range(n)]
+
+    def updates(self):
+        n = self.lib.astrea_program_length(self._h)
+        return [self.lib.astrea_instr_is_update(self._h, i) == 1 for i in range(n)]
+
+    def run_update_part(self, i, part):
+        self._check(self.lib.astrea_run_update_part(self._h, i, int(part)))
 
     def set_dt(self, dt):
         self._check(self.lib.astrea_set_dt(self._h, float(dt)))

@@ -27,6 +27,7 @@ using namespace astrea;
 namespace {
 
 constexpr int DT_HISTORY = 1024;
+constexpr int64_t UPDATE_EDGE = 32;              // rows of a register update done first when a slab host overlaps its halo exchange
 constexpr int64_t GRAPH_MAX_CELLS = 1 << 18;     // astrea_step_async replays a CUDA graph up to 512^2 cells
 
 struct Reg {
@@ -323,7 +324,7 @@ void build_program(int integrator, bool mhd, std::vector<Instr>& p, int& nregs, 
 
 // ---------------------------------------------------------------------------------------- launches
 int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
-    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, c->vars()};
+    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, c->vars(), 0};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     if (c->ghost_r > 0) {
         h.phase = 1;
@@ -351,7 +352,7 @@ int transpose_plane(astrea_ctx* c, Plane src, Plane dst, int64_t src_rows, int64
 }
 
 int fill_plane_halo(astrea_ctx* c, Plane pl, int64_t rows, int64_t cols) {
-    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1, all_vars()};
+    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1, all_vars(), 0};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)rows, 64, 0, c->st)); }
     h.phase = 1;
     const int gx = (int)((cols + 2 * GHOST + 255) / 256);
@@ -425,6 +426,7 @@ RateParams rate_params(astrea_ctx* c) {
     r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr;
     r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
     r.vars = c->vars();
+    r.row_lo = 0; r.row_hi = c->nrow;
     return r;
 }
 
@@ -541,7 +543,9 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     return 0;
 }
 
-int run_combine(astrea_ctx* c, const Instr& ins) {
+// rows [row_lo, row_hi) of one register update
+int run_combine(astrea_ctx* c, const Instr& ins, int64_t row_lo, int64_t row_hi) {
+    if (row_hi <= row_lo) return 0;
     CombineParams p{};
     p.out = c->regs[ins.out].plane;
     p.nterms = (int)ins.terms.size();
@@ -556,9 +560,11 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
     p.dt = c->dt_dev;
     p.nrow = c->nrow; p.ncol = c->ncol;
     p.vars = c->vars();
+    p.row_lo = row_lo;
     if (ins.fused_rate >= 0) {
         UpdateParams u{rate_params(c), p, ins.store_rate ? c->rates[ins.fused_rate].plane : Plane{nullptr, 0, 0}};
-        const int gx = (int)((c->ncol + 31) / 32), gy = (int)((c->nrow + 31) / 32);
+        u.rate.row_lo = row_lo; u.rate.row_hi = row_hi;
+        const int gx = (int)((c->ncol + 31) / 32), gy = (int)((row_hi - row_lo + 31) / 32);
         Timed timed(c, CLS_UPDATE);
         const size_t sm = UpdateKernel<1, false>::smem_bytes();
         int e = -1;
@@ -582,7 +588,7 @@ int run_combine(astrea_ctx* c, const Instr& ins) {
         return 0;
     }
     const int gx = (int)((c->ncol + 255) / 256);
-    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<CombineKernel>(p, gx, (int)c->nrow, 256, 0, c->st)); }
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<CombineKernel>(p, gx, (int)(row_hi - row_lo), 256, 0, c->st)); }
     return 0;
 }
 
@@ -769,8 +775,29 @@ int astrea_run_instr(astrea_ctx* c, int i, int external_rows) {
     if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_instr: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
     const Instr& ins = c->prog[i];
     const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0)
-                                  : (ins.special != SP_NONE ? run_special(c, ins) : run_combine(c, ins));
+                                  : (ins.special != SP_NONE ? run_special(c, ins) : run_combine(c, ins, 0, c->nrow));
     if (e) return e;
+    c->next_instr = i + 1;
+    return 0;
+}
+
+int astrea_instr_is_update(const astrea_ctx* c, int i) {
+    if (!c || i < 0 || i >= (int)c->prog.size()) return ASTREA_E_ARG;
+    return (!c->prog[i].is_operator && c->prog[i].special == SP_NONE) ? 1 : 0;
+}
+
+int astrea_run_update_part(astrea_ctx* c, int i, int part) {
+    if (!c || i < 0 || i >= (int)c->prog.size() || astrea_instr_is_update(c, i) != 1)
+        return fail(c, ASTREA_E_ARG, "astrea_run_update_part: not a register update");
+    if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_update_part: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
+    // the first / last UPDATE_EDGE rows are what the neighbours' ghost rows are made of (GHOST <= UPDATE_EDGE)
+    const int64_t edge = std::min<int64_t>(UPDATE_EDGE, c->nrow / 2);
+    const Instr& ins = c->prog[i];
+    if (part == 0) {
+        if (int e = run_combine(c, ins, 0, edge)) return e;
+        return run_combine(c, ins, c->nrow - edge, c->nrow);
+    }
+    if (int e = run_combine(c, ins, edge, c->nrow - edge)) return e;
     c->next_instr = i + 1;
     return 0;
 }
@@ -969,8 +996,12 @@ int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, d
 
 int astrea_halo_prepare(astrea_ctx* c, int i) {
     if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: not an operator instruction");
-    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars()};
-    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
+    // only the first / last ghost_r interior rows travel: fill their ghost columns
+    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars(), 0};
+    const int rows = (int)std::min<int64_t>(c->ghost_r, c->nrow);
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, rows, 64, 0, c->st)); }
+    h.row0 = c->nrow - rows;
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, rows, 64, 0, c->st)); }
     return 0;
 }
 

@@ -46,6 +46,7 @@ struct HaloParams {
     int phase;            // 0: ghost columns of interior rows, 1: ghost rows (full padded width, corners included)
     int fill_lo, fill_hi; // phase 1: which row ghosts to fill locally (0 when a neighbour rank provides them)
     VarList vars;
+    int64_t row0;         // phase 0: first interior row to treat (blockIdx.y counts from here)
 };
 struct HaloKernel {
     using Params = HaloParams;
@@ -57,7 +58,7 @@ struct HaloKernel {
         ex.phase([&](int tid) {
             if (p.phase == 0) {
                 // by = row, threads over the 2*GHOST ghost columns x NVAR
-                const int64_t r = by;
+                const int64_t r = p.row0 + by;
                 for (int e = tid; e < 2 * GHOST * p.vars.n; e += NT) {
                     const int v = p.vars.v[e / (2 * GHOST)], g = e % (2 * GHOST);
                     const int64_t c = g < GHOST ? g - GHOST : p.ncol + (g - GHOST);
@@ -128,6 +129,7 @@ struct RateParams {
     double dx;
     int bc;
     VarList vars;
+    int64_t row_lo, row_hi;   // half-open range of rows to process (slab hosts update the edge rows first)
 };
 struct RateKernel {
     using Params = RateParams;
@@ -137,7 +139,7 @@ struct RateKernel {
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
         double* tile = ex.smem();
-        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        const int64_t c0 = (int64_t)bx * TILE, r0 = p.row_lo + (int64_t)by * TILE;
         for (int a = 0; a < p.vars.n; ++a) {
             const int v = p.vars.v[a];
             if (p.dimension == 2) {
@@ -145,7 +147,7 @@ struct RateKernel {
                     const int tx = tid % TILE;
                     for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                         const int64_t yr = c0 + ty, xc = r0 + tx;
-                        if (yr < p.ncol && xc < p.nrow)
+                        if (yr < p.ncol && xc < p.row_hi)
                             tile[ty * (TILE + 1) + tx] = (*p.f1t.at(yr + 1, v, xc) - *p.f1t.at(yr, v, xc)) / p.dx;
                     }
                 });
@@ -154,7 +156,7 @@ struct RateKernel {
                 const int tx = tid % TILE;
                 for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                     const int64_t r = r0 + ty, c = c0 + tx;
-                    if (r >= p.nrow || c >= p.ncol) continue;
+                    if (r >= p.row_hi || c >= p.ncol) continue;
                     double total;
                     if (p.dimension == 2) {
                         // compute_L sums the sweeps in iteration order (evolvers.py:45-49); the sum of two terms
@@ -200,6 +202,7 @@ struct CombineParams {
     const double* dt;     // device scalar
     int64_t nrow, ncol;
     VarList vars;
+    int64_t row_lo;       // first row to process (blockIdx.y counts from here)
 };
 struct CombineKernel {
     using Params = CombineParams;
@@ -209,7 +212,7 @@ struct CombineKernel {
         const int NT = ex.nthreads();
         ex.phase([&](int tid) {
             const int64_t c = (int64_t)bx * NT + tid;
-            const int64_t r = by;
+            const int64_t r = p.row_lo + by;
             if (c >= p.ncol) return;
             const double dt = *p.dt;
             for (int a = 0; a < p.vars.n; ++a) {
@@ -262,7 +265,7 @@ struct UpdateKernel {
         const RateParams& p = pp.rate;
         const CombineParams& cb = pp.comb;
         double* tile = ex.smem();
-        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        const int64_t c0 = (int64_t)bx * TILE, r0 = p.row_lo + (int64_t)by * TILE;
         const bool two_d = p.dimension == 2;
         // every plane of a context has the same geometry: one offset addresses them all
         const int64_t rp = cb.out.row_pitch, cp = cb.out.col_pitch;
@@ -273,7 +276,7 @@ struct UpdateKernel {
                     const int tx = tid % TILE;
                     for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                         const int64_t yr = c0 + ty, xc = r0 + tx;
-                        if (yr < p.ncol && xc < p.nrow) {
+                        if (yr < p.ncol && xc < p.row_hi) {
                             const double* f = p.f1t.at(yr, v, xc);
                             tile[ty * (TILE + 1) + tx] = (f[p.f1t.row_pitch] - f[0]) / p.dx;
                         }
@@ -294,7 +297,7 @@ struct UpdateKernel {
                 }
                 for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                     const int64_t r = r0 + ty, c = c0 + tx;
-                    if (r >= p.nrow || c >= p.ncol) continue;
+                    if (r >= p.row_hi || c >= p.ncol) continue;
                     const int64_t off = r * rp + c;
                     double total;
                     if (two_d) {

@@ -48,6 +48,8 @@ class SlabExchange:
         self.hi = (rank + 1) % world if (periodic or rank < world - 1) else None
         self._views = {}
         self.stream = torch.cuda.ExternalStream(ctx.stream_handle, device=device_index) if on_device else None
+        self.comm = torch.cuda.Stream(device=device_index) if on_device else None
+        self._pending = None
         self._eig = _tensor_at(ctx.eigmax_device(), 3, on_device, device_index)
 
     def _blocks(self, instr):
@@ -55,10 +57,10 @@ class SlabExchange:
             self._views[instr] = [_tensor_at(p, self.count, self.on_device, self.device_index) for p in self.ctx.halo_ptrs(instr)]
         return self._views[instr]
 
-    def halo(self, instr):
+    def _ops(self, instr):
         dist = self.dist
         send_lo, send_hi, recv_lo, recv_hi = self._blocks(instr)
-        self.ctx.halo_prepare(instr)
+
         def op(kind, block, peer, tag):
             return dist.P2POp(kind, block, peer) if self.on_device else dist.P2POp(kind, block, peer, tag=tag)
 
@@ -72,16 +74,51 @@ class SlabExchange:
             ops.append(op(dist.irecv, recv_lo, self.lo, 0))
         if self.hi is not None:
             ops.append(op(dist.irecv, recv_hi, self.hi, 1))
+        return ops
+
+    def halo(self, instr):
+        """Exchange the ghost rows of the register operator ``instr`` reads, in order on the context's stream."""
+        self.ctx.halo_prepare(instr)
+        ops = self._ops(instr)
         if not ops:
             return
         if self.on_device:
             with self.torch.cuda.stream(self.stream):
-                for w in dist.batch_isend_irecv(ops):
+                for w in self.dist.batch_isend_irecv(ops):
                     w.wait()
         else:
             self.ctx.sync()
-            for w in dist.batch_isend_irecv(ops):
+            for w in self.dist.batch_isend_irecv(ops):
                 w.wait()
+
+    def start(self, instr):
+        """Begin the same exchange on the communication stream, behind what the context's stream has done so far
+        (the edge rows of the register update); the caller keeps enqueueing the interior rows meanwhile."""
+        self.ctx.halo_prepare(instr)
+        ops = self._ops(instr)
+        self._pending = None
+        if not ops:
+            return
+        if not self.on_device:
+            self.ctx.sync()
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+            return
+        torch = self.torch
+        ready, done = torch.cuda.Event(), torch.cuda.Event()
+        ready.record(self.stream)
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+            done.record(self.comm)
+        self._pending = done
+
+    def finish(self):
+        """Make the context's stream wait for the exchange begun by ``start``."""
+        if self.on_device and self._pending is not None:
+            self.stream.wait_event(self._pending)
+        self._pending = None
 
     def reduce_eigmax(self):
         """all-reduce(MAX), in place on the device, of the three doubles behind ``astrea_eigmax_device``: the two
@@ -109,7 +146,7 @@ class Simulation:
     """
 
     def __init__(self, config, cells, dimension, subgrid, solver, timestep, cfl=0.5, gamma=1.4, device=0, boundary=None,
-                 rank=0, world=1, cells_x=None, grid=None, _lib=None, **geometry):
+                 rank=0, world=1, cells_x=None, grid=None, overlap=True, _lib=None, **geometry):
         self.config, self.cells, self.dimension = config.lower(), int(cells), int(dimension)
         prob = problem(self.config, self.cells, gamma)
         self.boundary = boundary or prob["boundary"]
@@ -131,6 +168,9 @@ class Simulation:
         self.exchange = SlabExchange(self.ctx, rank, world, self.boundary == "wrap", self.on_device, device) if world > 1 else None
         self.t, self.steps_done = 0.0, 0
         self._program = self.ctx.program()
+        self._updates = self.ctx.updates()
+        self._halo_ready = False          # the ghost rows of the grid were already exchanged behind the last update
+        self.overlap = overlap
         if grid is None:
             grid = self.initial_grid()
         self.ctx.upload(grid)
@@ -141,26 +181,52 @@ class Simulation:
             return initial_slab(self.config, self.nx_local, self.cells, self.x_offset, self.nx_global, self.gamma, self.high_order)
         return initial_state(self.config, self.cells, self.dimension, self.gamma, self.high_order, boundary=self.boundary)
 
+    def _walk(self, after_first_operator):
+        """Run the step program on a slab.  The ghost rows an operator needs are exchanged while the register update
+        that produces its input is still running: the update does its edge rows first (``astrea_run_update_part``),
+        the exchange starts on a second stream, the interior rows follow on the context's stream."""
+        ctx, ex, prog = self.ctx, self.exchange, self._program
+        last = len(prog) - 1
+        ready = {0} if self._halo_ready else set()       # operators whose ghost rows are already in place
+        self._halo_ready = False
+        for i, is_operator in enumerate(prog):
+            if is_operator:
+                if i not in ready:
+                    ex.halo(i)
+                ctx.run_instr(i, external_rows=True)
+                if i == 0:
+                    after_first_operator()
+            elif self.overlap and self._updates[i] and (i == last or prog[i + 1]):
+                ctx.run_update_part(i, 0)
+                ex.start(0 if i == last else i + 1)       # the last update produces the grid the next step starts from
+                ctx.run_update_part(i, 1)
+                ex.finish()
+                if i == last:
+                    self._halo_ready = True
+                else:
+                    ready.add(i + 1)
+            else:
+                ctx.run_instr(i)
+        ctx.finish_step()
+
     def step(self, t_stop=None):
         """One pass of astrea.py:67-85.  Returns dt."""
         stop = self.t - 1.0 if t_stop is None else t_stop
         if self.exchange is None:
             dt = self.ctx.step(self.t, stop)
         else:
-            dt = None
-            for i, is_operator in enumerate(self._program):
-                if is_operator:
-                    self.exchange.halo(i)
-                    self.ctx.run_instr(i, external_rows=True)
-                    if i == 0:
-                        eig = self.exchange.global_eigmax()
-                        dt = self.cfl * min(self.dx / e for e in eig)
-                        if stop > self.t and self.t + dt >= stop:
-                            dt = stop - self.t
-                        self.ctx.set_dt(dt)
-                else:
-                    self.ctx.run_instr(i)
-            self.ctx.finish_step()
+            box = {}
+
+            def choose_dt():
+                eig = self.exchange.global_eigmax()
+                dt = self.cfl * min(self.dx / e for e in eig)
+                if stop > self.t and self.t + dt >= stop:
+                    dt = stop - self.t
+                self.ctx.set_dt(dt)
+                box["dt"] = dt
+
+            self._walk(choose_dt)
+            dt = box["dt"]
         self.t += dt
         self.steps_done += 1
         return dt
@@ -171,17 +237,23 @@ class Simulation:
         if self.exchange is None:
             self.ctx.step_async()
         else:
-            for i, is_operator in enumerate(self._program):
-                if is_operator:
-                    self.exchange.halo(i)
-                    self.ctx.run_instr(i, external_rows=True)
-                    if i == 0:
-                        self.exchange.reduce_eigmax()
-                        self.ctx.dt_async()
-                else:
-                    self.ctx.run_instr(i)
-            self.ctx.finish_step()
+            def device_dt():
+                self.exchange.reduce_eigmax()
+                self.ctx.dt_async()
+
+            self._walk(device_dt)
         self.steps_done += 1
+
+    def upload(self, grid):
+        self._halo_ready = False
+        self.ctx.upload(grid)
+
+    def save_state(self):
+        self.ctx.save_state()
+
+    def restore_state(self):
+        self._halo_ready = False
+        self.ctx.restore_state()
 
     def set_time(self, t=0.0, t_stop=None):
         self.t = t

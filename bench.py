@@ -190,7 +190,7 @@ def run_ours(a):
     if a.segment_2d:
         geometry["segment_2d"] = a.segment_2d
     sim = Simulation(config, cells, dim, subgrid, solver, timestep, device=local, rank=rank, world=world,
-                     cells_x=cells if dim == 2 else None, **geometry)
+                     cells_x=cells if dim == 2 else None, overlap=not a.no_overlap, **geometry)
     ctx = sim.ctx
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=local)
     cells_per_rank = cells ** dim
@@ -217,13 +217,13 @@ def run_ours(a):
         horizon = int(h.item())
     if horizon == 0:
         raise SystemExit("the workload produces non-finite wave speeds in its first step")
-    ctx.restore_state()
+    sim.restore_state()
 
     def run_steps(n):
         # steps are enqueued back to back: dt = cfl*min(dx/eigmax) is evaluated on the device (astrea_step_async)
         for k in range(n):
             if k % horizon == 0:
-                ctx.restore_state()
+                sim.restore_state()
                 sim.set_time(0.0)
             sim.step_async()
 
@@ -249,7 +249,7 @@ def run_ours(a):
     value = world * cells_per_rank * a.steps / (ms * 1e-3)
 
     # per-kernel-class device time of `horizon` steps (CUDA events around every launch, on the launching stream)
-    ctx.restore_state()
+    sim.restore_state()
     ctx.profile(True)
     sim.set_time(0.0)
     for _ in range(horizon):
@@ -309,6 +309,7 @@ def run_ours(a):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc if not a.cells else desc + f" (cells overridden: {cells})", "cells_per_gpu": cells_per_rank,
                            "global_cells": world * cells_per_rank, "stages_per_step": stages, "decomposition": f"x-slabs x{world}",
+                           "halo_exchange": "none (one GPU)" if world == 1 else ("NCCL send/recv on a second stream, overlapped with the interior rows of the register update" if not a.no_overlap else "NCCL send/recv in order on the compute stream"),
                            "finite_horizon_steps": horizon, "dt": "computed on the device every step (cfl*min(dx/eigmax)), no host round trip",
                            "l2": "state per register (%.0f MB) exceeds the 126 MB L2" % (cells_per_rank * 64 / 1e6)
                                  if cells_per_rank * 64 > 126e6 else "working set fits L2 (small workload)",
@@ -336,7 +337,7 @@ def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
     shape = tuple(ctx.shape)
     ic = torch.empty(shape, dtype=torch.float64).pin_memory()
     out = torch.empty(shape, dtype=torch.float64).pin_memory()
-    ctx.restore_state()
+    sim.restore_state()
     ic_np, out_np = ic.numpy(), out.numpy()
     ctx.download(out=ic_np)
     nbytes = ic_np.nbytes
@@ -367,6 +368,7 @@ def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
     else:
         def one_pass():
             for n in range(steps):
+                sim._halo_ready = False            # a fresh upload: ghost rows are stale
                 if n % horizon == 0:
                     ctx.upload_ptr(ic_np.ctypes.data)
                     ctx.parity = 0
@@ -424,6 +426,7 @@ def main():
     ap.add_argument("--threads-2d", type=int, default=0)
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange ghost rows in order instead of behind the register update")
     a = ap.parse_args()
     with StdoutToStderr() as OUT:
         if a.impl == "reference":

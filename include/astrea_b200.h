@@ -117,6 +117,12 @@ int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);
  * Each halo block is ghost_rows x 8 variables x col_pitch doubles, contiguous (the [row][var][col] layout). */
 int astrea_program_length(const astrea_ctx* ctx);
 int astrea_instr_is_operator(const astrea_ctx* ctx, int instr);
+/* 1 if instruction `instr` is a Runge-Kutta register update (not an operator, not a constrained-transport special) */
+int astrea_instr_is_update(const astrea_ctx* ctx, int instr);
+/* A register update in two parts, so that a slab host can overlap the halo exchange of the register it produces
+ * with most of the update: part 0 = the first and last 32 rows (what the neighbours' ghost rows are made of),
+ * part 1 = the rows in between (completes the instruction).  astrea_run_instr does both at once. */
+int astrea_run_update_part(astrea_ctx* ctx, int instr, int part);
 int astrea_set_dt(astrea_ctx* ctx, double dt);                 /* dt of astrea.py:70-78, read by the register updates */
 /* external_rows != 0: the caller has filled the x ghost rows (neighbour ranks); only ghost columns are filled here */
 int astrea_run_instr(astrea_ctx* ctx, int instr, int external_rows);

@@ -27,7 +27,7 @@ def _worker(rank, world, rendezvous, spec, outdir):
     np.save(os.path.join(outdir, f"slab{rank}.npy"), sim.state())
     np.save(os.path.join(outdir, f"dts{rank}.npy"), np.array(dts))
     # the same steps again through the asynchronous path (device-side dt after an in-place all-reduce)
-    sim.ctx.upload(full[rank * rows:(rank + 1) * rows])
+    sim.upload(full[rank * rows:(rank + 1) * rows])
     sim.ctx.parity = 0
     sim.set_time(0.0)
     for _ in range(steps):
