@@ -48,7 +48,8 @@ class SlabExchange:
         self.hi = (rank + 1) % world if (periodic or rank < world - 1) else None
         self._views = {}
         self.stream = torch.cuda.ExternalStream(ctx.stream_handle, device=device_index) if on_device else None
-        self.comm = torch.cuda.Stream(device=device_index) if on_device else None
+        # high priority: the exchange kernels must get SMs while the interior update still fills the device
+        self.comm = torch.cuda.Stream(device=device_index, priority=-1) if on_device else None
         self._pending = None
         self._eig = _tensor_at(ctx.eigmax_device(), 3, on_device, device_index)
 
