@@ -190,7 +190,7 @@ def run_ours(a):
     if a.segment_2d:
         geometry["segment_2d"] = a.segment_2d
     sim = Simulation(config, cells, dim, subgrid, solver, timestep, device=local, rank=rank, world=world,
-                     cells_x=cells if dim == 2 else None, overlap=not a.no_overlap, **geometry)
+                     cells_x=cells if dim == 2 else None, overlap=a.overlap, **geometry)
     ctx = sim.ctx
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=local)
     cells_per_rank = cells ** dim
@@ -309,7 +309,7 @@ def run_ours(a):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc if not a.cells else desc + f" (cells overridden: {cells})", "cells_per_gpu": cells_per_rank,
                            "global_cells": world * cells_per_rank, "stages_per_step": stages, "decomposition": f"x-slabs x{world}",
-                           "halo_exchange": "none (one GPU)" if world == 1 else ("NCCL send/recv on a second stream, overlapped with the interior rows of the register update" if not a.no_overlap else "NCCL send/recv in order on the compute stream"),
+                           "halo_exchange": "none (one GPU)" if world == 1 else ("NCCL send/recv on a second stream, overlapped with the interior rows of the register update" if a.overlap else "NCCL send/recv in order on the compute stream"),
                            "finite_horizon_steps": horizon, "dt": "computed on the device every step (cfl*min(dx/eigmax)), no host round trip",
                            "l2": "state per register (%.0f MB) exceeds the 126 MB L2" % (cells_per_rank * 64 / 1e6)
                                  if cells_per_rank * 64 > 126e6 else "working set fits L2 (small workload)",
@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--threads-2d", type=int, default=0)
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange ghost rows in order instead of behind the register update")
+    ap.add_argument("--overlap", action="store_true", help="multi-GPU: exchange ghost rows behind the register update (measured slower, see Simulation)")
     a = ap.parse_args()
     with StdoutToStderr() as OUT:
         if a.impl == "reference":
