@@ -22,7 +22,7 @@ def _worker(rank, world, rendezvous, spec, outdir):
     full = np.load(os.path.join(outdir, "g0.npy"))
     rows = cells // world
     sim = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, rank=rank, world=world, cells_x=rows,
-                     grid=full[rank * rows:(rank + 1) * rows], overlap=True, _lib=lib, threads_2d=32, segment_2d=9)
+                     grid=full[rank * rows:(rank + 1) * rows], overlap=(world == 3), _lib=lib, threads_2d=32, segment_2d=9)
     dts = sim.run(steps)
     np.save(os.path.join(outdir, f"slab{rank}.npy"), sim.state())
     np.save(os.path.join(outdir, f"dts{rank}.npy"), np.array(dts))
