@@ -2,12 +2,13 @@
 //
 // HBM layout: every state register is one ghost-padded plane [row][var][col] of fp64 with
 // GHOST cells on every side (2D: row = x, col = y; 1D: one row).  A spatial-operator evaluation is
-//     halo fill -> x sweep (reads the register)            -> d0   (x frame)
-//               -> transpose -> y sweep (transposed frame) -> d1t  (y frame)
-//               -> rate assembly L = -(d0 + d1)            -> rate buffer
-// and a Runge-Kutta register update is one combine kernel.  The order of operator evaluations and register
-// updates of a time step is a small "step program" built once per context from the integrator
-// (evolvers.py:79-206).
+//     halo fill -> PrimBothStage (primitive averages of both sweep frames)
+//               -> x sweep: ReconStage -> FluxStage -> F_x    (x frame)
+//               -> y sweep: ReconStage -> FluxStage -> F_y^T  (y frame, transposed planes)
+//               [-> constrained transport: corner E_z]
+// and a Runge-Kutta register update assembles L = -(dF_x + dF_y)/dx on the fly (UpdateKernel).  The order of
+// operator evaluations and register updates of a time step is a small "step program" built once per context
+// from the integrator (evolvers.py:79-206).
 #include "../../include/astrea_b200.h"
 #include "aux_kernels.cuh"
 #include "ct_kernels.cuh"
@@ -83,7 +84,6 @@ struct astrea_ctx {
     int grid_reg = 0;                 // register holding the current grid
     int final_reg = 0;                // register the last instruction writes
     int next_instr = 0;               // 0: nothing run for this step yet
-    int threads2d = 0, tt2d = 0, colblocks_x = 0, colblocks_y = 0;
     int tile1d = 0, threads1d = 0;
     bool stream_owned = false;
     Reg saved;                        // astrea_save_state copy of the grid
@@ -692,8 +692,6 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
         tile = std::max(1, std::min(tile, 256 - lo - hi));
         c->tile1d = tile;
         c->threads1d = tile + lo + hi;
-    } else {
-        c->threads2d = 128;
     }
     return c;
 }

@@ -261,3 +261,32 @@ def test_async_stepping_with_device_clock(hostsim_lib, spec):
     assert steps == 2 and ctx.dt_history(2) == used and t == used[0] + used[1]
     assert np.array_equal(ctx.download(), want, equal_nan=True)
     ctx.close()
+
+
+def test_drop_in_behind_the_reference_time_loop(hostsim_lib):
+    """The reference's own loop body (astrea.py:67-85, as driven by tests/golden/refharness.py) with its `evolvers`
+    module swapped for astrea_b200.evolvers: same sim_variables namedtuple, same calls, same results.  Needs the
+    reference checkout (build container only)."""
+    import sys
+    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__file__), "golden"))
+    import refharness as rh
+    if not rh.available():
+        pytest.skip("reference checkout not present")
+    from astrea_b200 import evolvers as ours
+    for config, cells, dim, subgrid, solver, timestep, steps in (("ll6", 32, 2, "ppm", "hllc", "ssprk(3,3)", 3),
+                                                                 ("sod", 128, 1, "plm", "lf", "ssprk(2,2)", 4),
+                                                                 ("orszag-tang", 24, 2, "plm", "hlld", "ssprk(3,3)", 3)):
+        sv = rh.make_sim_variables(config, cells, dim, subgrid, solver, timestep)
+        g0 = rh.initial_grid(sv)
+        want, dts, eigs, _ = rh.run_steps(sv, steps, grid=np.copy(g0))
+        grid, used = np.copy(g0), []
+        with np.errstate(all="ignore"):
+            for n in range(steps):
+                fluxes = ours.evolve_space(grid, sv, _lib=hostsim_lib)
+                dt = sv.cfl * min(sv.dx / f["eigmax"] for f in fluxes.values())
+                grid = ours.evolve_time(grid, fluxes, dt, sv, _lib=hostsim_lib)
+                sv = sv._replace(permutations=dict(reversed(list(sv.permutations.items()))))
+                used.append(dt)
+        ours.release()
+        assert np.allclose(used, dts, rtol=1e-12, atol=0)
+        assert np.all(rel_l1(grid, want[-1]) <= 1e-10), (config, rel_l1(grid, want[-1]))
