@@ -63,6 +63,7 @@ _SIGNATURES = {
     "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
     "astrea_program_length": (C.c_int, [C.c_void_p]),
     "astrea_instr_is_operator": (C.c_int, [C.c_void_p, C.c_int]),
+    "astrea_instr_needs_halo": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_instr_is_update": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_run_update_part": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "astrea_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
@@ -203,6 +204,10 @@ class Context:
     def program(self):
         n = self.lib.astrea_program_length(self._h)
         return [bool(self.lib.astrea_instr_is_operator(self._h, i)) for i in range(n)]
+
+    def halo_readers(self):
+        n = self.lib.astrea_program_length(self._h)
+        return [self.lib.astrea_instr_needs_halo(self._h, i) == 1 for i in range(n)]
 
     def updates(self):
         n = self.lib.astrea_program_length(self._h)

@@ -28,6 +28,8 @@ using namespace astrea;
 namespace {
 
 constexpr int DT_HISTORY = 1024;
+// reach of the transverse PPM of constrained transport beyond a slab: cells 0 .. n+1 with a stencil of -3 .. +4
+constexpr int CT_LO = 3, CT_HI = 6;
 constexpr int64_t UPDATE_EDGE = 32;              // rows of a register update done first when a slab host overlaps its halo exchange
 constexpr int64_t GRAPH_MAX_CELLS = 1 << 18;     // astrea_step_async replays a CUDA graph up to 512^2 cells
 
@@ -69,11 +71,17 @@ struct astrea_ctx {
     Reg qT, d0, d1t;                  // transposed input of the y sweep; interface fluxes of the x / y sweep (1D: flux difference)
     Reg ws, ws2, wp, wm;              // 2D scratch: primitive averages (x frame, y frame), interface states of the sweep in flight
     Reg wfx, wfy, ct0;                // magnetic_2d: face states of the two sweeps (each in its frame), one more scratch
-    double* emf = nullptr;            // magnetic_2d: corner electric field [nrow][ncol]
+    double* emf = nullptr;            // magnetic_2d: corner electric field [nrow (+1)][ncol]
+    int64_t emf_rows = 0;
     // hydro specialisation (physics.cuh): the uploaded grid has no v_z / B, so only [rho, m_x, m_y, E] are processed
     bool hydro = false, saved_hydro = false;
     int* mhd_flag = nullptr;          // device: set by the upload when a v_z / B component is non-zero
     VarList vars() const { return hydro ? hydro_vars() : all_vars(); }
+    // the ghost rows beyond the low / high end of this slab hold genuine neighbour data (exchanged), i.e. the end is
+    // not a physical 'edge' boundary and the grid is decomposed
+    bool slab() const { return cfg.dimension == 2 && cfg.nx != cfg.nx_global; }
+    bool ext_lo() const { return slab() && !(cfg.boundary == BC_EDGE && cfg.x_offset == 0); }
+    bool ext_hi() const { return slab() && !(cfg.boundary == BC_EDGE && cfg.x_offset + cfg.nx == cfg.nx_global); }
     unsigned long long* eig_bits = nullptr;   // [2] bit patterns of the per-axis max wave speed (operator 0)
     unsigned long long* eig_scratch = nullptr; // [2] same for the later stages (checked for finiteness only)
     unsigned long long* flag = nullptr;   // eig_bits[2]: 1.0 once a non-finite wave speed was seen (sticky until read)
@@ -101,6 +109,10 @@ struct astrea_ctx {
 };
 
 namespace {
+
+// instructions that read the ghost rows of a register: the spatial operator and refine_grid (inverse_reconstruct)
+bool needs_ghost_rows(const Instr& ins) { return ins.is_operator || ins.special == SP_REFINE; }
+int halo_register(const Instr& ins) { return ins.is_operator ? ins.src : ins.out; }
 
 int fail(astrea_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
@@ -324,7 +336,7 @@ void build_program(int integrator, bool mhd, std::vector<Instr>& p, int& nregs, 
 
 // ---------------------------------------------------------------------------------------- launches
 int fill_halo(astrea_ctx* c, Plane pl, int external_rows) {
-    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, c->vars(), 0};
+    HaloParams h{pl, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, c->vars(), 0, 0, 0};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
     if (c->ghost_r > 0) {
         h.phase = 1;
@@ -351,12 +363,17 @@ int transpose_plane(astrea_ctx* c, Plane src, Plane dst, int64_t src_rows, int64
     return 0;
 }
 
-int fill_plane_halo(astrea_ctx* c, Plane pl, int64_t rows, int64_t cols) {
-    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, 1, 1, all_vars(), 0};
-    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)rows, 64, 0, c->st)); }
+// "pad the derived array" for a plane: ghost columns (phase 0), then ghost rows (phase 1).  A side whose ghost cells
+// were computed from genuine neighbour data (slab interior) is left alone.
+int fill_plane_halo(astrea_ctx* c, Plane pl, int64_t rows, int64_t cols, bool keep_row_lo, bool keep_row_hi, bool keep_col_lo, bool keep_col_hi) {
+    HaloParams h{pl, rows, cols, c->cfg.boundary, 0, keep_row_lo ? 0 : 1, keep_row_hi ? 0 : 1, all_vars(), 0, keep_col_lo ? 1 : 0, keep_col_hi ? 1 : 0};
+    // ghost rows that are kept hold genuine values in their interior columns only: their ghost columns are padded too
+    h.row0 = keep_row_lo ? -(int64_t)GHOST : 0;
+    const int64_t row_end = keep_row_hi ? rows + GHOST : rows;
+    if (!(keep_col_lo && keep_col_hi)) { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)(row_end - h.row0), 64, 0, c->st)); }
     h.phase = 1;
     const int gx = (int)((cols + 2 * GHOST + 255) / 256);
-    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st)); }
+    if (h.fill_lo || h.fill_hi) { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, gx, 2 * GHOST * NVAR, 256, 0, c->st)); }
     return 0;
 }
 
@@ -366,13 +383,14 @@ int corner_field(astrea_ctx* c) {
     const int64_t nx = c->nrow, ny = c->ncol;
     const bool edge = g.boundary == BC_EDGE;
     // "pad the derived array": ghost cells of the face-state arrays are copies, not reconstructions
-    if (int e = fill_plane_halo(c, c->wfx.plane, nx, ny)) return e;
-    if (int e = fill_plane_halo(c, c->wfy.plane, ny, nx)) return e;
-    auto transverse_ppm = [&](Plane face_t, Plane d, Plane u, int64_t ns, int64_t ns_glob, int64_t s_off, int64_t nt) -> int {
+    const bool xl = c->ext_lo(), xh = c->ext_hi();
+    if (int e = fill_plane_halo(c, c->wfx.plane, nx, ny, xl, xh, false, false)) return e;      // x frame: rows are x
+    if (int e = fill_plane_halo(c, c->wfy.plane, ny, nx, false, false, xl, xh)) return e;      // y frame: columns are x
+    auto transverse_ppm = [&](Plane face_t, Plane d, Plane u, int64_t ns, int64_t ns_glob, int64_t s_off, int64_t nt, int64_t i_hi) -> int {
         ReconStageParams rp{};
         rp.w = face_t; rp.wp = d; rp.wm = u; rp.wf = Plane{nullptr, 0, 0};
         rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = 0; rp.c_hi = nt;
-        rp.i_lo = 0; rp.i_hi = edge ? ns - 1 : ns;          // pad(wD)[1:] needs cell ns when periodic
+        rp.i_lo = 0; rp.i_hi = i_hi;
         rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
         rp.nvar = NVAR;
         for (int k = 0; k < NVAR; ++k) rp.vars[k] = k;
@@ -386,21 +404,24 @@ int corner_field(astrea_ctx* c) {
     // bundle 1: face states of the x sweep, reconstructed along y (in the y frame), then brought to the x frame
     const Plane t1 = make_plane(c->ws.mem, nx, GHOST), d1y = make_plane(c->wp.mem, nx, GHOST), u1y = make_plane(c->wm.mem, nx, GHOST);
     if (int e = transpose_plane(c, c->wfx.plane, t1, nx, ny)) return e;
-    if (int e = transverse_ppm(t1, d1y, u1y, ny, ny, 0, nx)) return e;
+    // cells 0..ny along y (pad(wD)[1:] needs cell ny when periodic); one more column of x when the row behind the slab is genuine
+    if (int e = transverse_ppm(t1, d1y, u1y, ny, ny, 0, xh ? nx + 1 : nx, edge ? ny - 1 : ny)) return e;
     const Plane d1 = make_plane(c->qT.mem, ny, GHOST), u1 = make_plane(c->ws.mem, ny, GHOST);
     if (int e = transpose_plane(c, d1y, d1, ny, nx)) return e;
     if (int e = transpose_plane(c, u1y, u1, ny, nx)) return e;
     // bundle 0: face states of the y sweep, reconstructed along x (x frame)
     const Plane t0 = make_plane(c->wp.mem, ny, GHOST), d0 = make_plane(c->wm.mem, ny, GHOST), u0 = make_plane(c->ct0.mem, ny, GHOST);
     if (int e = transpose_plane(c, c->wfy.plane, t0, ny, nx)) return e;
-    if (int e = transverse_ppm(t0, d0, u0, nx, g.nx_global, g.x_offset, ny)) return e;
+    // cells 0..nx (+1 behind a slab: the corner row nx needs wD of cell nx + 1)
+    if (int e = transverse_ppm(t0, d0, u0, nx, g.nx_global, g.x_offset, ny, xh ? nx + 1 : (edge ? nx - 1 : nx))) return e;
+    c->emf_rows = xh ? nx + 1 : nx;
     CornerEmfParams ep{d0, u0, d1, u1, c->emf, nx, ny, g.nx_global, g.x_offset, g.gamma, g.boundary, c->parity};
     Timed timed(c, CLS_UPDATE);
-    ASTREA_TRY(launch<CornerEmfKernel>(ep, (int)((ny + 127) / 128), (int)nx, 128, 0, c->st));
+    ASTREA_TRY(launch<CornerEmfKernel>(ep, (int)((ny + 127) / 128), (int)c->emf_rows, 128, 0, c->st));
     return 0;
 }
 
-int run_special(astrea_ctx* c, const Instr& ins) {
+int run_special(astrea_ctx* c, const Instr& ins, int external_rows) {
     const astrea_cfg& g = c->cfg;
     if (ins.special == SP_FACE_FIELD) {
         FaceFieldParams fp{c->regs[c->grid_reg].plane, c->wfx.plane, c->wfy.plane, c->nrow, c->ncol};
@@ -410,7 +431,7 @@ int run_special(astrea_ctx* c, const Instr& ins) {
     }
     // refine_grid = mag_field.inverse_reconstruct on register `out`
     Plane reg = c->regs[ins.out].plane;
-    if (int e = fill_halo(c, reg, 0)) return e;
+    if (int e = fill_halo(c, reg, external_rows)) return e;
     RefineFieldParams rp{reg, make_plane(c->ws.mem, c->ncol, GHOST), c->nrow, c->ncol, g.nx_global, g.x_offset, g.boundary, 0};
     const int gx = (int)((c->ncol + 127) / 128);
     { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, (int)c->nrow, 128, 0, c->st)); }
@@ -423,7 +444,7 @@ RateParams rate_params(astrea_ctx* c) {
     const astrea_cfg& g = c->cfg;
     RateParams r{};
     r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane;
-    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr;
+    r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr; r.emf_rows = c->emf_rows;
     r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
     r.vars = c->vars();
     r.row_lo = 0; r.row_hi = c->nrow;
@@ -461,6 +482,11 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
             pb.q = q; pb.wx = make_plane(c->ws.mem, c->ncol, GHOST); pb.wy = make_plane(c->ws2.mem, c->nrow, GHOST);
             pb.gamma = g.gamma; pb.high_order = ho ? 1 : 0;
             pb.r_lo = -(int64_t)(lo + 1); pb.r_hi = c->nrow + hi + 2; pb.c_lo = -(int64_t)(lo + 1); pb.c_hi = c->ncol + hi + 2;
+            if (g.magnetic_2d && c->slab()) {
+                // constrained transport reconstructs the y-sweep face states along x: they are recomputed in the
+                // ghost rows of a slab (CT_LO / CT_HI cells deep) instead of being exchanged
+                pb.r_lo = std::min<int64_t>(pb.r_lo, -(int64_t)CT_LO); pb.r_hi = std::max<int64_t>(pb.r_hi, c->nrow + CT_HI);
+            }
             pb.r_min = -(int64_t)GHOST; pb.r_max = c->nrow + GHOST - 1; pb.c_min = -(int64_t)GHOST; pb.c_max = c->ncol + GHOST - 1;
             const int gx = (int)((pb.c_hi - pb.c_lo + PrimBothStage<false>::TX - 1) / PrimBothStage<false>::TX);
             const int gy = (int)((pb.r_hi - pb.r_lo + PrimBothStage<false>::TY - 1) / PrimBothStage<false>::TY);
@@ -491,6 +517,10 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 PrimStageParams pp{};
                 pp.q = qf; pp.w = ws; pp.gamma = g.gamma; pp.high_order = ho ? 1 : 0;
                 pp.r_lo = -(int64_t)(lo + 1); pp.r_hi = ns + hi + 2; pp.c_lo = -(int64_t)ht; pp.c_hi = nt + ht;
+                if (g.magnetic_2d && ax == 1) {      // pcm.py:35: the face state is wS itself, also in the ghost rows of a slab
+                    if (c->ext_lo()) pp.c_lo = -(int64_t)CT_LO;
+                    if (c->ext_hi()) pp.c_hi = nt + CT_HI;
+                }
                 pp.r_min = -(int64_t)GHOST; pp.r_max = ns + GHOST - 1; pp.c_min = -(int64_t)GHOST; pp.c_max = nt + GHOST - 1;
                 const int gx = (int)((pp.c_hi - pp.c_lo + PrimStage<false>::TX - 1) / PrimStage<false>::TX);
                 const int gy = (int)((pp.r_hi - pp.r_lo + PrimStage<false>::TY - 1) / PrimStage<false>::TY);
@@ -505,6 +535,10 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 rp.w = ws; rp.wp = wp; rp.wm = wm; rp.wf = Plane{nullptr, 0, 0};
                 if (g.magnetic_2d) rp.wf = (ax == 0) ? c->wfx.plane : c->wfy.plane;       // data[axes]['wF'] (plm.py:57, ppm.py:101, weno.py:184)
                 rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = -(int64_t)ht; rp.c_hi = nt + ht;
+                if (g.magnetic_2d && ax == 1) {      // face states of the y sweep in the ghost rows of a slab (columns here)
+                    if (c->ext_lo()) rp.c_lo = -(int64_t)CT_LO;
+                    if (c->ext_hi()) rp.c_hi = nt + CT_HI;
+                }
                 rp.i_lo = i_lo; rp.i_hi = i_hi; rp.bc = g.boundary; rp.limiter = g.limiter;
                 rp.seg = g.segment_2d > 0 ? g.segment_2d : 64;
                 const VarList vl = c->vars();
@@ -610,7 +644,6 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
             why = "magnetic_2d with a Lax-type solver takes corner speeds from np.linalg.eigvals (mag_field.py:152-159): not on the device path";
             return -1;
         }
-        if (g->nx != g->nx_global) { why = "magnetic_2d grids are not decomposed in this build"; return -1; }
     }
     if (g->dimension == 1) {
         if (g->nx < 1 || g->ny != 1) { why = "1D: nx >= 1 cells, ny == 1"; return -1; }
@@ -661,7 +694,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
         ok = ok && alloc_reg(c, c->ws, c->ncol) && alloc_reg(c, c->ws2, c->nrow) && alloc_reg(c, c->wp, c->ncol) && alloc_reg(c, c->wm, c->ncol);
         if (g.magnetic_2d) {
             ok = ok && alloc_reg(c, c->wfx, c->ncol) && alloc_reg(c, c->wfy, c->nrow) && alloc_reg(c, c->ct0, c->ncol);
-            c->emf = (double*)dev_alloc(sizeof(double) * (size_t)c->nrow * c->ncol);
+            c->emf = (double*)dev_alloc(sizeof(double) * (size_t)(c->nrow + 1) * c->ncol);
             ok = ok && c->emf;
         }
     } else {
@@ -773,10 +806,15 @@ int astrea_run_instr(astrea_ctx* c, int i, int external_rows) {
     if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_instr: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
     const Instr& ins = c->prog[i];
     const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0)
-                                  : (ins.special != SP_NONE ? run_special(c, ins) : run_combine(c, ins, 0, c->nrow));
+                                  : (ins.special != SP_NONE ? run_special(c, ins, external_rows) : run_combine(c, ins, 0, c->nrow));
     if (e) return e;
     c->next_instr = i + 1;
     return 0;
+}
+
+int astrea_instr_needs_halo(const astrea_ctx* c, int i) {
+    if (!c || i < 0 || i >= (int)c->prog.size()) return ASTREA_E_ARG;
+    return needs_ghost_rows(c->prog[i]) ? 1 : 0;
 }
 
 int astrea_instr_is_update(const astrea_ctx* c, int i) {
@@ -980,8 +1018,8 @@ int astrea_halo_info(const astrea_ctx* c, int64_t* ghost_rows, int64_t* doubles_
 }
 
 int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, double** recv_lo, double** recv_hi) {
-    if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_ptrs: not an operator instruction");
-    const Plane& p = c->regs[c->prog[i].src].plane;
+    if (!c || i < 0 || i >= (int)c->prog.size() || !needs_ghost_rows(c->prog[i])) return fail(c, ASTREA_E_ARG, "astrea_halo_ptrs: the instruction reads no ghost rows");
+    const Plane& p = c->regs[halo_register(c->prog[i])].plane;
     // whole padded rows (ghost columns included): the receiver's corner ghosts come along for free; the ghost
     // columns of the interior rows sent here are filled by astrea_halo_prepare()
     double* row0 = p.base - GHOST;
@@ -993,9 +1031,9 @@ int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, d
 }
 
 int astrea_halo_prepare(astrea_ctx* c, int i) {
-    if (!c || i < 0 || i >= (int)c->prog.size() || !c->prog[i].is_operator) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: not an operator instruction");
+    if (!c || i < 0 || i >= (int)c->prog.size() || !needs_ghost_rows(c->prog[i])) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: the instruction reads no ghost rows");
     // only the first / last ghost_r interior rows travel: fill their ghost columns
-    HaloParams h{c->regs[c->prog[i].src].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars(), 0};
+    HaloParams h{c->regs[halo_register(c->prog[i])].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars(), 0, 0, 0};
     const int rows = (int)std::min<int64_t>(c->ghost_r, c->nrow);
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, rows, 64, 0, c->st)); }
     h.row0 = c->nrow - rows;

@@ -47,6 +47,7 @@ struct HaloParams {
     int fill_lo, fill_hi; // phase 1: which row ghosts to fill locally (0 when a neighbour rank provides them)
     VarList vars;
     int64_t row0;         // phase 0: first interior row to treat (blockIdx.y counts from here)
+    int skip_col_lo, skip_col_hi;   // phase 0: leave the low / high ghost columns alone (they hold genuine neighbour data)
 };
 struct HaloKernel {
     using Params = HaloParams;
@@ -61,6 +62,7 @@ struct HaloKernel {
                 const int64_t r = p.row0 + by;
                 for (int e = tid; e < 2 * GHOST * p.vars.n; e += NT) {
                     const int v = p.vars.v[e / (2 * GHOST)], g = e % (2 * GHOST);
+                    if ((g < GHOST && p.skip_col_lo) || (g >= GHOST && p.skip_col_hi)) continue;
                     const int64_t c = g < GHOST ? g - GHOST : p.ncol + (g - GHOST);
                     *p.plane.at(r, v, c) = *p.plane.at(r, v, src(c, p.ncol, p.bc));
                 }
@@ -125,6 +127,7 @@ struct RateParams {
     int dimension;
     // constrained transport (evolvers.py:52-58): overwrite the in-plane field rates with emf differences
     const double* emf;    // corner field [x][y] (pitch ncol), or nullptr
+    int64_t emf_rows;     // rows of emf that hold data: nrow, or nrow + 1 when the row behind the slab was computed from ghost data
     int64_t nx_glob, x_off;
     double dx;
     int bc;
@@ -174,7 +177,7 @@ struct RateKernel {
                             const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
                             total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
                         } else {
-                            const int64_t rn = r + 1 < p.nrow ? r + 1 : (wrap ? 0 : p.nrow - 1);
+                            const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
                             total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
                         }
                     }
@@ -315,7 +318,7 @@ struct UpdateKernel {
                             const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
                             total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
                         } else {
-                            const int64_t rn = r + 1 < p.nrow ? r + 1 : (wrap ? 0 : p.nrow - 1);
+                            const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
                             total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
                         }
                     }

@@ -175,6 +175,7 @@ class Simulation:
         self.t, self.steps_done = 0.0, 0
         self._program = self.ctx.program()
         self._updates = self.ctx.updates()
+        self._readers = self.ctx.halo_readers()    # instructions that read ghost rows (operators, refine_grid)
         self._halo_ready = False          # the ghost rows of the grid were already exchanged behind the last update
         self.overlap = overlap
         if grid is None:
@@ -211,6 +212,10 @@ class Simulation:
                     self._halo_ready = True
                 else:
                     ready.add(i + 1)
+            elif self._readers[i]:
+                # refine_grid of constrained transport reads the ghost rows of the register it refines
+                ex.halo(i)
+                ctx.run_instr(i, external_rows=True)
             else:
                 ctx.run_instr(i)
         ctx.finish_step()

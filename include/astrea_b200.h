@@ -117,6 +117,10 @@ int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);
  * Each halo block is ghost_rows x 8 variables x col_pitch doubles, contiguous (the [row][var][col] layout). */
 int astrea_program_length(const astrea_ctx* ctx);
 int astrea_instr_is_operator(const astrea_ctx* ctx, int instr);
+/* 1 if instruction `instr` reads ghost rows of a register (a spatial operator, or the inverse reconstruction of
+ * constrained transport): a slab host exchanges them first (astrea_halo_prepare / astrea_halo_ptrs) and passes
+ * external_rows = 1 to astrea_run_instr */
+int astrea_instr_needs_halo(const astrea_ctx* ctx, int instr);
 /* 1 if instruction `instr` is a Runge-Kutta register update (not an operator, not a constrained-transport special) */
 int astrea_instr_is_update(const astrea_ctx* ctx, int instr);
 /* A register update in two parts, so that a slab host can overlap the halo exchange of the register it produces

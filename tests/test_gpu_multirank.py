@@ -41,7 +41,8 @@ def _worker(rank, world, port, spec, outdir, overlap):
 
 
 SPECS = [("ll3", 256, "ppm", "hllc", "ssprk(3,3)", "wrap", 2), ("ll4", 256, "weno5", "lf", "ssprk(2,2)", "edge", 3),
-         ("khi", 192, "plm", "hllc", "rk4", "wrap", 2)]
+         ("khi", 192, "plm", "hllc", "rk4", "wrap", 2), ("orszag-tang", 192, "plm", "hlld", "ssprk(3,3)", "wrap", 3),
+         ("orszag-tang", 160, "ppm", "hlld", "ssprk(2,2)", "edge", 2)]
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
