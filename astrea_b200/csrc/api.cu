@@ -640,10 +640,6 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
     if (g->integrator < ASTREA_EULER || g->integrator > ASTREA_SSPRK104) { why = "unknown integrator"; return -1; }
     if (g->magnetic_2d) {
         if (g->dimension != 2) { why = "magnetic_2d needs dimension == 2"; return -1; }
-        if (g->solver != ASTREA_HLLC && g->solver != ASTREA_HLLD) {
-            why = "magnetic_2d with a Lax-type solver takes corner speeds from np.linalg.eigvals (mag_field.py:152-159): not on the device path";
-            return -1;
-        }
     }
     if (g->dimension == 1) {
         if (g->nx < 1 || g->ny != 1) { why = "1D: nx >= 1 cells, ny == 1"; return -1; }

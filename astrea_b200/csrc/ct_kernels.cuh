@@ -29,7 +29,9 @@ struct CornerEmfParams {
 struct CornerEmfKernel {
     using Params = CornerEmfParams;
     static constexpr int MAX_THREADS = 128;
-    // mag_field.py:128-149 ('hll' branch): a+ = max(0, v_n + c_f), a- = -min(0, v_n - c_f) at the Roe average
+    // mag_field.py:128-149 ('hll' branch): a+ = max(0, v_n + c_f), a- = -min(0, v_n - c_f) at the Roe average.
+    // The Lax-type branch (:152-159) takes max / -min of np.linalg.eigvals of the primitive Jacobian, whose spectrum
+    // contains 0, v_n +- c_f: the same two numbers up to LAPACK round-off, so this closed form serves every solver.
     template <int AXIS>
     static HD void speeds(const double* plus, const double* minus, double gamma, double& ap, double& am) {
         double avg[NVAR];

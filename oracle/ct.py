@@ -41,7 +41,10 @@ def corner_wavespeeds(wD, wU, cfg, axis):
     bc = cfg.boundary
     plus, minus = extended(wD, 0, 1, bc), extended(wU, 1, 0, bc)
     avg = roe_state(plus, minus)[1:]
-    if cfg.solver_category == "hll":
+    # mag_field.py:152-159 takes max / -min of np.linalg.eigvals for the Lax-type solvers; the spectrum contains 0 (the
+    # B_n row of the Jacobian is zero), so that is max(0, v_n + c_f) and -min(0, v_n - c_f) again: with eigen='closed'
+    # the oracle (like the device) evaluates the closed form for every solver.
+    if cfg.solver_category == "hll" or cfg.eigen == "closed":
         rho, P, B = avg[..., 0], avg[..., 4], avg[..., 5:8]
         vn, Bn = avg[..., 1 + axis % 3], B[..., axis % 3]
         a = np.sqrt(cfg.gamma * safe_div(P, rho))

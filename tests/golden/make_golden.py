@@ -40,6 +40,8 @@ CASES = [
     ("x_shu_weno5_hllc_ssprk33_edge", "shu-osher", 128, 1, "weno5", "hllc", "ssprk(3,3)", 3, None),
     ("x_bw_plm_hlld_ssprk22", "brio-wu", 128, 1, "plm", "hlld", "ssprk(2,2)", 3, None),
     ("x_rj_ppm_hlld_ssprk33", "ryu-jones", 128, 1, "ppm", "hlld", "ssprk(3,3)", 3, None),
+    ("x_ot_plm_llf_ssprk22_ct", "orszag-tang", 32, 2, "plm", "lf", "ssprk(2,2)", 3, None),
+    ("x_ot_ppm_hllc_ssprk33_ct", "orszag-tang", 32, 2, "ppm", "hllc", "ssprk(3,3)", 2, None),
 ]
 
 
