@@ -50,6 +50,7 @@ _SIGNATURES = {
     "astrea_last_error": (C.c_char_p, [C.c_void_p]),
     "astrea_upload": (C.c_int, [C.c_void_p, C.c_void_p]),
     "astrea_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "astrea_diagnostics": (C.c_int, [C.c_void_p, _PD, _PD, C.c_int]),
     "astrea_evolve_space": (C.c_int, [C.c_void_p, C.c_int, _PD]),
     "astrea_evolve_time": (C.c_int, [C.c_void_p, C.c_double]),
     "astrea_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _PD]),
@@ -150,9 +151,17 @@ class Context:
         self._check(self.lib.astrea_upload(self._h, host_ptr))
 
     def download(self, primitive=False, out=None):
+        """``primitive``: False = conservative averages, True = the astrea.py:47 snapshot, 2 = the same on a slab whose
+        ghost rows the caller has exchanged."""
         out = np.empty(self.shape, dtype=np.float64) if out is None else out
-        self._check(self.lib.astrea_download(self._h, out.ctypes.data, 1 if primitive else 0))
+        self._check(self.lib.astrea_download(self._h, out.ctypes.data, int(primitive)))
         return out
+
+    def diagnostics(self, external_rows=False):
+        """(totals[8], total_variation[8]) of the current grid, reduced on the device (functions/analytic.py:48-77)."""
+        tot, tv = (C.c_double * 8)(), (C.c_double * 8)()
+        self._check(self.lib.astrea_diagnostics(self._h, tot, tv, 1 if external_rows else 0))
+        return np.array(tot), np.array(tv)
 
     def download_ptr(self, host_ptr, primitive=False):
         self._check(self.lib.astrea_download(self._h, host_ptr, 1 if primitive else 0))

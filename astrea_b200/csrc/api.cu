@@ -767,9 +767,9 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_download: a step is in flight (between evolve_space and evolve_time the scratch planes are live)");
     Plane src = c->regs[c->grid_reg].plane;
     if (as_primitive) {
-        if (c->cfg.nx != c->cfg.nx_global && c->cfg.dimension == 2 && scheme_high_order(c->cfg.scheme))
-            return fail(c, ASTREA_E_STATE, "astrea_download: primitive download of a slab needs the caller to exchange ghost rows first (use astrea_download_primitive_ext)");
-        if (int e = fill_halo(c, src, 0)) return e;
+        if (as_primitive != 2 && c->slab() && scheme_high_order(c->cfg.scheme))
+            return fail(c, ASTREA_E_STATE, "astrea_download: the 4th-order primitive snapshot of a slab reads ghost rows: exchange those of instruction 0 first and pass as_primitive = 2");
+        if (int e = fill_halo(c, src, as_primitive == 2 ? 1 : 0)) return e;
         Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r);
         PrimParams pp{src, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
         { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
@@ -781,6 +781,31 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     ASTREA_TRY(copy_d2h(grid_aos, staging, bytes, c->st));
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_download: stream sync failed");
+}
+
+int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, int external_rows) {
+    if (!c || !totals || !total_variation) return fail(c, ASTREA_E_ARG, "astrea_diagnostics: NULL argument");
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_diagnostics: a step is in flight");
+    Plane q = c->regs[c->grid_reg].plane;
+    if (int e = fill_halo(c, q, external_rows)) return e;
+    Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r);
+    PrimParams pp{q, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    const int gx = (int)((c->ncol + 255) / 256), gy = (int)c->nrow;
+    const size_t n = (size_t)gx * gy * 2 * NVAR;
+    double* partial = c->d0.mem;          // scratch between steps
+    DiagParams dp{q, w, c->nrow, c->ncol, c->cfg.dimension, partial};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<DiagKernel>(dp, gx, gy, 256, DiagKernel::smem_bytes(), c->st)); }
+    std::vector<double> host(n);
+    ASTREA_TRY(copy_d2h(host.data(), partial, n * sizeof(double), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_diagnostics: stream sync failed");
+    for (int k = 0; k < NVAR; ++k) { totals[k] = 0.0; total_variation[k] = 0.0; }
+    for (size_t b = 0; b < (size_t)gx * gy; ++b)
+        for (int k = 0; k < NVAR; ++k) {
+            totals[k] += host[b * 2 * NVAR + k];
+            total_variation[k] += host[b * 2 * NVAR + NVAR + k];
+        }
+    return 0;
 }
 
 int astrea_program_length(const astrea_ctx* c) { return c ? (int)c->prog.size() : ASTREA_E_ARG; }

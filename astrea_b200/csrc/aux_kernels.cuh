@@ -449,4 +449,54 @@ struct PrimKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ diagnostics
+// Device-side reductions of the post-processing the reference does on its HDF5 snapshots (functions/analytic.py):
+//   conservation (:66-77)    sum over the grid of every conservative variable
+//   total variation (:48-62) sum of |np.diff along every axis in turn| of the primitive snapshot
+// One partial result per block and variable, combined on the host in block order: deterministic.
+struct DiagParams {
+    Plane q;              // conservative cell averages
+    Plane w;              // primitive snapshot (PrimKernel output)
+    int64_t nrow, ncol;
+    int dimension;
+    double* partial;      // [gridDim.y * gridDim.x][2 * NVAR]: sums, then total variations
+};
+struct DiagKernel {
+    using Params = DiagParams;
+    static constexpr int MAX_THREADS = 256;
+    static size_t smem_bytes() { return sizeof(double) * MAX_THREADS; }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        double* red = ex.smem();
+        const int64_t r = by;
+        for (int k = 0; k < 2 * NVAR; ++k) {
+            const int v = k % NVAR;
+            ex.phase([&](int tid) {
+                const int64_t c = (int64_t)bx * NT + tid;
+                double x = 0.0;
+                if (c < p.ncol) {
+                    if (k < NVAR) {
+                        x = *p.q.at(r, v, c);
+                    } else if (p.dimension == 1) {
+                        if (c + 1 < p.ncol) x = fabs(*p.w.at(r, v, c + 1) - *p.w.at(r, v, c));
+                    } else if (c + 1 < p.ncol && r + 1 < p.nrow) {
+                        // np.diff along axis 0, then along axis 1
+                        const double d0 = *p.w.at(r + 1, v, c) - *p.w.at(r, v, c);
+                        const double d1 = *p.w.at(r + 1, v, c + 1) - *p.w.at(r, v, c + 1);
+                        x = fabs(d1 - d0);
+                    }
+                }
+                red[tid] = x;
+            });
+            for (int stride = NT / 2; stride > 0; stride >>= 1) {
+                ex.phase([&](int tid) { if (tid < stride) red[tid] = red[tid] + red[tid + stride]; });
+            }
+            ex.phase([&](int tid) {
+                if (tid == 0) p.partial[((int64_t)by * ((p.ncol + NT - 1) / NT) + bx) * 2 * NVAR + k] = red[0];
+            });
+        }
+    }
+};
+
 }  // namespace astrea

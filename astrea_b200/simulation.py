@@ -157,6 +157,7 @@ class Simulation:
         prob = problem(self.config, self.cells, gamma)
         self.boundary = boundary or prob["boundary"]
         self.dx, self.t_end = prob["dx"], prob["t_end"]
+        self.start_pos, self.end_pos = prob["start_pos"], prob["end_pos"]
         self.cfl, self.gamma = cfl, gamma
         self.rank, self.world = rank, world
         self.high_order = scheme_enum(subgrid) >= N.PPM
@@ -290,9 +291,33 @@ class Simulation:
 
     def state(self, primitive=False):
         """This rank's rows as the reference's ndarray (conservative averages, or the astrea.py:47 primitive snapshot)."""
-        if primitive and self.exchange is not None and self.high_order:
-            raise NotImplementedError("primitive snapshots of a decomposed 4th-order run: gather the conservative state instead")
+        if primitive and self.exchange is not None:
+            self.exchange.halo(0)                  # the 4th-order conversion reads one ghost row
+            self._halo_ready = False
+            return self.ctx.download(primitive=2)
         return self.ctx.download(primitive=primitive)
+
+    def snapshot(self):
+        """What astrea.py:47-50 stores per step: the primitive grid transposed by ``ortho_axis`` ((y, x, 8) in 2D)."""
+        w = self.state(primitive=True)
+        return w.transpose(1, 0, 2) if self.dimension == 2 else w
+
+    def diagnostics(self):
+        """Conservation totals (times the box volume, functions/analytic.py:66-77) and total variation (:48-62) of the
+        current grid, reduced on the device; summed over the ranks of a decomposed run (the total variation then
+        misses the differences across slab seams)."""
+        if self.exchange is not None:
+            self.exchange.halo(0)
+            self._halo_ready = False
+            tot, tv = self.ctx.diagnostics(external_rows=True)
+            t = self.exchange.torch.tensor(np.concatenate([tot, tv]), dtype=self.exchange.torch.float64,
+                                           device="cuda" if self.on_device else "cpu")
+            self.exchange.dist.all_reduce(t)
+            tot, tv = t[:8].cpu().numpy(), t[8:].cpu().numpy()
+        else:
+            tot, tv = self.ctx.diagnostics()
+        box = abs(self.end_pos - self.start_pos) ** self.dimension
+        return tot * box, tv
 
     def sync(self):
         self.ctx.sync()

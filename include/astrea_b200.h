@@ -74,7 +74,8 @@ const char* astrea_last_error(const astrea_ctx* ctx);   /* ctx may be NULL: erro
  * the `grid` argument of astrea.py:67) -> device. */
 int astrea_upload(astrea_ctx* ctx, const double* grid_aos);
 /* device -> host, same layout.  as_primitive != 0 applies sim_variables.convert_conservative first, i.e. what
- * astrea.py:47 snapshots (without its transpose). */
+ * astrea.py:47 snapshots (without its transpose); as_primitive == 2: the caller (a slab host) has already exchanged
+ * the ghost rows of instruction 0, which the 4th-order conversion reads. */
 int astrea_download(astrea_ctx* ctx, double* grid_aos, int as_primitive);
 
 /* evolvers.evolve_space(grid, sim_variables) for the uploaded grid (astrea.py:67).  step_parity = number of
@@ -102,6 +103,12 @@ int astrea_dt_history(astrea_ctx* ctx, double* out, int n);
 int astrea_dt_async(astrea_ctx* ctx);
 int astrea_get_parity(const astrea_ctx* ctx);
 int astrea_set_parity(astrea_ctx* ctx, int step_parity);
+
+/* Reductions of the current grid on the device, the quantities functions/analytic.py computes from the HDF5 snapshots:
+ * totals[8] = sum over the (local) cells of every conservative variable (calculate_conservation, :66-77, before its
+ * box-width factor); total_variation[8] = sum of |np.diff along every axis in turn| of the primitive snapshot
+ * (calculate_TV, :48-62).  Deterministic (fixed reduction order).  external_rows as in astrea_run_instr. */
+int astrea_diagnostics(astrea_ctx* ctx, double* totals, double* total_variation, int external_rows);
 
 /* magnetic_2d only: evolve_time overwrites the in-plane B of the caller's grid with face averages before the
  * stages (evolvers.py:73-76).  Copies those two components (host array (nx,ny,2): Bx, By). */

@@ -290,3 +290,41 @@ def test_drop_in_behind_the_reference_time_loop(hostsim_lib):
         ours.release()
         assert np.allclose(used, dts, rtol=1e-12, atol=0)
         assert np.all(rel_l1(grid, want[-1]) <= 1e-10), (config, rel_l1(grid, want[-1]))
+
+
+@pytest.mark.parametrize("dim,subgrid", [(1, "plm"), (2, "ppm"), (2, "plm")])
+def test_device_diagnostics(hostsim_lib, dim, subgrid):
+    """Conservation totals and total variation (functions/analytic.py:48-77) reduced on the device."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle.gridops import prim_avg_of_cons_avg
+    cells = 300 if dim == 1 else 70
+    config = "sod" if dim == 1 else "khi"
+    meta = _meta(config, cells, dim, subgrid, "hllc", "ssprk(2,2)", None)
+    g0 = initial_state(config, cells, dim, 1.4, subgrid == "ppm")
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    ctx.step()
+    q = ctx.download()
+    tot, tv = ctx.diagnostics()
+    ctx.close()
+    w = prim_avg_of_cons_avg(q, oracle_cfg(meta))
+    d = w
+    for ax in range(dim):
+        d = np.diff(d, axis=ax)
+    axes = tuple(range(dim))
+    scale = np.abs(q).sum(axis=axes)          # summation order differs: compare against the size of the terms
+    assert np.all(np.abs(tot - q.sum(axis=axes)) <= 1e-13 * np.where(scale > 0, scale, 1))
+    assert np.allclose(tv, np.abs(d).sum(axis=axes), rtol=1e-12, atol=1e-13)
+
+
+def test_snapshot_layout(hostsim_lib):
+    """astrea.py:47: the stored snapshot is the primitive grid transposed by ortho_axis."""
+    from astrea_b200.simulation import Simulation
+    from cases import oracle_cfg
+    from oracle.gridops import prim_avg_of_cons_avg
+    sim = Simulation("ll3", 24, 2, "ppm", "hllc", "ssprk(3,3)", _lib=hostsim_lib)
+    meta = _meta("ll3", 24, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    want = prim_avg_of_cons_avg(sim.state(), oracle_cfg(meta)).transpose(1, 0, 2)
+    assert np.array_equal(sim.snapshot(), want)
+    sim.close()
