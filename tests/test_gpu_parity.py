@@ -272,3 +272,26 @@ def test_async_stepping_with_device_clock(lib, spec):
     assert steps == 2 and abs(t - t_stop) <= 1e-15 and np.allclose(ctx.dt_history(2), used, rtol=1e-12, atol=0)
     assert np.all(rel_l1(ctx.download(), want) <= 1e-10)
     ctx.close()
+
+
+def test_device_diagnostics(lib):
+    """Conservation totals and total variation (functions/analytic.py:48-77) reduced on the device, 2D and 1D."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg, oracle_cfg
+    from oracle.gridops import prim_avg_of_cons_avg
+    for dim, config, cells, subgrid in ((2, "khi", 300, "ppm"), (1, "sod", 1000, "plm")):
+        meta = _meta(config, cells, dim, subgrid, "hllc", "ssprk(2,2)", None)
+        g0 = initial_state(config, cells, dim, 1.4, subgrid == "ppm")
+        ctx = N.Context(native_cfg(meta), lib=lib)
+        ctx.upload(g0)
+        ctx.step()
+        q = ctx.download()
+        tot, tv = ctx.diagnostics()
+        ctx.close()
+        d = prim_avg_of_cons_avg(q, oracle_cfg(meta))
+        for ax in range(dim):
+            d = np.diff(d, axis=ax)
+        axes = tuple(range(dim))
+        scale = np.abs(q).sum(axis=axes)
+        assert np.all(np.abs(tot - q.sum(axis=axes)) <= 1e-13 * np.where(scale > 0, scale, 1))
+        assert np.allclose(tv, np.abs(d).sum(axis=axes), rtol=1e-12, atol=1e-12)
