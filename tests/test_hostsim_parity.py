@@ -328,3 +328,21 @@ def test_snapshot_layout(hostsim_lib):
     want = prim_avg_of_cons_avg(sim.state(), oracle_cfg(meta)).transpose(1, 0, 2)
     assert np.array_equal(sim.snapshot(), want)
     sim.close()
+
+
+def test_tiny_grids(hostsim_lib):
+    """4 and 6 cells per side: every stencil wraps or clamps across the whole grid (ghost depth > grid size)."""
+    from astrea_b200.selectors import MAGNETIC_2D
+    for dim, config in ((1, "sod"), (2, "ll3"), (2, "orszag-tang")):
+        for cells in (4, 6):
+            for subgrid in ("pcm", "plm", "ppm", "weno5", "weno7"):
+                for solver, bc in (("lf", "wrap"), ("hllc", "edge"), ("hlld", "wrap")):
+                    mhd = config in MAGNETIC_2D
+                    meta = _meta(config, cells, dim, subgrid, solver, "ssprk(2,2)", bc, mhd=mhd)
+                    g0 = initial_state(config, cells, dim, 1.4, subgrid in ("ppm", "weno5", "weno7"), boundary=bc)
+                    try:
+                        want, dts = run_oracle(meta, g0, 2)
+                    except np.linalg.LinAlgError:
+                        continue
+                    got, used, _ = run_native(hostsim_lib, meta, g0, 2)
+                    assert used == dts and np.array_equal(got, want, equal_nan=True), (dim, config, cells, subgrid, solver, bc)
