@@ -1,3 +1,5 @@
+"""Small runs of every kernel family for `compute-sanitizer --tool memcheck|racecheck python tests/sanitize_smoke.py`
+(SURVEY.md §5).  Not a pytest module."""
 import sys
 sys.path.insert(0, '.')
 import numpy as np
@@ -12,7 +14,11 @@ for config, cells, dim, sub, sol, ts, mhd, bc in (("ll3", 70, 2, "ppm", "hllc", 
     cfg = make_cfg(dimension=dim, cells=cells, boundary=b, gamma=1.4, dx=pr["dx"], cfl=.5, subgrid=sub, solver=sol, timestep=ts, magnetic_2d=mhd)
     ctx = N.Context(cfg)
     ctx.upload(initial_state(config, cells, dim, 1.4, sub in ("ppm", "weno5", "weno7"), boundary=b))
-    ctx.step(); ctx.step()
-    ctx.set_time(0.0, 0.0); ctx.step_async(); ctx.step_async(); ctx.step_async()
-    print(config, sub, sol, ctx.get_time(), np.isfinite(ctx.download(primitive=True)).all(), ctx.diagnostics()[0][:2])
+    try:
+        ctx.step()
+        ctx.set_time(0.0, 0.0)
+        ctx.step_async()
+        print(config, sub, sol, ctx.get_time(), np.isfinite(ctx.download(primitive=True)).all(), ctx.diagnostics()[0][:2])
+    except np.linalg.LinAlgError as err:         # some of the reference's configurations die within a few steps
+        print(config, sub, sol, "non-finite:", err)
     ctx.close()
