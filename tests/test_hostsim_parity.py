@@ -346,3 +346,63 @@ def test_tiny_grids(hostsim_lib):
                         continue
                     got, used, _ = run_native(hostsim_lib, meta, g0, 2)
                     assert used == dts and np.array_equal(got, want, equal_nan=True), (dim, config, cells, subgrid, solver, bc)
+
+
+def test_step_program_contract(hostsim_lib):
+    """Call-order rules of the instruction-level interface (include/astrea_b200.h): violations are reported, not ignored."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll3", 24, 2, "plm", "hllc", "ssprk(3,3)", None)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(initial_state("ll3", 24, 2, 1.4, False))
+    prog, upd, readers = ctx.program(), ctx.updates(), ctx.halo_readers()
+    assert prog == [True, False, True, False, True, False] and upd == [not p for p in prog] and readers == prog
+    with pytest.raises(N.AstreaError) as err:
+        ctx.run_instr(2)                           # instruction 0 has not run
+    assert err.value.code == N.E_STATE
+    with pytest.raises(N.AstreaError) as err:
+        ctx.halo_ptrs(1)                           # a register update reads no ghost rows
+    assert err.value.code == N.E_ARG
+    ctx.run_instr(0)
+    for call in (lambda: ctx.download(), lambda: ctx.diagnostics(), lambda: ctx.save_state(), lambda: ctx.finish_step()):
+        with pytest.raises(N.AstreaError) as err:
+            call()                                 # a step is in flight
+        assert err.value.code == N.E_STATE
+    with pytest.raises(N.AstreaError):
+        ctx.run_update_part(0, 0)                  # not a register update
+    ctx.set_dt(1e-4)
+    ctx.run_update_part(1, 0)
+    ctx.run_update_part(1, 1)
+    for i in range(2, len(prog)):
+        ctx.run_instr(i)
+    ctx.finish_step()
+    assert ctx.parity == 1
+    with pytest.raises(N.AstreaError):
+        ctx.dt_history(5)                          # no asynchronous step has been taken
+    ctx.close()
+
+
+def test_split_update_equals_whole_update(hostsim_lib):
+    """astrea_run_update_part (edge rows, then interior rows) gives the same register as the undivided update."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll6", 80, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    g0 = initial_state("ll6", 80, 2, 1.4, True)
+    results = []
+    for split in (False, True):
+        ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+        ctx.upload(g0)
+        ctx.run_instr(0)
+        ctx.set_dt(2e-3)
+        for i, is_update in enumerate(ctx.updates()):
+            if i == 0:
+                continue
+            if is_update and split:
+                ctx.run_update_part(i, 0)
+                ctx.run_update_part(i, 1)
+            else:
+                ctx.run_instr(i)
+        ctx.finish_step()
+        results.append(ctx.download())
+        ctx.close()
+    assert np.array_equal(results[0], results[1])
