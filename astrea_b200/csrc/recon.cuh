@@ -59,28 +59,21 @@ HD double ppm_d3(const A& acc, int64_t k) {    // limiters.py:96 at (mapped) cel
     return ppm_d2c(acc, acc.b(k + 1)) - ppm_d2c(acc, k);
 }
 
-// McCorquodale & Colella limiter.  ``wF`` returns the face value kept for constrained transport (ppm.py:101).
+// McCorquodale & Colella limiter (limiters.py:89-143) from the gathered stencil quantities of one cell:
+// cell averages c, m1, p1, m2, p2, the two face values, the central second differences at i-1, i, i+1 and the
+// third differences at i-2, i-1, i, i+2 (limiters.py:126-129 really skips i+1).
 // The reference's grid-wide ``if cell_extrema.any()`` needs no reduction: when no extremum exists anywhere its
 // else-branch produces the same numbers as the if-branch, so the if-branch is always taken here.
-template <class A>
-HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, double& wF) {
+HD void ppm_mc_limit(double c, double m1, double p1, double m2, double p2, double faceL, double faceR, double d2c_m1, double d2c,
+                     double d2c_p1, double d3_m2, double d3_m1, double d3, double d3_p2, double& wL, double& wR) {
     const double C = 5.0 / 4.0;
-    const double c = acc.s(i);
-    const double m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
-    const double faceR = 7.0 / 12.0 * (c + p1) - 1.0 / 12.0 * (m1 + p2);
-    const double faceL = ppm_face(acc, acc.b(i - 1));
-    wF = faceR;
     const double dwm = c - faceL, dwp = faceR - c;
     const double d2f = 6.0 * (faceL - 2.0 * c + faceR);
-    const double d2c = m1 - 2.0 * c + p1;
-    const double d2c_m1 = ppm_d2c(acc, acc.b(i - 1)), d2c_p1 = ppm_d2c(acc, acc.b(i + 1));
-    const double d3 = d2c_p1 - d2c;
     const bool extremum = (dwm * dwp <= 0.0) || ((c - m2) * (p2 - c) <= 0.0);
     double d2lim = 0.0;
     if (extremum) d2lim = npsign(d2c) * npmin(npmin(fabs(d2f), C * fabs(d2c)), npmin(C * fabs(d2c_p1), C * fabs(d2c_m1)));
     const double scale = npmax(fabs(c), npmax(npmax(fabs(m1), fabs(p1)), npmax(fabs(m2), fabs(p2))));
     const double rho = (fabs(d2f) > 1e-12 * scale) ? sdiv(d2lim, d2f) : 0.0;
-    const double d3_m1 = ppm_d3(acc, acc.b(i - 1)), d3_m2 = ppm_d3(acc, acc.b(i - 2)), d3_p2 = ppm_d3(acc, acc.b(i + 2));
     const double d3min = npmin(npmin(d3_m1, d3), npmin(d3_m2, d3_p2));
     const double d3max = npmax(npmax(d3_m1, d3), npmax(d3_m2, d3_p2));
     const bool act = (rho < (1.0 - 1e-12)) || (0.1 * npmax(fabs(d3max), fabs(d3min)) <= (d3max - d3min));
@@ -94,6 +87,48 @@ HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, doubl
         if (fabs(dwm) >= 2.0 * fabs(dwp)) wL = c - 2.0 * (1.0 - rho) * dwp - rho * dwm;
         if (fabs(dwp) >= 2.0 * fabs(dwm)) wR = c + 2.0 * (1.0 - rho) * dwm + rho * dwp;
     }
+}
+
+// Generic form over an accessor (any boundary map).  ``wF`` returns the face value kept for constrained transport (ppm.py:101).
+template <class A>
+HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, double& wF) {
+    const double c = acc.s(i);
+    const double m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
+    const double faceR = 7.0 / 12.0 * (c + p1) - 1.0 / 12.0 * (m1 + p2);
+    const double faceL = ppm_face(acc, acc.b(i - 1));
+    wF = faceR;
+    const double d2c = m1 - 2.0 * c + p1;
+    const double d2c_m1 = ppm_d2c(acc, acc.b(i - 1)), d2c_p1 = ppm_d2c(acc, acc.b(i + 1));
+    const double d3 = d2c_p1 - d2c;
+    const double d3_m1 = ppm_d3(acc, acc.b(i - 1)), d3_m2 = ppm_d3(acc, acc.b(i - 2)), d3_p2 = ppm_d3(acc, acc.b(i + 2));
+    ppm_mc_limit(c, m1, p1, m2, p2, faceL, faceR, d2c_m1, d2c, d2c_p1, d3_m2, d3_m1, d3, d3_p2, wL, wR);
+}
+
+// Marching form: the second differences d2c(i-2 .. i+3) and the two face values of the previous cell are carried
+// from one cell to the next (identical expressions, identical bits), so each cell evaluates one new second
+// difference and one new face value instead of six and two.  ``w`` points at the stencil value of the cell itself
+// (w[-3] .. w[4] valid, identity boundary map); ``fresh``: nothing to carry yet.
+struct PpmWindow {
+    double d2[6];      // d2c(i-2), .., d2c(i+3)
+    double face[2];    // face value at the left / right face of cell i
+};
+HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF) {
+    auto d2c = [&](int k) { return w[k - 1] - 2.0 * w[k] + w[k + 1]; };
+    auto face = [&](int k) { return 7.0 / 12.0 * (w[k] + w[k + 1]) - 1.0 / 12.0 * (w[k - 1] + w[k + 2]); };
+    if (fresh) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) win.d2[k] = d2c(k - 2);
+        win.face[0] = face(-1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) win.d2[k] = win.d2[k + 1];
+        win.face[0] = win.face[1];
+    }
+    win.d2[5] = d2c(3);
+    win.face[1] = face(0);
+    wF = win.face[1];
+    ppm_mc_limit(w[0], w[-1], w[1], w[-2], w[2], win.face[0], win.face[1], win.d2[1], win.d2[2], win.d2[3],
+                 win.d2[1] - win.d2[0], win.d2[2] - win.d2[1], win.d2[3] - win.d2[2], win.d2[5] - win.d2[4], wL, wR);
 }
 
 // ----------------------------------------------------------------------------------------- WENO

@@ -245,6 +245,8 @@ struct ReconStage {
             const int64_t rp = p.w.row_pitch;
             const bool edge = p.bc == BC_EDGE;
             double r[NW];
+            PpmWindow win;                                   // PPM: second differences / face values carried along the march
+            bool fresh = true;
 #pragma unroll
             for (int k = 0; k < NW - 1; ++k) r[k + 1] = col[(first - LO + k) * rp];
             double ahead = col[(first + HI) * rp];           // row i + HI, requested one iteration early
@@ -256,9 +258,13 @@ struct ReconStage {
                 const int64_t ig = i + p.s_off;
                 double wl, wr, wf;
                 if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
+                    fresh = true;
                     if (ig < 0 || ig > p.ns_glob - 1) continue;          // no such cell
                     ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
                     cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf);
+                } else if constexpr (SCHEME == SCH_PPM) {
+                    cell_faces_ppm_mc_march(r + LO, win, fresh, wl, wr, wf);
+                    fresh = false;
                 } else {
                     StencilAccessor<LO> acc{r};
                     cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf);
