@@ -295,3 +295,18 @@ def test_device_diagnostics(lib):
         scale = np.abs(q).sum(axis=axes)
         assert np.all(np.abs(tot - q.sum(axis=axes)) <= 1e-12 * np.where(scale > 0, scale, 1))   # summation order differs
         assert np.allclose(tv, np.abs(d).sum(axis=axes), rtol=1e-12, atol=1e-12)
+
+
+def test_hllc_low_mach_switch(lib):
+    """solvers.py:118-122 (off by default): goes through sin(), so the north-star tolerance applies, not bit equality."""
+    from cases import oracle_cfg
+    from oracle import advance
+    for dim, config, cells in ((1, "sod", 512), (2, "khi", 128)):
+        meta = _meta(config, cells, dim, "plm", "hllc", "ssprk(2,2)", None)
+        g0 = initial_state(config, cells, dim, 1.4, False)
+        cfg = oracle_cfg(meta)
+        cfg.low_mach = True
+        want, dts = advance(np.copy(g0), cfg, 2)
+        got, used, _ = run_native(lib, meta, g0, 2, low_mach=True)
+        assert np.allclose(used, dts, rtol=1e-13, atol=0)
+        assert np.all(rel_l1(got, want) <= 2e-12)

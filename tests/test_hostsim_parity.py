@@ -406,3 +406,21 @@ def test_split_update_equals_whole_update(hostsim_lib):
         results.append(ctx.download())
         ctx.close()
     assert np.array_equal(results[0], results[1])
+
+
+def test_hllc_low_mach_switch(hostsim_lib):
+    """solvers.py:118-122: the low-Mach rescaling of the HLLC wave speeds (off by default; no caller in the reference
+    turns it on).  It goes through sin(), whose last bit may differ between libraries: north-star tolerance."""
+    from cases import oracle_cfg
+    from oracle import advance
+    for dim, config, cells in ((1, "sod", 128), (2, "khi", 32)):
+        meta = _meta(config, cells, dim, "plm", "hllc", "ssprk(2,2)", None)
+        g0 = initial_state(config, cells, dim, 1.4, False)
+        cfg = oracle_cfg(meta)
+        cfg.low_mach = True
+        want, dts = advance(np.copy(g0), cfg, 2)
+        got, used, _ = run_native(hostsim_lib, meta, g0, 2, low_mach=True)
+        assert np.allclose(used, dts, rtol=1e-13, atol=0)
+        assert np.all(rel_l1(got, want) <= 2e-12)
+        plain, _, _ = run_native(hostsim_lib, meta, g0, 2)
+        assert not np.array_equal(plain, got)      # the switch does something
