@@ -14,6 +14,7 @@ DEVICE_LIB = os.environ.get("ASTREA_B200_LIB") or os.path.join(_HERE, "lib", "li
 
 # enums of include/astrea_b200.h
 PCM, PLM, PPM, WENO3, WENO5, WENO7 = range(6)
+PPM_MC, PPM_COLELLA, PPM_PH = range(3)
 MINMOD, VANLEER, OSPRE, VANALBADA, KOREN, SUPERBEE = range(6)
 LLF, LW, HLLC, HLLD = range(4)
 EULER, RK4, SSPRK22, SSPRK33, SSPRK43, SSPRK53, SSPRK54, SSPRK104 = range(8)

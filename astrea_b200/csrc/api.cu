@@ -76,6 +76,7 @@ struct astrea_ctx {
     // hydro specialisation (physics.cuh): the uploaded grid has no v_z / B, so only [rho, m_x, m_y, E] are processed
     bool hydro = false, saved_hydro = false;
     int* mhd_flag = nullptr;          // device: set by the upload when a v_z / B component is non-zero
+    int* ppm_flags = nullptr;         // device [4]: grid-wide switches of the PPM authors 'c' / 'ph' (recon.cuh)
     VarList vars() const { return hydro ? hydro_vars() : all_vars(); }
     // the ghost rows beyond the low / high end of this slab hold genuine neighbour data (exchanged), i.e. the end is
     // not a physical 'edge' boundary and the grid is decomposed
@@ -394,6 +395,7 @@ int corner_field(astrea_ctx* c) {
         rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
         rp.nvar = NVAR;
         for (int k = 0; k < NVAR; ++k) rp.vars[k] = k;
+        rp.ppm_author = PPM_MC; rp.pass = 0; rp.force_any3 = 0; rp.ppm_flags = c->ppm_flags; rp.nt = nt;   // mag_field.py:11: author='mc'
         const int nthreads = 128;
         const int gx = (int)((nt + nthreads - 1) / nthreads);
         const int nseg = (int)((rp.i_hi - rp.i_lo + 1 + rp.seg - 1) / rp.seg);
@@ -462,6 +464,17 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
         p.q = q; p.d = c->d0.plane; p.n = g.ny; p.gamma = g.gamma; p.dx = g.dx;
         p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach; p.tile = c->tile1d;
         p.eigmax_bits = eig; p.flag = c->flag;
+        p.ppm_author = g.ppm_author; p.pass = 0; p.ppm_flags = c->ppm_flags;
+        if (g.scheme == SCH_PPM && g.ppm_author != PPM_MC) {
+            // the grid-wide switches of the interface / extrapolant limiters first (two flag passes)
+            ASTREA_TRY(dev_zero(c->ppm_flags, 4 * sizeof(int), c->st));
+            for (int pass = 1; pass <= 2; ++pass) {
+                p.pass = pass;
+                Timed timed(c, CLS_RECON);
+                ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st));
+            }
+            p.pass = 0;
+        }
         { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st)); }
     } else {
         // sweep order and the solver's private axis counter (solvers.py:34-36,63; astrea.py:85)
@@ -547,6 +560,17 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 const int nthreads = 128;
                 const int gx = (int)((rp.c_hi - rp.c_lo + nthreads - 1) / nthreads);
                 const int nseg = (int)((i_hi - i_lo + 1 + rp.seg - 1) / rp.seg);
+                rp.ppm_author = g.ppm_author; rp.pass = 0; rp.ppm_flags = c->ppm_flags; rp.nt = nt;
+                rp.force_any3 = c->hydro ? 1 : 0;       // an identically zero variable makes `cell_extrema.any()` true (0 * 0 <= 0)
+                if (g.scheme == SCH_PPM && g.ppm_author != PPM_MC) {
+                    ASTREA_TRY(dev_zero(c->ppm_flags, 4 * sizeof(int), c->st));
+                    for (int pass = 1; pass <= 2; ++pass) {
+                        rp.pass = pass;
+                        Timed timed(c, CLS_RECON);
+                        ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * rp.nvar, nthreads, c->st));
+                    }
+                    rp.pass = 0;
+                }
                 Timed timed(c, CLS_RECON);
                 ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * rp.nvar, nthreads, c->st));
             }
@@ -631,7 +655,11 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
     if (g->dimension != 1 && g->dimension != 2) { why = "dimension must be 1 or 2"; return -1; }
     if (g->boundary != ASTREA_EDGE && g->boundary != ASTREA_WRAP) { why = "boundary must be ASTREA_EDGE or ASTREA_WRAP"; return -1; }
     if (g->scheme < ASTREA_PCM || g->scheme > ASTREA_WENO7) { why = "unknown scheme"; return -1; }
-    if (g->ppm_author != ASTREA_PPM_MC) { why = "only the 'mc' PPM limiter is wired (evolvers.py:17)"; return -1; }
+    if (g->ppm_author < ASTREA_PPM_MC || g->ppm_author > ASTREA_PPM_PH) { why = "unknown PPM author"; return -1; }
+    if (g->ppm_author != ASTREA_PPM_MC && g->dimension == 2 && g->nx != g->nx_global) {
+        why = "PPM authors 'c' / 'ph' switch on grid-wide any() tests (limiters.py:58,164): not available on slabs";
+        return -1;
+    }
     if (g->limiter < ASTREA_MINMOD || g->limiter > ASTREA_SUPERBEE) { why = "unknown slope limiter"; return -1; }
     if (g->solver != ASTREA_LLF && g->solver != ASTREA_HLLC && g->solver != ASTREA_HLLD) {
         why = "solver not available on the device path (Lax-Wendroff depends on LAPACK eigenvalue slot order, SURVEY Q11)";
@@ -697,7 +725,9 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
         ok = ok && alloc_reg(c, c->qT, c->ncol);   // scratch for primitive downloads
     }
     c->mhd_flag = (int*)dev_alloc(sizeof(int));
-    ok = ok && c->mhd_flag;
+    c->ppm_flags = (int*)dev_alloc(4 * sizeof(int));
+    ok = ok && c->mhd_flag && c->ppm_flags;
+    if (ok) dev_zero(c->ppm_flags, 4 * sizeof(int), c->st);
     c->eig_bits = (unsigned long long*)dev_alloc(8 * sizeof(unsigned long long));
     c->clock = (double*)dev_alloc((4 + DT_HISTORY) * sizeof(double));
     c->dt_dev = (double*)dev_alloc(sizeof(double));
@@ -733,7 +763,7 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
     dev_free(c->ws.mem); dev_free(c->ws2.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
-    dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag);
+    dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags);
 #ifdef ASTREA_DEVICE_BUILD
     for (auto& row : c->step_graph)
         for (auto& g : row)

@@ -131,6 +131,93 @@ HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, dou
                  win.d2[1] - win.d2[0], win.d2[2] - win.d2[1], win.d2[3] - win.d2[2], win.d2[5] - win.d2[4], wL, wR);
 }
 
+// ----------------------------------------------------------------------------------------- PPM, authors 'c' / 'ph'
+// Colella et al. (2011) and Peterson & Hammett (2008) variants: interface limiter (limiters.py:53-78) + extrapolant
+// limiter (limiters.py:144-201).  evolvers.py:17 always passes 'mc', so these are reachable only by calling
+// ppm.run(author=...) directly; they are selectable through astrea_cfg.ppm_author.
+//
+// Both limiters start with a grid-wide ``if mask.any()`` over all cells and variables of the sweep that
+// changes the result for EVERY cell, so the kernels run in passes: flag pass 1 -> any_a / any_b (interface limiter),
+// flag pass 2 -> any_3 (extrapolant limiter, needs the limited faces), then the reconstruction proper.
+struct PpmSwitches { bool any_a, any_b, any_3; };
+
+HD double ppm_limit_face(double w_face, double w_m1, double w_c, double w_p1, double w_p2, bool any) {
+    if (!any) return w_face;
+    const double C = 5.0 / 4.0;
+    const double dL = w_m1 - 2.0 * w_c + w_p1;
+    const double dC = 3.0 * (w_c - 2.0 * w_face + w_p1);
+    const double dR = w_c - 2.0 * w_p1 + w_p2;
+    const double sL = npsign(dL), sC = npsign(dC), sR = npsign(dR);
+    const bool agree = (sL == sR) && (sC == sR) && (sC == sL);
+    const double lim = sC * npmin(fabs(dC), npmin(fabs(C * dL), fabs(C * dR)));
+    const double d2 = agree ? lim : 0.0;
+    return 0.5 * (w_c + w_p1) - d2 / 6.0;
+}
+HD bool ppm_face_extremum(double w_face, double w_c, double w_p1) { return (w_face - w_c) * (w_p1 - w_face) < 0.0; }
+
+// limited value of the face right of (mapped) cell k — author 'c' pads this derived array (ppm.py:69-71)
+template <class A>
+HD double ppm_face_c(const A& acc, int64_t k, bool any) {
+    return ppm_limit_face(ppm_face(acc, k), acc.s(acc.b(k - 1)), acc.s(k), acc.s(acc.b(k + 1)), acc.s(acc.b(k + 2)), any);
+}
+
+// what == 0: wL / wR / wF of cell i.  what == 1: only the interface-limiter masks -> (pa, pb).  what == 2: only the
+// extrapolant-limiter mask -> p3 (needs sw.any_a / any_b).
+template <class A>
+HD void cell_faces_ppm_cph(const A& acc, int64_t i, bool ph, PpmSwitches sw, int what, double& wL, double& wR, double& wF,
+                           bool& pa, bool& pb, bool& p3) {
+    const double C = 5.0 / 4.0;
+    const double c = acc.s(i);
+    const double m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
+    const double face_unl = 7.0 / 12.0 * (c + p1) - 1.0 / 12.0 * (m1 + p2);        // ppm.py:38
+    double faceL, faceR;
+    if (ph) {
+        const double faceL0 = 7.0 / 12.0 * (m1 + c) - 1.0 / 12.0 * (m2 + p1);        // ppm.py:52
+        if (what == 1) { pa = ppm_face_extremum(faceL0, m1, c); pb = ppm_face_extremum(face_unl, c, p1); return; }
+        faceL = ppm_limit_face(faceL0, m2, m1, c, p1, sw.any_a);
+        faceR = ppm_limit_face(face_unl, m1, c, p1, p2, sw.any_b);
+        wF = face_unl;
+    } else {
+        if (what == 1) { pa = ppm_face_extremum(face_unl, c, p1); pb = false; return; }
+        faceR = ppm_limit_face(face_unl, m1, c, p1, p2, sw.any_a);
+        faceL = ppm_face_c(acc, acc.b(i - 1), sw.any_a);
+        wF = faceR;
+    }
+    const double dwm = c - faceL, dwp = faceR - c;
+    const bool extremum = dwm * dwp <= 0.0;
+    bool ext2;
+    if (ph) {
+        ext2 = (m1 - c) * (c - p1) <= 0.0;
+    } else {
+        const double dfL = faceL - ppm_face_c(acc, acc.b(i - 2), sw.any_a), dfR = ppm_face_c(acc, acc.b(i + 2), sw.any_a) - faceR;
+        const double dsL = c - m1, dsR = p1 - c;
+        const double dfm = npmin(fabs(dfL), fabs(dfR)), dsm = npmin(fabs(dsL), fabs(dsR));
+        ext2 = ((dfm >= dsm) && (dfL * dfR < 0.0)) || ((dsm >= dfm) && (dsL * dsR < 0.0));
+    }
+    if (what == 2) { p3 = extremum || ext2; return; }
+    if (!sw.any_3) { wL = faceL; wR = faceR; return; }
+    const double D2 = 6.0 * (faceL - 2.0 * c + faceR);
+    const double D2L = m2 - 2.0 * m1 + c, D2C = m1 - 2.0 * c + p1, D2R = c - 2.0 * p1 + p2;
+    const double s0 = npsign(D2), sC = npsign(D2C), sL = npsign(D2L), sR = npsign(D2R);
+    const bool agree = (s0 == sC) && (s0 == sL) && (s0 == sR) && (sC == sL) && (sC == sR) && (sL == sR);
+    const double curv = s0 * npmin(npmin(fabs(D2), fabs(C * D2C)), npmin(fabs(C * D2L), fabs(C * D2R)));
+    double D2lim = 0.0;
+    if (extremum && agree) D2lim = curv;
+    if (ph) {
+        const double phi = sdiv(D2lim, D2);
+        wL = c + phi * (faceL - c);
+        wR = c + phi * (faceR - c);
+        return;
+    }
+    if (ext2 && agree) D2lim = curv;
+    const double phi = sdiv(D2lim, D2);
+    double duL = dwm, duR = dwp;
+    if (fabs(dwm) > 2.0 * fabs(dwp)) duL = 2.0 * dwp;
+    if (fabs(dwp) > 2.0 * fabs(dwm)) duR = 2.0 * dwm;
+    wL = c - phi * duL;
+    wR = c + phi * duR;
+}
+
 // ----------------------------------------------------------------------------------------- WENO
 template <class A>
 HD void cell_faces_weno3(const A& acc, int64_t i, double& wL, double& wR) {

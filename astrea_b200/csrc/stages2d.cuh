@@ -202,6 +202,10 @@ struct ReconStageParams {
     int cell_aligned;          // 1: wp / wm receive wL / wR of cell i at row i (transverse reconstruction of mag_field.py)
     int nvar;                  // variables to reconstruct (8, or 4 for a hydro state) and their indices
     int vars[NVAR];
+    // PPM authors 'c' / 'ph' (recon.cuh): pass 1 / 2 only evaluate the grid-wide switches into ppm_flags[0..2]
+    int ppm_author, pass, force_any3;
+    int* ppm_flags;
+    int64_t nt;                // interior columns (the switches look at genuine cells only)
 };
 
 // accessor over the register stencil: logical offset k relative to the cell, identity boundary map
@@ -257,6 +261,31 @@ struct ReconStage {
                 if (i < last) ahead = col[(i + 1 + HI) * rp];
                 const int64_t ig = i + p.s_off;
                 double wl, wr, wf;
+                if constexpr (SCHEME == SCH_PPM) {
+                    if (p.ppm_author != PPM_MC) {
+                        if (edge && (ig < 0 || ig > p.ns_glob - 1)) continue;
+                        const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
+                        if (p.pass != 0 && !interior) continue;
+                        const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0 || p.force_any3 != 0};
+                        const bool ph = p.ppm_author == PPM_PH;
+                        bool pa = false, pb = false, p3 = false;
+                        if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
+                            ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
+                            cell_faces_ppm_cph(acc, i, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                        } else {
+                            StencilAccessor<LO> acc{r};
+                            cell_faces_ppm_cph(acc, 0, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                        }
+                        if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; continue; }
+                        if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; continue; }
+                        *p.wp.at(i, v, t) = wl;
+                        *p.wm.at(i + 1, v, t) = wr;
+                        if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
+                        if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
+                        if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+                        continue;
+                    }
+                }
                 if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
                     fresh = true;
                     if (ig < 0 || ig > p.ns_glob - 1) continue;          // no such cell

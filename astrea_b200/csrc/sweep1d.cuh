@@ -24,6 +24,9 @@ struct Sweep1DParams {
     int bc, limiter, low_mach, tile;
     unsigned long long* eigmax_bits;   // [1]
     unsigned long long* flag;                         // non-finite wave speed seen
+    // PPM authors 'c' / 'ph' (recon.cuh): pass 1 / 2 only evaluate the grid-wide switches into ppm_flags[0..2]
+    int ppm_author, pass;
+    int* ppm_flags;
 };
 
 struct TileAccessor {
@@ -102,11 +105,25 @@ struct Sweep1D {
             for (int v = 0; v < NVAR; ++v) {
                 TileAccessor acc{W + v * NT, base, p.n, p.bc};
                 double wl, wr, wf;
-                cell_faces<SCHEME>(acc, c, p.limiter, wl, wr, wf);
+                if (SCHEME == SCH_PPM && p.ppm_author != PPM_MC) {
+                    const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0};
+                    bool pa = false, pb = false, p3 = false;
+                    cell_faces_ppm_cph(acc, c, p.ppm_author == PPM_PH, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                    if (p.pass != 0) {      // the switches look at the cells of the domain only
+                        if (c >= 0 && c < p.n) {
+                            if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; }
+                            else if (p3) p.ppm_flags[2] = 1;
+                        }
+                        continue;
+                    }
+                } else {
+                    cell_faces<SCHEME>(acc, c, p.limiter, wl, wr, wf);
+                }
                 WL[v * NT + k] = wl;
                 WR[v * NT + k] = wr;
             }
         });
+        if (p.pass != 0) return;
         const int kr0 = kw0 + LO, kr1 = kw1 - HI;                 // threads holding valid WL / WR
         auto bmap = [&](int64_t c) { return p.bc == BC_WRAP ? c : clamp_index(c, 0, p.n - 1); };
         // wave-speed estimate (fv.py:157-169) at the averaged interface state, or at the cells for PCM

@@ -69,6 +69,17 @@ def integrator_enum(timestep):
     return N.EULER
 
 
+def ppm_author_enum(author):
+    """ppm.py:43,61-66 / limiters.py:89,148: 'mc' (McCorquodale & Colella, what evolvers.py:17 passes), 'c' (Colella
+    et al. 2011), 'ph' (Peterson & Hammett 2008)."""
+    a = author.lower()
+    if "x" in a or "ph" in a or a in ("peterson", "hammett"):
+        return N.PPM_PH
+    if a == "mc" or "mccorquodale" in a:
+        return N.PPM_MC
+    return N.PPM_COLELLA
+
+
 def limiter_enum(name):
     return {"minmod": N.MINMOD, "vanleer": N.VANLEER, "van leer": N.VANLEER, "ospre": N.OSPRE, "vanalbada": N.VANALBADA,
             "van albada": N.VANALBADA, "koren": N.KOREN, "superbee": N.SUPERBEE}[name.lower()]
@@ -85,7 +96,7 @@ def stages_of(integrator):
 
 def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cfl, subgrid, solver, timestep,
              solver_category_name=None, magnetic_2d=False, limiter="minmod", low_mach=False, device=0,
-             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False):
+             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False, ppm_author="mc"):
     cfg = N.Cfg()
     cfg.dimension = int(dimension)
     cfg.boundary = boundary_enum(boundary)
@@ -93,7 +104,7 @@ def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cf
     cfg.ny = 1 if dimension == 1 else int(ny if ny is not None else cells)
     cfg.gamma, cfg.dx, cfg.cfl = float(gamma), float(dx), float(cfl)
     cfg.scheme = scheme_enum(subgrid)
-    cfg.ppm_author = 0
+    cfg.ppm_author = ppm_author_enum(ppm_author)
     cfg.limiter = limiter_enum(limiter)
     cfg.solver = solver_enum(solver, solver_category_name)
     cfg.low_mach = int(bool(low_mach))

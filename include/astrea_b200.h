@@ -22,7 +22,7 @@ extern "C" {
 typedef struct astrea_ctx astrea_ctx;
 
 enum { ASTREA_PCM = 0, ASTREA_PLM = 1, ASTREA_PPM = 2, ASTREA_WENO3 = 3, ASTREA_WENO5 = 4, ASTREA_WENO7 = 5 };   /* sim_variables.subgrid, evolvers.py:14-21 */
-enum { ASTREA_PPM_MC = 0 };                                                                                   /* evolvers.py:17 passes author='mc' */
+enum { ASTREA_PPM_MC = 0, ASTREA_PPM_COLELLA = 1, ASTREA_PPM_PH = 2 };   /* ppm.run(author=...): evolvers.py:17 passes 'mc'; 'c' / 'ph' = limiters.py:53-78,144-201 */
 enum { ASTREA_MINMOD = 0, ASTREA_VANLEER = 1, ASTREA_OSPRE = 2, ASTREA_VANALBADA = 3, ASTREA_KOREN = 4, ASTREA_SUPERBEE = 5 }; /* limiters.py:10-49 */
 enum { ASTREA_LLF = 0, ASTREA_LW = 1, ASTREA_HLLC = 2, ASTREA_HLLD = 3 };                                         /* sim_variables.solver, solvers.py:13-31 */
 enum { ASTREA_EULER = 0, ASTREA_RK4 = 1, ASTREA_SSPRK22 = 2, ASTREA_SSPRK33 = 3, ASTREA_SSPRK43 = 4,
@@ -48,7 +48,7 @@ typedef struct astrea_cfg {
     double dx;             /* cell width, dx == dy (tests.py:326-327) */
     double cfl;
     int32_t scheme;        /* ASTREA_PCM .. ASTREA_WENO7 */
-    int32_t ppm_author;    /* ASTREA_PPM_MC */
+    int32_t ppm_author;    /* ASTREA_PPM_MC (what the reference's evolve_space uses) | ASTREA_PPM_COLELLA | ASTREA_PPM_PH */
     int32_t limiter;       /* slope limiter of PLM */
     int32_t solver;        /* ASTREA_LLF .. ASTREA_HLLD */
     int32_t low_mach;      /* solvers.py:92 low_mach switch of HLLC */

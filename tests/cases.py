@@ -9,13 +9,14 @@ from oracle import OracleConfig, advance
 def oracle_cfg(meta, eigen="closed"):
     return OracleConfig(config=meta["config"], cells=meta["cells"], dimension=meta["dimension"], subgrid=meta["subgrid"],
                         solver=meta["solver"], timestep=meta["timestep"], boundary=meta["boundary"], dx=meta["dx"],
-                        gamma=meta["gamma"], cfl=meta["cfl"], magnetic_2d=meta["magnetic_2d"], eigen=eigen)
+                        gamma=meta["gamma"], cfl=meta["cfl"], magnetic_2d=meta["magnetic_2d"], eigen=eigen,
+                        ppm_author=meta.get("ppm_author", "mc"))
 
 
 def native_cfg(meta, **geometry):
     return make_cfg(dimension=meta["dimension"], cells=meta["cells"], boundary=meta["boundary"], gamma=meta["gamma"],
                     dx=meta["dx"], cfl=meta["cfl"], subgrid=meta["subgrid"], solver=meta["solver"], timestep=meta["timestep"],
-                    magnetic_2d=meta["magnetic_2d"], **geometry)
+                    magnetic_2d=meta["magnetic_2d"], ppm_author=meta.get("ppm_author", "mc"), **geometry)
 
 
 def run_native(lib, meta, g0, steps, dts=None, **geometry):

@@ -45,8 +45,45 @@ CASES = [
 ]
 
 
+# PPM authors 'c' / 'ph' (limiters.py:53-78,144-201) are reachable only through ppm.run(author=...): evolve_space
+# hard-codes 'mc' (evolvers.py:17).  One forward-Euler step from ppm.run(author) -> calculate_Riemann_flux -> evolve_time.
+AUTHOR_CASES = [
+    ("a_sod_ppm_c_hllc", "sod", 128, 1, "hllc", "c"),
+    ("a_ll3_ppm_ph_hllc", "ll3", 32, 2, "hllc", "ph"),
+    ("a_khi_ppm_c_llf", "khi", 32, 2, "lf", "c"),
+    ("a_shu_ppm_ph_llf", "shu-osher", 128, 1, "lf", "ph"),
+]
+
+
+def author_cases(index):
+    rh._import_ref()
+    from schemes import ppm
+    from num_methods import evolvers, solvers
+    from oracle import space_operator, time_update
+    for cid, config, cells, dim, solver, author in AUTHOR_CASES:
+        sv = rh.make_sim_variables(config, cells, dim, "ppm", solver, "euler")
+        g0 = rh.initial_grid(sv)
+        with np.errstate(all="ignore"):
+            fluxes = solvers.calculate_Riemann_flux(ppm.run(np.copy(g0), sv, author=author), sv)
+            eig = [float(v["eigmax"]) for v in fluxes.values()]
+            dt = sv.cfl * min(sv.dx / e for e in eig)
+            g1 = evolvers.evolve_time(np.copy(g0), fluxes, dt, sv)
+        cfg = OracleConfig(config=config, cells=cells, dimension=dim, subgrid="ppm", solver=solver, timestep="euler",
+                           boundary=sv.boundary, dx=sv.dx, ppm_author=author)
+        with np.errstate(all="ignore"):
+            go = time_update(np.copy(g0), space_operator(np.copy(g0), cfg), dt, cfg)
+        pinned = bool(np.array_equal(go, g1, equal_nan=True))
+        assert pinned, f"oracle differs from the reference on {cid}"
+        np.savez_compressed(os.path.join(HERE, cid + ".npz"), g0=g0, g=g1, dts=np.array([dt]), eigmax=np.array([eig]))
+        index[cid] = dict(config=config, cells=cells, dimension=dim, subgrid="ppm", solver=solver, timestep="euler", steps=1,
+                          boundary=sv.boundary, dx=sv.dx, gamma=sv.gamma, cfl=sv.cfl, magnetic_2d=False,
+                          finite=bool(np.isfinite(g1).all()), oracle_bit_equal=pinned, ppm_author=author)
+        print(cid, "oracle bit-equal:", pinned)
+
+
 def main():
     index = {}
+    author_cases(index)
     for cid, config, cells, dim, subgrid, solver, timestep, steps, bc in CASES:
         sv = rh.make_sim_variables(config, cells, dim, subgrid, solver, timestep, boundary=bc)
         g0 = rh.initial_grid(sv)

@@ -310,3 +310,19 @@ def test_hllc_low_mach_switch(lib):
         got, used, _ = run_native(lib, meta, g0, 2, low_mach=True)
         assert np.allclose(used, dts, rtol=1e-13, atol=0)
         assert np.all(rel_l1(got, want) <= 2e-12)
+
+
+@pytest.mark.parametrize("author", ["c", "ph"])
+@pytest.mark.parametrize("config,dim,solver,bc", [("sod", 1, "hllc", None), ("ll3", 2, "hllc", None), ("ll4", 2, "lf", "edge"),
+                                                  ("orszag-tang", 2, "hlld", None)])
+def test_ppm_authors_colella_and_peterson_hammett(lib, config, dim, solver, bc, author):
+    """ppm.run(author='c' | 'ph') (limiters.py:53-78,144-201): grid-wide any() switches via flag passes."""
+    from astrea_b200.selectors import MAGNETIC_2D
+    cells = 700 if dim == 1 else 130
+    meta = _meta(config, cells, dim, "ppm", solver, "ssprk(3,3)", bc, mhd=config in MAGNETIC_2D)
+    meta["ppm_author"] = author
+    g0 = initial_state(config, cells, dim, 1.4, True, boundary=meta["boundary"])
+    want, dts = run_oracle(meta, g0, 2)
+    got, used, _ = run_native(lib, meta, g0, 2)
+    assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
+    assert np.allclose(used, dts, rtol=1e-13, atol=0)

@@ -424,3 +424,50 @@ def test_hllc_low_mach_switch(hostsim_lib):
         assert np.all(rel_l1(got, want) <= 2e-12)
         plain, _, _ = run_native(hostsim_lib, meta, g0, 2)
         assert not np.array_equal(plain, got)      # the switch does something
+
+
+PPM_AUTHORS = [(cfg, dim, sol, ts, bc, author)
+               for cfg, dim, sol, ts, bc in (("sod", 1, "hllc", "ssprk(3,3)", None), ("sin", 1, "lf", "rk4", None),
+                                             ("ll3", 2, "hllc", "ssprk(3,3)", None), ("ll4", 2, "lf", "ssprk(2,2)", "edge"),
+                                             ("orszag-tang", 2, "hlld", "ssprk(2,2)", None))
+               for author in ("c", "ph")]
+
+
+@pytest.mark.parametrize("config,dim,solver,timestep,bc,author", PPM_AUTHORS, ids=["-".join(map(str, m)) for m in PPM_AUTHORS])
+def test_ppm_authors_colella_and_peterson_hammett(hostsim_lib, config, dim, solver, timestep, bc, author):
+    """ppm.run(author='c' | 'ph'): interface limiter + extrapolant limiter with their grid-wide any() switches."""
+    from astrea_b200.selectors import MAGNETIC_2D
+    cells = 96 if dim == 1 else 30
+    meta = _meta(config, cells, dim, "ppm", solver, timestep, bc, mhd=config in MAGNETIC_2D)
+    meta["ppm_author"] = author
+    g0 = initial_state(config, cells, dim, 1.4, True, boundary=meta["boundary"])
+    want, dts = run_oracle(meta, g0, 2)
+    for general in (False, True):
+        got, used, _ = run_native(hostsim_lib, meta, g0, 2, segment_2d=11, tile_1d=19, general_path=general)
+        assert used == dts
+        assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("author", ["c", "ph"])
+def test_ppm_author_switches_off(hostsim_lib, author):
+    """A strictly monotone profile with outflow boundaries has no face extremum: `local_extrema.any()` is False and the
+    interface limiter returns the faces untouched for every cell (limiters.py:58,76-78)."""
+    from oracle.reconstruct import ppm_face_value
+    from oracle.gridops import prim_avg_of_cons_avg
+    from cases import oracle_cfg
+    cells = 80
+    x = (np.arange(cells) + .5) / cells
+    w = np.zeros((cells, 8))
+    w[:, 0], w[:, 1], w[:, 4] = 1 + x, .2 + .3 * x, 1 + 2 * x
+    w[:, 2], w[:, 3], w[:, 5], w[:, 6], w[:, 7] = .1 + .1 * x, .3 + x, .2 + .1 * x, .4 + .2 * x, .1 + .3 * x
+    from oracle.gridops import cons_of_prim
+    g0 = cons_of_prim(w, 1.4)
+    meta = dict(config="sod", cells=cells, dimension=1, subgrid="ppm", solver="lf", timestep="euler", boundary="edge", dx=1 / cells,
+                gamma=1.4, cfl=.5, magnetic_2d=False, ppm_author=author)
+    wS = prim_avg_of_cons_avg(g0, oracle_cfg(meta))
+    face = ppm_face_value(wS, "edge")
+    assert not ((face - wS) * (np.roll(wS, -1, axis=0) - face) < 0)[:-1].any()      # the premise of the test
+    want, dts = run_oracle(meta, g0, 1)
+    got, used, _ = run_native(hostsim_lib, meta, g0, 1, tile_1d=23)
+    assert used == dts
+    assert np.array_equal(got, want, equal_nan=True)
