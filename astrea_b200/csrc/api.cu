@@ -74,9 +74,11 @@ struct astrea_ctx {
     double* emf = nullptr;            // magnetic_2d: corner electric field [nrow (+1)][ncol]
     int64_t emf_rows = 0;
     // hydro specialisation (physics.cuh): the uploaded grid has no v_z / B, so only [rho, m_x, m_y, E] are processed
-    bool hydro = false, saved_hydro = false;
+    bool hydro = false, saved_hydro = false, saved_field_free = false;
     int* mhd_flag = nullptr;          // device: set by the upload when a v_z / B component is non-zero
     int* ppm_flags = nullptr;         // device [4]: grid-wide switches of the PPM authors 'c' / 'ph' (recon.cuh)
+    unsigned long long* lw_keys = nullptr;   // device [4]: Lax-Wendroff column search (FluxStage / Sweep1D)
+    bool field_free = false;          // the uploaded grid has no v_z / B
     VarList vars() const { return hydro ? hydro_vars() : all_vars(); }
     // the ghost rows beyond the low / high end of this slab hold genuine neighbour data (exchanged), i.e. the end is
     // not a physical 'edge' boundary and the grid is decomposed
@@ -459,12 +461,18 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
     if (int e = fill_halo(c, q, external_rows)) return e;
     unsigned long long* eig = first ? c->eig_bits : c->eig_scratch;
     ASTREA_TRY(dev_zero(eig, 2 * sizeof(unsigned long long), c->st));
+    const bool lw = g.solver == SOL_LW;
+    if (lw && !(g.dimension == 1 ? c->field_free : c->hydro))
+        return fail(c, ASTREA_E_ARG, "Lax-Wendroff on the device needs a grid without v_z / B (its column pick follows LAPACK's "
+                                     "eigenvalue slot order, which is only reproducible for that spectrum; SURVEY Q11)");
     if (g.dimension == 1) {
         Sweep1DParams p{};
         p.q = q; p.d = c->d0.plane; p.n = g.ny; p.gamma = g.gamma; p.dx = g.dx;
         p.bc = g.boundary; p.limiter = g.limiter; p.low_mach = g.low_mach; p.tile = c->tile1d;
         p.eigmax_bits = eig; p.flag = c->flag;
         p.ppm_author = g.ppm_author; p.pass = 0; p.ppm_flags = c->ppm_flags;
+        p.lw_pass = 0; p.lw_keys = c->lw_keys;
+        if (lw) ASTREA_TRY(dev_ones(c->lw_keys, 4 * sizeof(unsigned long long), c->st));
         if (g.scheme == SCH_PPM && g.ppm_author != PPM_MC) {
             // the grid-wide switches of the interface / extrapolant limiters first (two flag passes)
             ASTREA_TRY(dev_zero(c->ppm_flags, 4 * sizeof(int), c->st));
@@ -474,6 +482,11 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st));
             }
             p.pass = 0;
+        }
+        if (lw) {      // search pass of the Lax-Wendroff column pick
+            p.lw_pass = 1;
+            { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st)); }
+            p.lw_pass = 0;
         }
         { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_sweep1d(g.scheme, g.solver, p, c->threads1d, c->st)); }
     } else {
@@ -583,6 +596,13 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 const int nthreads = (g.threads_2d >= 32 && g.threads_2d <= 128) ? g.threads_2d / 32 * 32 : 128;
                 const int own = 32 - 2 * ht, nwarp = nthreads / 32;
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
+                fp.lw_pass = 0; fp.lw_keys = c->lw_keys;
+                if (lw) {      // search pass of the Lax-Wendroff column pick, per sweep
+                    ASTREA_TRY(dev_ones(c->lw_keys, 4 * sizeof(unsigned long long), c->st));
+                    fp.lw_pass = 1;
+                    { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, 1, fp, gx, gy, nthreads, c->st)); }
+                    fp.lw_pass = 0;
+                }
                 Timed timed(c, CLS_SWEEP);
                 ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, c->hydro ? 1 : 0, fp, gx, gy, nthreads, c->st));
             }
@@ -661,8 +681,10 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
         return -1;
     }
     if (g->limiter < ASTREA_MINMOD || g->limiter > ASTREA_SUPERBEE) { why = "unknown slope limiter"; return -1; }
-    if (g->solver != ASTREA_LLF && g->solver != ASTREA_HLLC && g->solver != ASTREA_HLLD) {
-        why = "solver not available on the device path (Lax-Wendroff depends on LAPACK eigenvalue slot order, SURVEY Q11)";
+    if (g->solver < ASTREA_LLF || g->solver > ASTREA_HLLD) { why = "unknown solver"; return -1; }
+    if (g->solver == ASTREA_LW && (g->magnetic_2d || (g->dimension == 2 && g->nx != g->nx_global))) {
+        why = "Lax-Wendroff (solvers.py:79-88) picks a spectrum column by a grid-wide lexicographic sort (SURVEY Q11): "
+              "available for states without v_z / B on one GPU";
         return -1;
     }
     if (g->integrator < ASTREA_EULER || g->integrator > ASTREA_SSPRK104) { why = "unknown integrator"; return -1; }
@@ -726,7 +748,8 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     }
     c->mhd_flag = (int*)dev_alloc(sizeof(int));
     c->ppm_flags = (int*)dev_alloc(4 * sizeof(int));
-    ok = ok && c->mhd_flag && c->ppm_flags;
+    c->lw_keys = (unsigned long long*)dev_alloc(4 * sizeof(unsigned long long));
+    ok = ok && c->mhd_flag && c->ppm_flags && c->lw_keys;
     if (ok) dev_zero(c->ppm_flags, 4 * sizeof(int), c->st);
     c->eig_bits = (unsigned long long*)dev_alloc(8 * sizeof(unsigned long long));
     c->clock = (double*)dev_alloc((4 + DT_HISTORY) * sizeof(double));
@@ -763,7 +786,7 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->qT.mem); dev_free(c->d0.mem); dev_free(c->d1t.mem);
     dev_free(c->ws.mem); dev_free(c->ws2.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
-    dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags);
+    dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags); dev_free(c->lw_keys);
 #ifdef ASTREA_DEVICE_BUILD
     for (auto& row : c->step_graph)
         for (auto& g : row)
@@ -788,6 +811,7 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     ASTREA_TRY(copy_d2h(&has_field, c->mhd_flag, sizeof(int), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_upload: stream sync failed");
     // 2D hydro with LLF / HLLC: v_z and B stay identically zero, the kernels skip them (bit-identical results)
+    c->field_free = !has_field;
     c->hydro = !has_field && c->cfg.dimension == 2 && !c->cfg.magnetic_2d && c->cfg.solver != SOL_HLLD && !(c->cfg.flags & 1);
     return 0;
 }
@@ -1121,6 +1145,7 @@ int astrea_save_state(astrea_ctx* c) {
     ASTREA_TRY(copy_d2d(c->saved.mem, c->regs[c->grid_reg].mem, c->plane_doubles * sizeof(double), c->st));
     c->saved_parity = c->parity;
     c->saved_hydro = c->hydro;
+    c->saved_field_free = c->field_free;
     return 0;
 }
 
@@ -1131,6 +1156,7 @@ int astrea_restore_state(astrea_ctx* c) {
     ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));
     c->parity = c->saved_parity;
     c->hydro = c->saved_hydro;
+    c->field_free = c->saved_field_free;
     c->next_instr = 0;
     return 0;
 }

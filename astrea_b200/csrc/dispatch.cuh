@@ -30,6 +30,13 @@ int launch_flux_ho(int solver, int ax, int sax, int hydro, const FluxStageParams
     int launch_flux_##NAME(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
         const int key = ax * 2 + sax;                                                                                \
         switch (solver) {                                                                                            \
+            case SOL_LW: /* Lax-Wendroff: states without v_z / B only (the launcher checks), no solver axis */         \
+                if (!hydro) return -1;                                                                               \
+                if (p.bc == BC_EDGE)                                                                                 \
+                    return ax == 0 ? launch<FluxStage<KIND, SOL_LW, 0, 0, true, true>>(p, gx, gy, nthreads, 0, st)   \
+                                   : launch<FluxStage<KIND, SOL_LW, 1, 1, true, true>>(p, gx, gy, nthreads, 0, st);  \
+                return ax == 0 ? launch<FluxStage<KIND, SOL_LW, 0, 0, true, false>>(p, gx, gy, nthreads, 0, st)      \
+                               : launch<FluxStage<KIND, SOL_LW, 1, 1, true, false>>(p, gx, gy, nthreads, 0, st);     \
             case SOL_LLF: /* LLF ignores the solver axis (solvers.py:69) */                                          \
                 return ax == 0 ? runflux_##NAME<SOL_LLF, 0, 0>(hydro, p, gx, gy, nthreads, st)                       \
                                : runflux_##NAME<SOL_LLF, 1, 1>(hydro, p, gx, gy, nthreads, st);                      \

@@ -7,6 +7,7 @@ static int run1d(int solver, const Sweep1DParams& p, int nthreads, Stream st) {
     switch (solver) {
         case SOL_LLF: return launch<Sweep1D<SCH, SOL_LLF>>(p, gx, 1, nthreads, Sweep1D<SCH, SOL_LLF>::smem_bytes(nthreads), st);
         case SOL_HLLC: return launch<Sweep1D<SCH, SOL_HLLC>>(p, gx, 1, nthreads, Sweep1D<SCH, SOL_HLLC>::smem_bytes(nthreads), st);
+        case SOL_LW: return launch<Sweep1D<SCH, SOL_LW>>(p, gx, 1, nthreads, Sweep1D<SCH, SOL_LW>::smem_bytes(nthreads), st);
         case SOL_HLLD: return launch<Sweep1D<SCH, SOL_HLLD>>(p, gx, 1, nthreads, Sweep1D<SCH, SOL_HLLD>::smem_bytes(nthreads), st);
         default: return -1;
     }

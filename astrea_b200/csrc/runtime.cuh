@@ -83,6 +83,20 @@ struct DeviceExec {
         }
         __syncthreads();
     }
+    // Three running minima (64-bit keys) of per-thread values -> atomicMin on dst[0..2]; warp shuffle first.
+    template <class G>
+    __device__ void publish_min3(G&& get, unsigned long long* dst) {
+        unsigned long long v[3];
+        get((int)threadIdx.x, v);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[k], o);
+                v[k] = other < v[k] ? other : v[k];
+            }
+            if ((threadIdx.x & 31) == 0 && v[k] != ~0ull) atomicMin(dst + k, v[k]);
+        }
+    }
 };
 
 // resident blocks per SM the register allocation should allow: K::MIN_BLOCKS when the kernel declares it, else 1
@@ -114,6 +128,7 @@ inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, siz
 inline void* dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
 inline int dev_zero(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAsync(p, 0, bytes, st.s); }
+inline int dev_ones(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAsync(p, 0xFF, bytes, st.s); }
 inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s); }
 inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s); }
 inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st.s); }
@@ -156,6 +171,14 @@ struct HostExec {
             if (bad) *flag = 0x3FF0000000000000ull;
         }
     }
+    template <class G>
+    void publish_min3(G&& get, unsigned long long* dst) {
+        for (int t = 0; t < nthr; ++t) {
+            unsigned long long v[3];
+            get(t, v);
+            for (int k = 0; k < 3; ++k) if (v[k] < dst[k]) dst[k] = v[k];
+        }
+    }
 };
 
 struct Stream { int s; };
@@ -173,6 +196,7 @@ inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, siz
 inline void* dev_alloc(size_t bytes) { return std::malloc(bytes); }
 inline void dev_free(void* p) { std::free(p); }
 inline int dev_zero(void* p, size_t bytes, Stream) { std::memset(p, 0, bytes); return 0; }
+inline int dev_ones(void* p, size_t bytes, Stream) { std::memset(p, 0xFF, bytes); return 0; }
 inline int copy_h2d(void* d, const void* h, size_t bytes, Stream) { std::memcpy(d, h, bytes); return 0; }
 inline int copy_d2h(void* h, const void* d, size_t bytes, Stream) { std::memcpy(h, d, bytes); return 0; }
 inline int copy_d2d(void* d, const void* s, size_t bytes, Stream) { std::memcpy(d, s, bytes); return 0; }

@@ -325,6 +325,11 @@ struct FluxStageParams {
     int bc, low_mach;
     unsigned long long* eigmax_bits;
     unsigned long long* flag;
+    // Lax-Wendroff (solvers.py:79-88): lw_pass == 1 only searches, for each of the spectrum columns
+    // u - c, u, u + c, the first entry of the (N+2, N) array of padded averaged states that is non-zero
+    // (lw_keys[k] = 2 * flat index + (entry > 0)); the flux pass ranks the all-zero column among them.
+    int lw_pass;
+    unsigned long long* lw_keys;
 };
 
 // KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)
@@ -351,7 +356,8 @@ struct FluxStage {
     static constexpr bool HO = KIND == 2, PCM = KIND == 0;
     static constexpr int H = HO ? 2 : 1;            // halo lanes on each side of a warp
     static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
-    static constexpr bool LLF = SOLVER == SOL_LLF;
+    static constexpr bool LW = SOLVER == SOL_LW;
+    static constexpr bool LLF = SOLVER == SOL_LLF || LW;     // Lax-Wendroff has LLF's form with another coefficient
 
     // Per-thread values; a member read by the neighbouring lanes in phase n is never written in phase n.
     struct Tls {
@@ -392,9 +398,26 @@ struct FluxStage {
             }
             return (b - own) - (own - a);
         };
-        // averaged-state wave speed of interface row jj at this thread's column (fv.py:157-169)
-        auto speed_at = [&](int64_t jj, int64_t tc) -> double {
-            double a[NVAR], x[NVAR], y[NVAR];
+        // Lax-Wendroff: which column np.unique(characteristics, axis=-1)[..., 1] is.  For a state without v_z / B the
+        // LAPACK spectrum has the four distinct columns u - c < u < u + c and 0; they are sorted lexicographically
+        // over all padded points, so only the place of the zero column has to be found: the number of columns whose
+        // first non-zero entry is negative.  0: second = u - c, 1: second = 0, else: second = u.
+        int lw_rank = 0;
+        if (LW) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) lw_rank += (p.lw_keys[k] != ~0ull && (p.lw_keys[k] & 1ull) == 0) ? 1 : 0;
+        }
+        // LLF: max |eigenvalue|; LW: second^2 / max |eigenvalue| (solvers.py:84-87) of an averaged (or PCM cell) state
+        auto dissipation = [&](const double* a) -> double {
+            const double lam = spectral_radius_t<AX, HYDRO>(a, gamma);
+            if (!LW) return lam;
+            const double u = a[1 + AX], c = sqrt(gamma * a[4] / a[0]);
+            const double second = lw_rank == 0 ? u - c : (lw_rank == 1 ? 0.0 : u);
+            return sdiv(second * second, lam);
+        };
+        // the state of padded entry `jj` (interface row, or cell row for PCM) at this thread's column (fv.py:157-169)
+        auto state_at = [&](int64_t jj, int64_t tc, double* a) {
+            double x[NVAR], y[NVAR];
             if (PCM) {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); a[v] = *p.ws.at(jj, v, tc); }
@@ -404,8 +427,43 @@ struct FluxStage {
                 const int v = VS::at(kv); x[v] = *p.wp.at(jj, v, tc); y[v] = *p.wm.at(jj, v, tc); }
                 if (KIND == 1) mean_state_t<HYDRO>(x, y, a); else roe_state_t<HYDRO>(x, y, a);
             }
-            return spectral_radius_t<AX, HYDRO>(a, gamma);
         };
+        auto speed_at = [&](int64_t jj, int64_t tc) -> double {
+            double a[NVAR];
+            state_at(jj, tc, a);
+            return dissipation(a);
+        };
+
+        if (LW && p.lw_pass == 1) {
+            // search pass: rows of the padded array are m = 0 .. N+1; entry m holds interface bc(m) (cells bc(m-1) for PCM)
+            ex.publish_min3([&](int tid, unsigned long long* key) {
+                key[0] = key[1] = key[2] = ~0ull;
+                const int lane_id = tid & 31, w = tid >> 5;
+                const int64_t j = (int64_t)by * nwarp + w, t = (int64_t)bx * OWN - H + lane_id;
+                const int64_t n = p.ns_glob;
+                const int64_t first = PCM ? 0 : 1, last = PCM ? n - 1 : n;     // interfaces 1..N, or cells 0..N-1
+                if (lane_id < H || lane_id >= 32 - H || t < 0 || t >= p.nt || j < first || j > last) return;
+                double a[NVAR];
+                state_at(j, t, a);
+                const double u = a[1 + AX], c = sqrt(gamma * a[4] / a[0]);
+                const double col[3] = {u - c, u, u + c};
+                // padded rows this entry appears in
+                int64_t rows[3] = {PCM ? j + 1 : j, -1, -1};
+                const bool wrap = p.bc == BC_WRAP;
+                if (j == (wrap ? last : first)) rows[1] = 0;            // pad in front: np.pad wraps / repeats the edge
+                if (j == (wrap ? first : last)) rows[2] = n + 1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (!(col[k] != 0.0)) continue;
+                    for (int q = 0; q < 3; ++q) {
+                        if (rows[q] < 0) continue;
+                        const unsigned long long kk = ((unsigned long long)(rows[q] * p.nt + t) << 1) | (col[k] > 0.0 ? 1ull : 0ull);
+                        if (kk < key[k]) key[k] = kk;
+                    }
+                }
+            }, p.lw_keys);
+            return;
+        }
 
         // A: load the interface states, pointwise conversions, wave speed
         ex.wphase([&](int tid) {
@@ -442,10 +500,9 @@ struct FluxStage {
             bool counts;
             if (PCM) {
                 // pcm.py:30: Jacobian at the padded cells; interface j sees cells b(j-1) and b(j)
-                const double lp = spectral_radius_t<AX, HYDRO>(st.wp, gamma);
-                lam_here = lp;
+                lam_here = spectral_radius_t<AX, HYDRO>(st.wp, gamma);
                 counts = jg >= 0 && jg < p.ns_glob && j < p.ns;
-                if (LLF) st.lam = npmax(spectral_radius_t<AX, HYDRO>(st.wm, gamma), lp);
+                if (LLF) st.lam = npmax(dissipation(st.wm), dissipation(st.wp));
             } else {
                 double a[NVAR];
                 if (KIND == 1) mean_state_t<HYDRO>(st.wp, st.wm, a); else roe_state_t<HYDRO>(st.wp, st.wm, a);
@@ -455,14 +512,18 @@ struct FluxStage {
                     // entries j and j+1 of the pad-1 array of interface speeds (solvers.py:73-74)
                     const int64_t ja = edge ? clamp_index(jg, 1, p.ns_glob) - p.s_off : j;
                     const int64_t jb = edge ? clamp_index(jg + 1, 1, p.ns_glob) - p.s_off : j + 1;
-                    const double la = (ja == j) ? lam_here : speed_at(ja, tc);
-                    const double lb = (jb == j) ? lam_here : speed_at(jb, tc);
+                    const double here = LW ? dissipation(a) : lam_here;
+                    const double la = (ja == j) ? here : speed_at(ja, tc);
+                    const double lb = (jb == j) ? here : speed_at(jb, tc);
                     st.lam = npmax(la, lb);
                 }
             }
             const bool owned = lane_id >= H && lane_id < 32 - H && st.t >= 0 && st.t < p.nt;
             if (counts && owned) {
                 if (lam_here == lam_here && lam_here <= 1.7976931348623157e308) st.lam_max = lam_here; else st.bad = true;
+                // Lax-Wendroff with a negative averaged pressure: the reference carries on in complex arithmetic
+                // (complex eigenvalues); the device path does not follow it there and reports the step as non-finite
+                if (LW && !(st.lam == st.lam)) st.bad = true;
             }
         });
         ex.publish_max([&](int k, double& val, bool& bad) { val = tls[k].lam_max; bad = tls[k].bad; }, p.eigmax_bits, p.flag);

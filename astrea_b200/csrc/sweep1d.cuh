@@ -27,6 +27,10 @@ struct Sweep1DParams {
     // PPM authors 'c' / 'ph' (recon.cuh): pass 1 / 2 only evaluate the grid-wide switches into ppm_flags[0..2]
     int ppm_author, pass;
     int* ppm_flags;
+    // Lax-Wendroff (see FluxStage in stages2d.cuh): lw_pass == 1 searches the first non-zero entry of the columns
+    // u - c, u, u + c of the padded spectrum into lw_keys[0..2]
+    int lw_pass;
+    unsigned long long* lw_keys;
 };
 
 struct TileAccessor {
@@ -49,7 +53,7 @@ struct Sweep1D {
     static int threads_for(int tile) { return tile + HL + HH; }
     static size_t smem_bytes(int nthreads) { return sizeof(double) * (size_t)nthreads * (NVAR * 5 + 1); }
 
-    struct Tls { double lam; bool bad; };
+    struct Tls { double lam; bool bad; unsigned long long key[3]; };
 
     template <class Ex>
     static HD void block(const Params& p, int bx, int, Ex& ex) {
@@ -68,6 +72,7 @@ struct Sweep1D {
         ex.phase([&](int k) {
             tls[k].lam = 0.0;
             tls[k].bad = false;
+            tls[k].key[0] = tls[k].key[1] = tls[k].key[2] = ~0ull;
             const int64_t c = clamp_index(base + k, -GHOST, p.n + GHOST - 1);
 #pragma unroll
             for (int v = 0; v < NVAR; ++v) Q[v * NT + k] = *p.q.at(0, v, c);
@@ -148,7 +153,38 @@ struct Sweep1D {
             if (counts && j >= c0 && j <= c0 + p.tile) {
                 if (lam == lam && lam <= 1.7976931348623157e308) tls[k].lam = lam; else tls[k].bad = true;
             }
+            if (SOLVER == SOL_LW) {
+                // solvers.py:84-87: second^2 / max|lambda| with second = np.unique(characteristics, axis=-1)[..., 1]
+                const double u = a[1], c = sqrt(gamma * a[4] / a[0]);
+                if (p.lw_pass == 1) {
+                    const int64_t first = SCHEME == SCH_PCM ? 0 : 1, last = SCHEME == SCH_PCM ? p.n - 1 : p.n;
+                    if (!(counts && j >= c0 && j <= c0 + p.tile)) return;
+                    const bool wrap = p.bc == BC_WRAP;
+                    const int64_t rows[3] = {SCHEME == SCH_PCM ? j + 1 : j, j == (wrap ? last : first) ? 0 : -1,
+                                             j == (wrap ? first : last) ? p.n + 1 : -1};
+                    const double col[3] = {u - c, u, u + c};
+                    for (int q = 0; q < 3; ++q) {
+                        if (!(col[q] != 0.0)) continue;
+                        for (int m = 0; m < 3; ++m) {
+                            if (rows[m] < 0) continue;
+                            const unsigned long long kk = ((unsigned long long)rows[m] << 1) | (col[q] > 0.0 ? 1ull : 0ull);
+                            if (kk < tls[k].key[q]) tls[k].key[q] = kk;
+                        }
+                    }
+                    return;
+                }
+                int rank = 0;
+                for (int q = 0; q < 3; ++q) rank += (p.lw_keys[q] != ~0ull && (p.lw_keys[q] & 1ull) == 0) ? 1 : 0;
+                const double second = rank == 0 ? u - c : (rank == 1 ? 0.0 : u);
+                LAM[k] = sdiv(second * second, lam);
+                // negative averaged pressure: the reference continues in complex arithmetic, the device reports it
+                if (counts && j >= c0 && j <= c0 + p.tile && !(LAM[k] == LAM[k])) tls[k].bad = true;
+            }
         });
+        if (SOLVER == SOL_LW && p.lw_pass == 1) {
+            ex.publish_min3([&](int k, unsigned long long* key) { for (int q = 0; q < 3; ++q) key[q] = tls[k].key[q]; }, p.lw_keys);
+            return;
+        }
         // Riemann flux at interface j = base + k
         ex.phase([&](int k) {
             const int64_t j = base + k;

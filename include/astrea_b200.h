@@ -24,7 +24,8 @@ typedef struct astrea_ctx astrea_ctx;
 enum { ASTREA_PCM = 0, ASTREA_PLM = 1, ASTREA_PPM = 2, ASTREA_WENO3 = 3, ASTREA_WENO5 = 4, ASTREA_WENO7 = 5 };   /* sim_variables.subgrid, evolvers.py:14-21 */
 enum { ASTREA_PPM_MC = 0, ASTREA_PPM_COLELLA = 1, ASTREA_PPM_PH = 2 };   /* ppm.run(author=...): evolvers.py:17 passes 'mc'; 'c' / 'ph' = limiters.py:53-78,144-201 */
 enum { ASTREA_MINMOD = 0, ASTREA_VANLEER = 1, ASTREA_OSPRE = 2, ASTREA_VANALBADA = 3, ASTREA_KOREN = 4, ASTREA_SUPERBEE = 5 }; /* limiters.py:10-49 */
-enum { ASTREA_LLF = 0, ASTREA_LW = 1, ASTREA_HLLC = 2, ASTREA_HLLD = 3 };                                         /* sim_variables.solver, solvers.py:13-31 */
+enum { ASTREA_LLF = 0, ASTREA_LW = 1, ASTREA_HLLC = 2, ASTREA_HLLD = 3 };                                         /* sim_variables.solver, solvers.py:13-31;
+                                                    ASTREA_LW: grids without v_z / B, one GPU (solvers.py:84 sorts LAPACK's eigenvalue slots grid-wide) */
 enum { ASTREA_EULER = 0, ASTREA_RK4 = 1, ASTREA_SSPRK22 = 2, ASTREA_SSPRK33 = 3, ASTREA_SSPRK43 = 4,
        ASTREA_SSPRK53 = 5, ASTREA_SSPRK54 = 6, ASTREA_SSPRK104 = 7 };                                          /* sim_variables.timestep, evolvers.py:79-206 */
 enum { ASTREA_EDGE = 0, ASTREA_WRAP = 1 };                                                                       /* sim_variables.boundary (np.pad mode), fv.py:57-61 */

@@ -27,6 +27,9 @@ def extended(a, lo, hi, bc, axis=0):
 
 def safe_div(num, den):
     """fv.py:19-20 — quotient, 0 where the divisor is exactly 0."""
+    # LAPACK may hand back a complex-typed spectrum whose imaginary parts are all zero (Lax-Wendroff path)
+    num = num.real if np.iscomplexobj(num) else num
+    den = den.real if np.iscomplexobj(den) else den
     num, den = np.broadcast_arrays(np.asarray(num, dtype=float), np.asarray(den, dtype=float))
     out = np.zeros(num.shape)
     np.divide(num, den, out=out, where=den != 0)

@@ -29,6 +29,32 @@ def lw_flux(spectrum, qp, qm, fp, fm):
     return .5 * (fm + fp) - .5 * ((qp - qm) * lam[..., None])
 
 
+def lw_flux_closed(avg_pad, gamma, axis, qp, qm, fp, fm):
+    """The same without LAPACK, for states with v_z = 0 and B = 0 (what the device computes).
+
+    There the spectrum of the primitive Jacobian is {u - c, u, u + c, 0} (the value u fills five slots), LAPACK returns
+    it in a fixed slot order, and np.unique(axis=-1) sorts the four distinct columns lexicographically over all
+    padded points: u - c < u < u + c at the first point, so only the place of the all-zero column is open — it is
+    the number of columns whose first non-zero entry is negative.  Column 1 is then u - c, 0 or u.
+    """
+    from .gridops import closed_spectral_radius
+    if np.any(avg_pad[..., 3] != 0) or np.any(avg_pad[..., 5:8] != 0):
+        raise ValueError("closed-form Lax-Wendroff needs v_z = 0 and B = 0 (SURVEY Q11)")
+    with np.errstate(all="ignore"):
+        u = avg_pad[..., 1 + axis]
+        c = np.sqrt(gamma * avg_pad[..., 4] / avg_pad[..., 0])
+        rank = 0
+        for column in (u - c, u, u + c):
+            flat = column.reshape(-1)
+            nz = np.nonzero(flat)[0]
+            if len(nz) and flat[nz[0]] < 0:
+                rank += 1
+        second = (u - c) if rank == 0 else (np.zeros_like(u) if rank == 1 else u)
+        coeff = safe_div(second * second, closed_spectral_radius(avg_pad, gamma, axis))
+    lam = pairwise_max(coeff)
+    return .5 * (fm + fp) - .5 * ((qp - qm) * lam[..., None])
+
+
 def hllc_flux(axis, gamma, wp, wm, qp, qm, fp, fm, low_mach=False):
     """solvers.py:92-138 — HLLC with the reference's star-state and selection quirks."""
     rL, uL, pL = wm[..., 0], wm[..., axis + 1], wm[..., 4]

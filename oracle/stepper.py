@@ -11,7 +11,7 @@ from . import ct
 from .gridops import (extended, second_difference, ONE_24TH, prim_avg_of_cons_avg, cons_avg_of_prim_avg,
                       centred_of_avg, physical_flux, roe_state, spectral_radius)
 from .reconstruct import cell_states_pcm, cell_states_plm, cell_states_ppm, cell_states_weno
-from .riemann import llf_flux, lw_flux, hllc_flux, hlld_flux
+from .riemann import llf_flux, lw_flux, lw_flux_closed, hllc_flux, hlld_flux
 
 
 def _frame(a, ax):
@@ -25,7 +25,7 @@ def sweep_data(qbar, ax, cfg):
     kind, order = cfg.scheme
     qf = _frame(qbar, ax)
     wS = prim_avg_of_cons_avg(qf, cfg, "cell")
-    d = {"wS": wS}
+    d = {"wS": wS, "sweep_axis": ax}
     if kind == "pcm":
         w_pad = extended(wS, 1, 1, bc)
         q_pad = extended(qf, 1, 1, bc)
@@ -60,8 +60,8 @@ def _solve(cfg, solver_axis, spectrum, local_speed, d):
     if kind == "hlld":
         return hlld_flux(solver_axis, cfg.gamma, cfg.boundary, d["wS"], d["wp"], d["wm"], d["qp"], d["qm"], d["fp"], d["fm"])
     if kind == "lw":
-        if spectrum is None:
-            raise ValueError("Lax-Wendroff needs eigen='lapack' (SURVEY Q11)")
+        if spectrum is None:      # eigen='closed'
+            return lw_flux_closed(d["avg_pad"], cfg.gamma, d["sweep_axis"], d["qp"], d["qm"], d["fp"], d["fm"])
         return lw_flux(spectrum, d["qp"], d["qm"], d["fp"], d["fm"])
     return llf_flux(local_speed, d["qp"], d["qm"], d["fp"], d["fm"])
 

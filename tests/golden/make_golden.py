@@ -42,6 +42,11 @@ CASES = [
     ("x_rj_ppm_hlld_ssprk33", "ryu-jones", 128, 1, "ppm", "hlld", "ssprk(3,3)", 3, None),
     ("x_ot_plm_llf_ssprk22_ct", "orszag-tang", 32, 2, "plm", "lf", "ssprk(2,2)", 3, None),
     ("x_ot_ppm_hllc_ssprk33_ct", "orszag-tang", 32, 2, "ppm", "hllc", "ssprk(3,3)", 2, None),
+    # Lax-Wendroff (solvers.py:79-88), states whose averaged pressures stay positive (real spectrum)
+    ("x_sod_plm_lw_ssprk22", "sod", 128, 1, "plm", "lw", "ssprk(2,2)", 3, None),
+    ("x_khi_plm_lw_ssprk22", "khi", 32, 2, "plm", "lw", "ssprk(2,2)", 3, None),
+    ("x_toro2_pcm_lw_euler", "toro2", 64, 1, "pcm", "lw", "euler", 3, None),
+    ("x_sq_weno3_lw_ssprk22", "square", 48, 1, "weno3", "lw", "ssprk(2,2)", 2, None),
 ]
 
 

@@ -216,11 +216,26 @@ def test_call_order_is_enforced(hostsim_lib):
 
 
 def test_unsupported_selectors_fail_loudly(hostsim_lib):
+    """Lax-Wendroff is reproduced for spectra without v_z / B only: anything else is refused, not guessed."""
     from astrea_b200 import _native as N
     from cases import native_cfg
-    meta = _meta("sod", 64, 1, "plm", "lw", "ssprk(2,2)", None)     # Lax-Wendroff: SURVEY Q11
+    # constrained transport + Lax-Wendroff: refused at creation
+    meta = _meta("orszag-tang", 16, 2, "plm", "lw", "ssprk(2,2)", None, mhd=True)
     with pytest.raises(N.AstreaError):
         N.Context(native_cfg(meta), lib=hostsim_lib)
+    # a 1D MHD state (B != 0) + Lax-Wendroff: refused when the operator runs
+    meta = _meta("brio-wu", 64, 1, "plm", "lw", "ssprk(2,2)", None)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(initial_state("brio-wu", 64, 1, 1.4, False))
+    with pytest.raises(N.AstreaError) as err:
+        ctx.step()
+    assert err.value.code == N.E_ARG and "Lax-Wendroff" in str(err.value)
+    ctx.close()
+    # unknown enums
+    cfg = native_cfg(_meta("sod", 64, 1, "plm", "lf", "ssprk(2,2)", None))
+    cfg.solver = 9
+    with pytest.raises(N.AstreaError):
+        N.Context(cfg, lib=hostsim_lib)
 
 
 @pytest.mark.parametrize("spec", [("sod", 1, "plm", "lf", "ssprk(2,2)", 96), ("ll6", 2, "ppm", "hllc", "ssprk(3,3)", 32),
