@@ -4,7 +4,9 @@ namespace astrea {
 int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
     switch (scheme) {
         case SCH_PLM: return launch<ReconStage<SCH_PLM>>(p, gx, gy, nthreads, 0, st);
-        case SCH_PPM: return launch<ReconStage<SCH_PPM>>(p, gx, gy, nthreads, 0, st);
+        case SCH_PPM:
+            if (p.ppm_author != PPM_MC) return launch<ReconStage<SCH_PPM, true>>(p, gx, gy, nthreads, 0, st);
+            return launch<ReconStage<SCH_PPM>>(p, gx, gy, nthreads, 0, st);
         case SCH_WENO3: return launch<ReconStage<SCH_WENO3>>(p, gx, gy, nthreads, 0, st);
         case SCH_WENO5: return launch<ReconStage<SCH_WENO5>>(p, gx, gy, nthreads, 0, st);
         case SCH_WENO7: return launch<ReconStage<SCH_WENO7>>(p, gx, gy, nthreads, 0, st);

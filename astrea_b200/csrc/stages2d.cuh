@@ -223,7 +223,8 @@ struct ColumnAccessor {
     HD int64_t b(int64_t k) const { return clamp_index(k + off, lo_glob, hi_glob) - off; }
 };
 
-template <int SCHEME>
+// CPH: the PPM authors 'c' / 'ph' (a separate instantiation keeps the default 'mc' march lean)
+template <int SCHEME, bool CPH = false>
 struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
@@ -261,8 +262,8 @@ struct ReconStage {
                 if (i < last) ahead = col[(i + 1 + HI) * rp];
                 const int64_t ig = i + p.s_off;
                 double wl, wr, wf;
-                if constexpr (SCHEME == SCH_PPM) {
-                    if (p.ppm_author != PPM_MC) {
+                if constexpr (SCHEME == SCH_PPM && CPH) {
+                    {
                         if (edge && (ig < 0 || ig > p.ns_glob - 1)) continue;
                         const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
                         if (p.pass != 0 && !interior) continue;
