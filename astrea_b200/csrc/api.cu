@@ -642,7 +642,9 @@ int run_combine(astrea_ctx* c, const Instr& ins, int64_t row_lo, int64_t row_hi)
     if (ins.fused_rate >= 0) {
         UpdateParams u{rate_params(c), p, ins.store_rate ? c->rates[ins.fused_rate].plane : Plane{nullptr, 0, 0}};
         u.rate.row_lo = row_lo; u.rate.row_hi = row_hi;
-        const int gx = (int)((c->ncol + 31) / 32), gy = (int)((row_hi - row_lo + 31) / 32);
+        const bool one_d = c->cfg.dimension == 1;
+        const int gx = one_d ? (int)((c->ncol + 255) / 256) : (int)((c->ncol + 31) / 32);
+        const int gy = one_d ? 1 : (int)((row_hi - row_lo + 31) / 32);
         Timed timed(c, CLS_UPDATE);
         const size_t sm = UpdateKernel<1, false>::smem_bytes();
         int e = -1;

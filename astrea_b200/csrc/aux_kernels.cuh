@@ -272,6 +272,44 @@ struct UpdateKernel {
         const bool two_d = p.dimension == 2;
         // every plane of a context has the same geometry: one offset addresses them all
         const int64_t rp = cb.out.row_pitch, cp = cb.out.col_pitch;
+        if (!two_d) {
+            // 1D: one row, a thread per cell (blocks of MAX_THREADS cells), every variable in one go — no tile, no barrier
+            ex.phase([&](int tid) {
+                const int64_t c = (int64_t)bx * MAX_THREADS + tid;
+                if (c >= p.ncol) return;
+                const double dt = *cb.dt;
+                for (int a = 0; a < p.vars.n; ++a) {
+                    const int64_t off = (int64_t)p.vars.v[a] * cp + c;
+                    const double L = -p.d0.base[off];
+                    if (pp.rate_store.base != nullptr) pp.rate_store.base[off] = L;
+                    double acc = 0.0;
+                    if (!BRACKET) {
+#pragma unroll
+                        for (int k = 0; k < NTERMS; ++k) {
+                            const double x = cb.is_rate[k] == 2 ? L : cb.term[k].base[off];
+                            const double t = (cb.is_rate[k] ? cb.coef[k] * dt : cb.coef[k]) * x;
+                            acc = (k == 0) ? t : acc + t;
+                        }
+                        if (cb.scale != 1.0) acc = cb.scale * acc;
+                    } else {
+                        double regs = 0.0, rates = 0.0;
+                        bool fr = true, fl = true;
+#pragma unroll
+                        for (int k = 0; k < NTERMS; ++k) {
+                            const double x = cb.is_rate[k] == 2 ? L : cb.term[k].base[off];
+                            const double t = cb.coef[k] * x;
+                            if (cb.is_rate[k]) { rates = fl ? t : rates + t; fl = false; }
+                            else { regs = fr ? t : regs + t; fr = false; }
+                        }
+                        double tail = dt * rates;
+                        if (cb.scale != 1.0) tail = cb.scale * tail;
+                        acc = regs + tail;
+                    }
+                    cb.out.base[off] = acc;
+                }
+            });
+            return;
+        }
         for (int a = 0; a < p.vars.n; ++a) {
             const int v = p.vars.v[a];
             if (two_d) {
