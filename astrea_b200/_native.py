@@ -78,6 +78,7 @@ _SIGNATURES = {
     "astrea_read_eigmax": (C.c_int, [C.c_void_p, _PD]),
     "astrea_sync": (C.c_int, [C.c_void_p]),
     "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
+    "astrea_fp64_probe": (C.c_int, [C.c_void_p, _PD]),
     "astrea_launch_count": (C.c_int64, [C.c_void_p]),
     "astrea_save_state": (C.c_int, [C.c_void_p]),
     "astrea_restore_state": (C.c_int, [C.c_void_p]),
@@ -257,6 +258,12 @@ class Context:
         eig = (C.c_double * 2)()
         self._check(self.lib.astrea_read_eigmax(self._h, eig))
         return [eig[a] for a in range(self.cfg.dimension)]
+
+    def fp64_probe(self):
+        """Sustained fp64 FMA rate of this GPU in TFLOP/s (measurement aid of bench.py)."""
+        t = C.c_double()
+        self._check(self.lib.astrea_fp64_probe(self._h, C.byref(t)))
+        return t.value
 
     def sync(self):
         self._check(self.lib.astrea_sync(self._h))

@@ -864,6 +864,35 @@ int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, i
     return 0;
 }
 
+int astrea_fp64_probe(astrea_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(c, ASTREA_E_ARG, "astrea_fp64_probe: NULL argument");
+    *tflops = 0.0;
+#ifdef ASTREA_DEVICE_BUILD
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_fp64_probe: a step is in flight");
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    if ((size_t)blocks * threads > c->plane_doubles) return 0;      // tiny grid: no scratch to write to
+    Fp64ProbeParams p{c->d0.mem, iters, 1.0000001, 1e-9};
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    ASTREA_TRY(launch<Fp64ProbeKernel>(p, blocks, 1, threads, 0, c->st));       // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a, c->st.s);
+        ASTREA_TRY(launch<Fp64ProbeKernel>(p, blocks, 1, threads, 0, c->st));
+        cudaEventRecord(b, c->st.s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+#endif
+    return 0;
+}
+
 int astrea_program_length(const astrea_ctx* c) { return c ? (int)c->prog.size() : ASTREA_E_ARG; }
 
 int astrea_instr_is_operator(const astrea_ctx* c, int i) {

@@ -487,6 +487,33 @@ struct PrimKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ fp64 peak probe
+// Measurement aid for bench.py: dependent-free chains of DFMA, so that the roofline discussion can quote the fp64
+// rate this GPU actually sustains (the path is bound by the fp64 pipe).  8 independent accumulators per
+// thread, `iters` x 8 FMAs each; the result is stored so that nothing is optimised away.
+struct Fp64ProbeParams {
+    double* out;
+    int iters;
+    double a, b;
+};
+struct Fp64ProbeKernel {
+    using Params = Fp64ProbeParams;
+    static constexpr int MAX_THREADS = 256;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            double x0 = tid, x1 = tid + 1, x2 = tid + 2, x3 = tid + 3, x4 = tid + 4, x5 = tid + 5, x6 = tid + 6, x7 = tid + 7;
+            const double a = p.a, b = p.b;
+            for (int i = 0; i < p.iters; ++i) {
+                x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+                x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+            }
+            p.out[(int64_t)bx * NT + tid] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ diagnostics
 // Device-side reductions of the post-processing the reference does on its HDF5 snapshots (functions/analytic.py):
 //   conservation (:66-77)    sum over the grid of every conservative variable

@@ -278,6 +278,11 @@ def run_ours(a):
                 "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
                 "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak,
                 "note": "fp64-pipe bound, not HBM bound: see DESIGN.md"}
+    # the bound that really applies: the fp64 pipe.  Measured FMA peak of this GPU, and how busy ncu saw the pipe.
+    sim.restore_state()
+    roofline["fp64"] = {"peak_tflops_measured": ctx.fp64_probe(),
+                        "pipe_busy_ncu": "FluxStage 53 %, ReconStage 53 %, PrimBothStage 40 % (profiles/README.md r1g); "
+                                         "issue-slot limit for the flux stage's instruction mix: 57 % (DESIGN.md)"}
     # DRAM bytes actually moved per sweep, from the committed `ncu --set full` capture (profiles/summarize.py)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):

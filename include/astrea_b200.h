@@ -164,6 +164,10 @@ int astrea_restore_state(astrea_ctx* ctx);
 int astrea_profile(astrea_ctx* ctx, int enable);
 int astrea_profile_read(astrea_ctx* ctx, double* ms_by_class, int64_t* launches_by_class);
 
+/* Measurement aid: the fp64 FMA rate (TFLOP/s, FMA = 2) this GPU sustains on independent DFMA chains, so that the
+ * roofline report can say how far the fp64-bound stages are from the fp64 peak.  0 in the host-simulated build. */
+int astrea_fp64_probe(astrea_ctx* ctx, double* tflops);
+
 /* Number of kernels this library launched on the context's stream since creation (bench.py "gpu_launches"). */
 int64_t astrea_launch_count(const astrea_ctx* ctx);
 /* 1 when built by nvcc for sm_100a, 0 for the host-simulated test build. */
