@@ -262,7 +262,9 @@ struct UpdateKernel {
     using Params = UpdateParams;
     static constexpr int MAX_THREADS = 256;
     static constexpr int TILE = 32;
-    static size_t smem_bytes() { return sizeof(double) * TILE * (TILE + 1); }
+    static constexpr int VG = 4;                          // variables per pass through the tile (a hydro state is one pass)
+    static constexpr int ROWS = TILE * TILE / MAX_THREADS; // tile rows per thread
+    static size_t smem_bytes() { return sizeof(double) * VG * TILE * (TILE + 1); }
     template <class Ex>
     static HD void block(const Params& pp, int bx, int by, Ex& ex) {
         const RateParams& p = pp.rate;
@@ -310,82 +312,105 @@ struct UpdateKernel {
             });
             return;
         }
-        for (int a = 0; a < p.vars.n; ++a) {
-            const int v = p.vars.v[a];
-            if (two_d) {
-                ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
-                    const int tx = tid % TILE;
-                    for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
-                        const int64_t yr = c0 + ty, xc = r0 + tx;
-                        if (yr < p.ncol && xc < p.row_hi) {
-                            const double* f = p.f1t.at(yr, v, xc);
-                            tile[ty * (TILE + 1) + tx] = (f[p.f1t.row_pitch] - f[0]) / p.dx;
-                        }
+        // 2D: the variables go through the tile in groups of VG, so that one barrier covers a whole group and every
+        // load of a group is in flight at once (the update is bound by memory latency, not by arithmetic)
+        const double dt = *cb.dt;
+        double cf[NTERMS];
+        int kind[NTERMS];
+#pragma unroll
+        for (int k = 0; k < NTERMS; ++k) {
+            kind[k] = cb.is_rate[k];
+            cf[k] = (!BRACKET && kind[k]) ? cb.coef[k] * dt : cb.coef[k];
+        }
+        const bool wrap = p.bc == BC_WRAP;
+        for (int a0 = 0; a0 < p.vars.n; a0 += VG) {
+            ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
+                const int tx = tid % TILE;
+                const int64_t xc = r0 + tx;
+                double lo[VG][ROWS], hi[VG][ROWS];
+#pragma unroll
+                for (int g = 0; g < VG; ++g) {
+                    const int v = p.vars.v[a0 + g < p.vars.n ? a0 + g : a0];
+#pragma unroll
+                    for (int i = 0; i < ROWS; ++i) {
+                        const int ty = tid / TILE + i * (MAX_THREADS / TILE);
+                        const int64_t yr = c0 + ty;
+                        const bool ok = yr < p.ncol && xc < p.row_hi && a0 + g < p.vars.n;
+                        const double* f = p.f1t.at(ok ? yr : 0, v, ok ? xc : 0);
+                        lo[g][i] = ok ? f[0] : 0.0;
+                        hi[g][i] = ok ? f[p.f1t.row_pitch] : 0.0;
                     }
-                });
-            }
+                }
+#pragma unroll
+                for (int g = 0; g < VG; ++g)
+#pragma unroll
+                    for (int i = 0; i < ROWS; ++i) {
+                        const int ty = tid / TILE + i * (MAX_THREADS / TILE);
+                        tile[(g * TILE + ty) * (TILE + 1) + tx] = (hi[g][i] - lo[g][i]) / p.dx;
+                    }
+            });
             ex.phase([&](int tid) {
                 const int tx = tid % TILE;
-                const double dt = *cb.dt;
-                const double* tp[NTERMS];
-                double cf[NTERMS];
-                int kind[NTERMS];
+                const int64_t c = c0 + tx;
 #pragma unroll
-                for (int k = 0; k < NTERMS; ++k) {
-                    tp[k] = cb.term[k].base + (int64_t)v * cp;
-                    kind[k] = cb.is_rate[k];
-                    cf[k] = (!BRACKET && kind[k]) ? cb.coef[k] * dt : cb.coef[k];
-                }
-                for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
-                    const int64_t r = r0 + ty, c = c0 + tx;
+                for (int i = 0; i < ROWS; ++i) {
+                    const int ty = tid / TILE + i * (MAX_THREADS / TILE);
+                    const int64_t r = r0 + ty;
                     if (r >= p.row_hi || c >= p.ncol) continue;
                     const int64_t off = r * rp + c;
-                    double total;
-                    if (two_d) {
-                        const double* f = p.f0.base + off + (int64_t)v * cp;
-                        total = (f[rp] - f[0]) / p.dx;
-                        total = total + tile[tx * (TILE + 1) + ty];
-                    } else {
-                        total = p.d0.base[off + (int64_t)v * cp];
+                    double fl[VG], fh[VG], x[VG][NTERMS];
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) {
+                        if (a0 + g >= p.vars.n) continue;
+                        const int64_t o = off + (int64_t)p.vars.v[a0 + g] * cp;
+                        fl[g] = p.f0.base[o];
+                        fh[g] = p.f0.base[o + rp];
+#pragma unroll
+                        for (int k = 0; k < NTERMS; ++k) x[g][k] = kind[k] == 2 ? 0.0 : cb.term[k].base[o];
                     }
-                    if (p.emf != nullptr && (v == 5 || v == 6)) {
-                        // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
-                        const bool wrap = p.bc == BC_WRAP;
-                        const double e0 = p.emf[r * p.ncol + c];
-                        if (v == 5) {
-                            const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
-                            total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
+#pragma unroll
+                    for (int g = 0; g < VG; ++g) {
+                        if (a0 + g >= p.vars.n) continue;
+                        const int v = p.vars.v[a0 + g];
+                        const int64_t o = off + (int64_t)v * cp;
+                        double total = (fh[g] - fl[g]) / p.dx;
+                        total = total + tile[(g * TILE + tx) * (TILE + 1) + ty];
+                        if (p.emf != nullptr && (v == 5 || v == 6)) {
+                            // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
+                            const double e0 = p.emf[r * p.ncol + c];
+                            if (v == 5) {
+                                const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
+                                total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
+                            } else {
+                                const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
+                                total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
+                            }
+                        }
+                        const double L = -total;
+                        if (pp.rate_store.base != nullptr) pp.rate_store.base[o] = L;
+                        double acc = 0.0;
+                        if (!BRACKET) {
+#pragma unroll
+                            for (int k = 0; k < NTERMS; ++k) {
+                                const double t = cf[k] * (kind[k] == 2 ? L : x[g][k]);
+                                acc = (k == 0) ? t : acc + t;
+                            }
+                            if (cb.scale != 1.0) acc = cb.scale * acc;
                         } else {
-                            const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
-                            total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
-                        }
-                    }
-                    const double L = -total;
-                    if (pp.rate_store.base != nullptr) pp.rate_store.base[off + (int64_t)v * cp] = L;
-                    double acc = 0.0;
-                    if (!BRACKET) {
+                            double regs = 0.0, rates = 0.0;
+                            bool fr = true, fl_ = true;
 #pragma unroll
-                        for (int k = 0; k < NTERMS; ++k) {
-                            const double x = kind[k] == 2 ? L : tp[k][off];
-                            const double t = cf[k] * x;
-                            acc = (k == 0) ? t : acc + t;
+                            for (int k = 0; k < NTERMS; ++k) {
+                                const double t = cf[k] * (kind[k] == 2 ? L : x[g][k]);
+                                if (kind[k]) { rates = fl_ ? t : rates + t; fl_ = false; }
+                                else { regs = fr ? t : regs + t; fr = false; }
+                            }
+                            double tail = dt * rates;
+                            if (cb.scale != 1.0) tail = cb.scale * tail;
+                            acc = regs + tail;
                         }
-                        if (cb.scale != 1.0) acc = cb.scale * acc;
-                    } else {
-                        double regs = 0.0, rates = 0.0;
-                        bool fr = true, fl = true;
-#pragma unroll
-                        for (int k = 0; k < NTERMS; ++k) {
-                            const double x = kind[k] == 2 ? L : tp[k][off];
-                            const double t = cf[k] * x;
-                            if (kind[k]) { rates = fl ? t : rates + t; fl = false; }
-                            else { regs = fr ? t : regs + t; fr = false; }
-                        }
-                        double tail = dt * rates;
-                        if (cb.scale != 1.0) tail = cb.scale * tail;
-                        acc = regs + tail;
+                        cb.out.base[o] = acc;
                     }
-                    cb.out.base[off + (int64_t)v * cp] = acc;
                 }
             });
         }

@@ -17,7 +17,7 @@ HD void prim_of_cons(const double* q, double* w, double gamma) {
 
 HD void cons_of_prim(const double* w, double* q, double gamma) {
     const double rho = w[0];
-    const double e = w[4] / (gamma - 1.0) + 0.5 * (rho * norm3sq(w[1], w[2], w[3]) + norm3sq(w[5], w[6], w[7]));
+    const double e = ddiv(w[4], gamma - 1.0) + 0.5 * (rho * norm3sq(w[1], w[2], w[3]) + norm3sq(w[5], w[6], w[7]));
     q[0] = rho; q[1] = w[1] * rho; q[2] = w[2] * rho; q[3] = w[3] * rho; q[4] = e; q[5] = w[5]; q[6] = w[6]; q[7] = w[7];
 }
 
@@ -32,7 +32,7 @@ HD void physical_flux(const double* w, double* f, double gamma) {
     f[1 + t1] = rho * vn * w[1 + t1] - bn * w[5 + t1];
     f[1 + t2] = rho * vn * w[1 + t2] - bn * w[5 + t2];
     const double vdotb = (w[1] * w[5] + w[2] * w[6]) + w[3] * w[7];
-    f[4] = vn * (0.5 * rho * norm3sq(w[1], w[2], w[3]) + (gamma * p) / (gamma - 1.0) + norm3sq(w[5], w[6], w[7])) - bn * vdotb;
+    f[4] = vn * (0.5 * rho * norm3sq(w[1], w[2], w[3]) + ddiv(gamma * p, gamma - 1.0) + norm3sq(w[5], w[6], w[7])) - bn * vdotb;
     f[5 + n] = 0.0;
     f[5 + t1] = w[5 + t1] * vn - bn * w[1 + t1];
     f[5 + t2] = w[5 + t2] * vn - bn * w[1 + t2];
@@ -40,7 +40,7 @@ HD void physical_flux(const double* w, double* f, double gamma) {
 
 // make_Roe_average(first = w_plus, second = w_minus)
 HD void roe_state(const double* first, const double* second, double* out) {
-    const double s2 = sqrt(second[0]), s1 = sqrt(first[0]);
+    const double s2 = dsqrt(second[0]), s1 = dsqrt(first[0]);
     const double den = s2 + s1;
     out[0] = s2 * s1;
     out[1] = sdiv(first[1] * s1 + second[1] * s2, den);
@@ -66,7 +66,7 @@ template <bool H> struct VarSet;
 template <> struct VarSet<false> { static constexpr int N = 8; static HD constexpr int at(int a) { return a; } };
 template <> struct VarSet<true> { static constexpr int N = 4; static HD constexpr int at(int a) { return a < 3 ? a : 4; } };
 
-HD double norm2sq(double a, double b) { double n = sqrt(a * a + b * b); return n * n; }
+HD double norm2sq(double a, double b) { double n = dsqrt(a * a + b * b); return n * n; }
 
 template <bool H>
 HD void prim_of_cons_t(const double* q, double* w, double gamma) {
@@ -82,7 +82,7 @@ HD void cons_of_prim_t(const double* w, double* q, double gamma) {
     if (!H) { cons_of_prim(w, q, gamma); return; }
     const double rho = w[0];
     q[0] = rho; q[1] = w[1] * rho; q[2] = w[2] * rho;
-    q[4] = w[4] / (gamma - 1.0) + 0.5 * (rho * norm2sq(w[1], w[2]));
+    q[4] = ddiv(w[4], gamma - 1.0) + 0.5 * (rho * norm2sq(w[1], w[2]));
 }
 
 template <int AX, bool H>
@@ -93,13 +93,13 @@ HD void physical_flux_t(const double* w, double* f, double gamma) {
     f[0] = rho * vn;
     f[1 + n] = rho * (vn * vn) + p;
     f[1 + t] = rho * vn * w[1 + t];
-    f[4] = vn * (0.5 * rho * norm2sq(w[1], w[2]) + (gamma * p) / (gamma - 1.0));
+    f[4] = vn * (0.5 * rho * norm2sq(w[1], w[2]) + ddiv(gamma * p, gamma - 1.0));
 }
 
 template <bool H>
 HD void roe_state_t(const double* first, const double* second, double* out) {
     if (!H) { roe_state(first, second, out); return; }
-    const double s2 = sqrt(second[0]), s1 = sqrt(first[0]);
+    const double s2 = dsqrt(second[0]), s1 = dsqrt(first[0]);
     const double den = s2 + s1;
     out[0] = s2 * s1;
     out[1] = sdiv(first[1] * s1 + second[1] * s2, den);
@@ -119,28 +119,28 @@ HD void mean_state_t(const double* a, const double* b, double* out) {
 // reference feeds unphysical reconstructed states (negative pressure) to np.linalg.eigvals as they are; a root
 // x < 0 then gives the complex pair v +- i sqrt(-x) of modulus sqrt(v^2 - x), which is what np.abs returns
 // (fv.py:157-162), so those branches are kept.
-HD double wave_modulus(double vn, double x) { return x >= 0.0 ? vn + sqrt(x) : sqrt(vn * vn + (-x)); }
+HD double wave_modulus(double vn, double x) { return x >= 0.0 ? vn + dsqrt(x) : dsqrt(vn * vn + (-x)); }
 
 template <int AX>
 HD double spectral_radius(const double* w, double gamma) {
     const double rho = w[0];
-    const double a2 = gamma * w[4] / rho;
-    const double b2 = ((w[5] * w[5] + w[6] * w[6]) + w[7] * w[7]) / rho;
-    const double bn2 = w[5 + AX] * w[5 + AX] / rho;
+    const double a2 = ddiv(gamma * w[4], rho);
+    const double b2 = ddiv((w[5] * w[5] + w[6] * w[6]) + w[7] * w[7], rho);
+    const double bn2 = ddiv(w[5 + AX] * w[5 + AX], rho);
     const double s = a2 + b2;
     const double disc = s * s - 4.0 * (a2 * bn2);
     const double vn = fabs(w[1 + AX]);
     if (disc >= 0.0) {
-        const double root = sqrt(disc);
+        const double root = dsqrt(disc);
         const double cf2 = 0.5 * (s + root), cs2 = 0.5 * (s - root);
-        if (cs2 >= 0.0 && bn2 >= 0.0) return vn + sqrt(cf2);
+        if (cs2 >= 0.0 && bn2 >= 0.0) return vn + dsqrt(cf2);
         return npmax(npmax(wave_modulus(vn, cf2), wave_modulus(vn, cs2)), wave_modulus(vn, bn2));
     }
     if (disc < 0.0) {   // complex conjugate roots x = p +- iq (needs rho < 0)
-        const double p = 0.5 * s, q = 0.5 * sqrt(-disc);
-        const double m = sqrt(p * p + q * q);
-        const double al = sqrt(0.5 * (m + p)), be = sqrt(0.5 * (m - p));
-        return npmax(sqrt((vn + al) * (vn + al) + be * be), wave_modulus(vn, bn2));
+        const double p = 0.5 * s, q = 0.5 * dsqrt(-disc);
+        const double m = dsqrt(p * p + q * q);
+        const double al = dsqrt(0.5 * (m + p)), be = dsqrt(0.5 * (m - p));
+        return npmax(dsqrt((vn + al) * (vn + al) + be * be), wave_modulus(vn, bn2));
     }
     return disc;        // NaN
 }
@@ -149,10 +149,10 @@ HD double spectral_radius(const double* w, double gamma) {
 template <int AX, bool H>
 HD double spectral_radius_t(const double* w, double gamma) {
     if (!H) return spectral_radius<AX>(w, gamma);
-    const double a2 = gamma * w[4] / w[0];
+    const double a2 = ddiv(gamma * w[4], w[0]);
     const double vn = fabs(w[1 + AX]);
-    if (a2 >= 0.0) return vn + sqrt(a2);
-    if (a2 < 0.0) return npmax(vn, sqrt(vn * vn + (-a2)));
+    if (a2 >= 0.0) return vn + dsqrt(a2);
+    if (a2 < 0.0) return npmax(vn, dsqrt(vn * vn + (-a2)));
     return a2;          // NaN
 }
 

@@ -23,12 +23,12 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
     constexpr int NV = VarSet<H>::N;
     const double rL = wm[0], uL = wm[1 + SAX], pL = wm[4];
     const double rR = wp[0], uR = wp[1 + SAX], pR = wp[4];
-    const double cL = sqrt(gamma * sdiv(pL, rL)), cR = sqrt(gamma * sdiv(pR, rR));
-    const double sqL = sqrt(rL), sqR = sqrt(rR);
+    const double cL = dsqrt(gamma * sdiv(pL, rL)), cR = dsqrt(gamma * sdiv(pR, rR));
+    const double sqL = dsqrt(rL), sqR = dsqrt(rR);
     const double u_roe = sdiv(uL * sqL + uR * sqR, sqL + sqR);
     const double c2_roe = sdiv(sqL * (cL * cL) + sqR * (cR * cR), sqL + sqR) + 0.5 * sq(uR - uL) * sdiv(sqL * sqR, sq(sqL + sqR));
-    double sL = npmin(uL - cL, u_roe - sqrt(c2_roe));
-    double sR = npmax(uR + cR, u_roe + sqrt(c2_roe));
+    double sL = npmin(uL - cL, u_roe - dsqrt(c2_roe));
+    double sR = npmax(uR + cR, u_roe + dsqrt(c2_roe));
     const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR), rL * (sL - uL) - rR * (sR - uR));
     if (low_mach) {   // solvers.py:118-122
         const double mach = npmax(fabs(sdiv(uL, cL)), fabs(sdiv(uR, cR)));
@@ -69,11 +69,11 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
 
 HD double hlld_fast_speed(const double* w, double gamma) {   // solvers.py:144-153: B[...,0] whatever the axis
     const double rho = w[0];
-    const double a = sqrt(sdiv(gamma * w[4], rho));
-    const double sr = sqrt(rho);
+    const double a = dsqrt(sdiv(gamma * w[4], rho));
+    const double sr = dsqrt(rho);
     const double b = sdiv(norm3(w[5], w[6], w[7]), sr);
     const double bx = sdiv(w[5], sr);
-    return sqrt(0.5 * (a * a + b * b + sqrt(sq(a * a + b * b) - (4.0 * (a * a) * (bx * bx)))));
+    return dsqrt(0.5 * (a * a + b * b + dsqrt(sq(a * a + b * b) - (4.0 * (a * a) * (bx * bx)))));
 }
 
 // bn_cell = normal field of the padded *cell* average on the right of the interface, wS[bc(j)][5+SAX] (solvers.py:168)
@@ -91,7 +91,7 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
     const double den = rL * (sL - uL) - rR * (sR - uR);
     const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR) + 0.5 * b2R - 0.5 * b2L, den);
     const double rLs = rL * sdiv(sL - uL, sL - sM), rRs = rR * sdiv(sR - uR, sR - sM);
-    const double sLs = sM - sdiv(wm[5 + SAX], sqrt(rLs)), sRs = sM - sdiv(wp[5 + SAX], sqrt(rRs));
+    const double sLs = sM - sdiv(wm[5 + SAX], dsqrt(rLs)), sRs = sM - sdiv(wp[5 + SAX], dsqrt(rRs));
     const double p_star = sdiv(rL * (pR + 0.5 * b2R) * (sL - uL) - rR * (pL + 0.5 * b2L) * (sR - uR) + rR * rL * (sL - uL) * (sR - uR), den);
 
     const bool m1 = (sL <= 0.0) && (0.0 < sLs);
@@ -150,11 +150,11 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
         return;
     }
     const double sgn = npsign(Bn);
-    const double sqL = sqrt(rLs), sqR = sqrt(rRs);
+    const double sqL = dsqrt(rLs), sqR = dsqrt(rRs);
     const double sden = sqL + sqR;
     const double v1ss = sdiv(v1Rs * sqR + v1Ls * sqL + sgn * (B1Ls - B1Rs), sden);
     const double v2ss = sdiv(v2Rs * sqR + v2Ls * sqL + sgn * (B2Ls - B2Rs), sden);
-    const double srr = sqrt(rRs * rLs);
+    const double srr = dsqrt(rRs * rLs);
     const double B1ss = sdiv(B1Ls * sqR + B1Rs * sqL + sgn * (v1Ls - v1Rs) * srr, sden);
     const double B2ss = sdiv(B2Ls * sqR + B2Rs * sqL + sgn * (v2Ls - v2Rs) * srr, sden);
     const double* qs = (sel == 2) ? qLs : qRs;
@@ -169,7 +169,7 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
     qss[5 + t2] = B2ss;
     const double mbs = (sel == 2) ? mbLs : mbRs;
     const double mbss = (qss[1] * qss[5] + qss[2] * qss[6]) + qss[3] * qss[7];
-    qss[4] = qs[4] - sqrt(rs) * sgn * (mbs - mbss);
+    qss[4] = qs[4] - dsqrt(rs) * sgn * (mbs - mbss);
     if (sel == 2) {
 #pragma unroll
         for (int v = 0; v < NVAR; ++v) out[v] = fm[v] + (qss[v] - qLs[v]) * sLs;   // Q4: built on the minus flux

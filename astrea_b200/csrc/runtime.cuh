@@ -53,35 +53,24 @@ struct DeviceExec {
         const double own = get(tid);
         return __shfl_sync(0xffffffffu, own, ((tid & 31) + delta) & 31);
     }
-    // Block-wide max of a non-negative per-thread value -> atomicMax on the bit pattern of *dst; ``bad``
-    // (non-finite seen) sets *flag to the bit pattern of 1.0.  Call from block scope (not inside a phase): get(tid, val, bad).
+    // Max of a non-negative, finite per-thread value -> atomicMax on the bit pattern of *dst (for such values the
+    // bit pattern orders like the value); ``bad`` (non-finite seen) sets *flag to the bit pattern of 1.0.
+    // Warp scope: two 32-bit REDUX steps (high word, then the low words of the lanes that hold the maximal high
+    // word) and one vote; lane 0 touches memory only when its warp raises the running maximum.  No block barrier.
     template <class G>
-    __device__ void publish_max(G&& get, unsigned long long* dst, unsigned long long* flag) {
-        __shared__ double red[32];
-        __shared__ int redbad[32];
+    __device__ __forceinline__ void publish_max(G&& get, unsigned long long* dst, unsigned long long* flag) {
         double val = 0.0;
         bool bad = false;
         get((int)threadIdx.x, val, bad);
-        for (int o = 16; o > 0; o >>= 1) {
-            val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
-            bad = bad | (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
+        const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        const bool any_bad = __any_sync(0xffffffffu, bad) != 0;
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned long long bits = ((unsigned long long)mhi << 32) | mlo;
+            if (bits > *(volatile unsigned long long*)dst) atomicMax(dst, bits);
+            if (any_bad) atomicMax(flag, 0x3FF0000000000000ull);      // bit pattern of 1.0: the flag is all-reduced (MAX) as a double
         }
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-        if (lane == 0) { red[warp] = val; redbad[warp] = bad; }
-        __syncthreads();
-        if (warp == 0) {
-            val = lane < nw ? red[lane] : 0.0;
-            bad = lane < nw ? (bool)redbad[lane] : false;
-            for (int o = 16; o > 0; o >>= 1) {
-                val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
-                bad = bad | (bool)__shfl_xor_sync(0xffffffffu, (int)bad, o);
-            }
-            if (lane == 0) {
-                atomicMax(dst, (unsigned long long)__double_as_longlong(val));
-                if (bad) atomicMax(flag, 0x3FF0000000000000ull);      // bit pattern of 1.0: the flag is all-reduced (MAX) as a double
-            }
-        }
-        __syncthreads();
     }
     // Three running minima (64-bit keys) of per-thread values -> atomicMin on dst[0..2]; warp shuffle first.
     template <class G>

@@ -412,7 +412,7 @@ struct FluxStage {
         auto dissipation = [&](const double* a) -> double {
             const double lam = spectral_radius_t<AX, HYDRO>(a, gamma);
             if (!LW) return lam;
-            const double u = a[1 + AX], c = sqrt(gamma * a[4] / a[0]);
+            const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0]));
             const double second = lw_rank == 0 ? u - c : (lw_rank == 1 ? 0.0 : u);
             return sdiv(second * second, lam);
         };
@@ -446,7 +446,7 @@ struct FluxStage {
                 if (lane_id < H || lane_id >= 32 - H || t < 0 || t >= p.nt || j < first || j > last) return;
                 double a[NVAR];
                 state_at(j, t, a);
-                const double u = a[1 + AX], c = sqrt(gamma * a[4] / a[0]);
+                const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0]));
                 const double col[3] = {u - c, u, u + c};
                 // padded rows this entry appears in
                 int64_t rows[3] = {PCM ? j + 1 : j, -1, -1};
