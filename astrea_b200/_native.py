@@ -79,6 +79,7 @@ _SIGNATURES = {
     "astrea_sync": (C.c_int, [C.c_void_p]),
     "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
     "astrea_fp64_probe": (C.c_int, [C.c_void_p, _PD]),
+    "astrea_arith_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "astrea_launch_count": (C.c_int64, [C.c_void_p]),
     "astrea_save_state": (C.c_int, [C.c_void_p]),
     "astrea_restore_state": (C.c_int, [C.c_void_p]),
@@ -264,6 +265,12 @@ class Context:
         t = C.c_double()
         self._check(self.lib.astrea_fp64_probe(self._h, C.byref(t)))
         return t.value
+
+    def arith_check(self, samples=1 << 24, seed=1):
+        """(accepted, wrong, declined) of the branch-free division / square root against the IEEE routines."""
+        counts = (C.c_uint64 * 3)()
+        self._check(self.lib.astrea_arith_check(self._h, samples, seed, counts))
+        return int(counts[0]), int(counts[1]), int(counts[2])
 
     def sync(self):
         self._check(self.lib.astrea_sync(self._h))

@@ -893,6 +893,25 @@ int astrea_fp64_probe(astrea_ctx* c, double* tflops) {
     return 0;
 }
 
+int astrea_arith_check(astrea_ctx* c, int64_t samples, uint64_t seed, uint64_t* counts) {
+    if (!c || !counts || samples < 1) return fail(c, ASTREA_E_ARG, "astrea_arith_check: bad argument");
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_arith_check: a step is in flight");
+    unsigned long long* dev = (unsigned long long*)dev_alloc(3 * sizeof(unsigned long long));
+    if (!dev) return fail(c, ASTREA_E_CUDA, "astrea_arith_check: allocation failed");
+    const int threads = 256, per_thread = 256;
+    const int blocks = (int)((samples + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread));
+    int e = dev_zero(dev, 3 * sizeof(unsigned long long), c->st);
+    ArithCheckParams p{dev, (unsigned long long)seed, per_thread};
+    if (!e) e = launch<ArithCheckKernel>(p, blocks, 1, threads, 0, c->st);
+    unsigned long long host[3] = {0, 0, 0};
+    if (!e) e = copy_d2h(host, dev, sizeof(host), c->st);
+    if (!e) e = stream_sync(c->st);
+    dev_free(dev);
+    if (e) return fail(c, ASTREA_E_CUDA, "astrea_arith_check: launch failed");
+    for (int k = 0; k < 3; ++k) counts[k] = host[k];
+    return 0;
+}
+
 int astrea_program_length(const astrea_ctx* c) { return c ? (int)c->prog.size() : ASTREA_E_ARG; }
 
 int astrea_instr_is_operator(const astrea_ctx* c, int i) {

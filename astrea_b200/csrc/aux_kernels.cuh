@@ -262,11 +262,32 @@ struct UpdateKernel {
     using Params = UpdateParams;
     static constexpr int MAX_THREADS = 256;
     static constexpr int TILE = 32;
-    static constexpr int VG = 4;                          // variables per pass through the tile (a hydro state is one pass)
+#ifndef ASTREA_UPDATE_MIN_BLOCKS
+#define ASTREA_UPDATE_MIN_BLOCKS 4
+#endif
+    static constexpr int MIN_BLOCKS = ASTREA_UPDATE_MIN_BLOCKS;   // 64 registers: 1024 threads per SM keep enough loads in flight
+#ifndef ASTREA_UPDATE_VG
+#define ASTREA_UPDATE_VG 4
+#endif
+    static constexpr int VG = ASTREA_UPDATE_VG;           // variables per pass through the tile (4: a hydro state is one pass)
     static constexpr int ROWS = TILE * TILE / MAX_THREADS; // tile rows per thread
     static size_t smem_bytes() { return sizeof(double) * VG * TILE * (TILE + 1); }
+    // The flux differences are divided by dx with the Fast guard first (one shared reciprocal); a block that met a
+    // numerator outside Fast's range repeats its tile with Exact (common.cuh).
     template <class Ex>
     static HD void block(const Params& pp, int bx, int by, Ex& ex) {
+#ifdef ASTREA_DEVICE_BUILD
+        if (pp.rate.dimension == 2) {
+            Fast fast;
+            body(pp, bx, by, ex, fast);
+            if (!ex.block_any(!fast.ok)) return;
+        }
+#endif
+        HostGuard exact;
+        body(pp, bx, by, ex, exact);
+    }
+    template <class Ex, class G>
+    static HD void body(const Params& pp, int bx, int by, Ex& ex, G& g) {
         const RateParams& p = pp.rate;
         const CombineParams& cb = pp.comb;
         double* tile = ex.smem();
@@ -327,32 +348,31 @@ struct UpdateKernel {
             ex.phase([&](int tid) {     // flux difference of the y sweep, read coalesced along its own columns (= x)
                 const int tx = tid % TILE;
                 const int64_t xc = r0 + tx;
-                double lo[VG][ROWS], hi[VG][ROWS];
 #pragma unroll
-                for (int g = 0; g < VG; ++g) {
-                    const int v = p.vars.v[a0 + g < p.vars.n ? a0 + g : a0];
+                for (int gi = 0; gi < VG; ++gi) {
+                    if (a0 + gi >= p.vars.n) continue;
+                    const int v = p.vars.v[a0 + gi];
+                    double lo[ROWS], hi[ROWS];
 #pragma unroll
                     for (int i = 0; i < ROWS; ++i) {
                         const int ty = tid / TILE + i * (MAX_THREADS / TILE);
                         const int64_t yr = c0 + ty;
-                        const bool ok = yr < p.ncol && xc < p.row_hi && a0 + g < p.vars.n;
+                        const bool ok = yr < p.ncol && xc < p.row_hi;
                         const double* f = p.f1t.at(ok ? yr : 0, v, ok ? xc : 0);
-                        lo[g][i] = ok ? f[0] : 0.0;
-                        hi[g][i] = ok ? f[p.f1t.row_pitch] : 0.0;
+                        lo[i] = f[0];
+                        hi[i] = f[p.f1t.row_pitch];
                     }
-                }
-#pragma unroll
-                for (int g = 0; g < VG; ++g)
 #pragma unroll
                     for (int i = 0; i < ROWS; ++i) {
                         const int ty = tid / TILE + i * (MAX_THREADS / TILE);
-                        tile[(g * TILE + ty) * (TILE + 1) + tx] = (hi[g][i] - lo[g][i]) / p.dx;
+                        tile[(gi * TILE + ty) * (TILE + 1) + tx] = ddiv(hi[i] - lo[i], p.dx, g);
                     }
+                }
             });
             ex.phase([&](int tid) {
                 const int tx = tid % TILE;
                 const int64_t c = c0 + tx;
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < ROWS; ++i) {
                     const int ty = tid / TILE + i * (MAX_THREADS / TILE);
                     const int64_t r = r0 + ty;
@@ -360,30 +380,30 @@ struct UpdateKernel {
                     const int64_t off = r * rp + c;
                     double fl[VG], fh[VG], x[VG][NTERMS];
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) {
-                        if (a0 + g >= p.vars.n) continue;
-                        const int64_t o = off + (int64_t)p.vars.v[a0 + g] * cp;
-                        fl[g] = p.f0.base[o];
-                        fh[g] = p.f0.base[o + rp];
+                    for (int gi = 0; gi < VG; ++gi) {
+                        if (a0 + gi >= p.vars.n) continue;
+                        const int64_t o = off + (int64_t)p.vars.v[a0 + gi] * cp;
+                        fl[gi] = p.f0.base[o];
+                        fh[gi] = p.f0.base[o + rp];
 #pragma unroll
-                        for (int k = 0; k < NTERMS; ++k) x[g][k] = kind[k] == 2 ? 0.0 : cb.term[k].base[o];
+                        for (int k = 0; k < NTERMS; ++k) x[gi][k] = kind[k] == 2 ? 0.0 : cb.term[k].base[o];
                     }
 #pragma unroll
-                    for (int g = 0; g < VG; ++g) {
-                        if (a0 + g >= p.vars.n) continue;
-                        const int v = p.vars.v[a0 + g];
+                    for (int gi = 0; gi < VG; ++gi) {
+                        if (a0 + gi >= p.vars.n) continue;
+                        const int v = p.vars.v[a0 + gi];
                         const int64_t o = off + (int64_t)v * cp;
-                        double total = (fh[g] - fl[g]) / p.dx;
-                        total = total + tile[(g * TILE + tx) * (TILE + 1) + ty];
+                        double total = ddiv(fh[gi] - fl[gi], p.dx, g);
+                        total = total + tile[(gi * TILE + tx) * (TILE + 1) + ty];
                         if (p.emf != nullptr && (v == 5 || v == 6)) {
                             // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
                             const double e0 = p.emf[r * p.ncol + c];
                             if (v == 5) {
                                 const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
-                                total = (p.emf[r * p.ncol + cn] - e0) / p.dx;                 // (-1)^0 dE/dy
+                                total = ddiv(p.emf[r * p.ncol + cn] - e0, p.dx, g);                 // (-1)^0 dE/dy
                             } else {
                                 const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
-                                total = (-1.0 * (p.emf[rn * p.ncol + c] - e0)) / p.dx;        // (-1)^1 dE/dx
+                                total = ddiv(-1.0 * (p.emf[rn * p.ncol + c] - e0), p.dx, g);        // (-1)^1 dE/dx
                             }
                         }
                         const double L = -total;
@@ -392,7 +412,7 @@ struct UpdateKernel {
                         if (!BRACKET) {
 #pragma unroll
                             for (int k = 0; k < NTERMS; ++k) {
-                                const double t = cf[k] * (kind[k] == 2 ? L : x[g][k]);
+                                const double t = cf[k] * (kind[k] == 2 ? L : x[gi][k]);
                                 acc = (k == 0) ? t : acc + t;
                             }
                             if (cb.scale != 1.0) acc = cb.scale * acc;
@@ -401,7 +421,7 @@ struct UpdateKernel {
                             bool fr = true, fl_ = true;
 #pragma unroll
                             for (int k = 0; k < NTERMS; ++k) {
-                                const double t = cf[k] * (kind[k] == 2 ? L : x[g][k]);
+                                const double t = cf[k] * (kind[k] == 2 ? L : x[gi][k]);
                                 if (kind[k]) { rates = fl_ ? t : rates + t; fl_ = false; }
                                 else { regs = fr ? t : regs + t; fr = false; }
                             }
@@ -535,6 +555,77 @@ struct Fp64ProbeKernel {
                 x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
             }
             p.out[(int64_t)bx * NT + tid] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ arithmetic self-check
+// Fast (common.cuh) against the compiler's IEEE division and square root on generated operands.  Operand classes,
+// by the low bits of the sample index: ordinary magnitudes (exponents within +-40 of 1), magnitudes across the
+// whole of Fast's range (+-400), arbitrary bit patterns (subnormals, huge values, Inf, NaN), and hand-picked
+// specials (+-0, +-1, +-Inf, NaN, smallest / largest normals).  counts[0]: operations Fast accepted (ok stayed
+// true); counts[1]: of those, results whose bits differ from IEEE (NaN matches NaN); counts[2]: operations Fast
+// declined.  counts[1] must be 0; counts[0] must cover the ordinary classes.
+struct ArithCheckParams {
+    unsigned long long* counts;
+    unsigned long long seed;
+    int per_thread;
+};
+struct ArithCheckKernel {
+    using Params = ArithCheckParams;
+    static constexpr int MAX_THREADS = 256;
+    static HD unsigned long long mix(unsigned long long z) {
+        z += 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    static HD double operand(unsigned long long bits, int cls) {
+        double v;
+        if (cls == 2) { memcpy(&v, &bits, 8); return v; }
+        if (cls == 3) {
+            const double special[12] = {0.0, -0.0, 1.0, -1.0, INFINITY, -INFINITY, NAN, 2.2250738585072014e-308,
+                                        1.7976931348623157e308, 4.9e-324, 3.0, 0.1};
+            return special[bits % 12];
+        }
+        const int span = cls == 0 ? 40 : 400;
+        const long long e = 1023 + (long long)((bits >> 52) % (2 * span + 1)) - span;
+        const unsigned long long b = (bits & 0x800FFFFFFFFFFFFFull) | ((unsigned long long)e << 52);
+        memcpy(&v, &b, 8);
+        return v;
+    }
+    static HD bool same(double a, double b) {
+        unsigned long long x, y;
+        memcpy(&x, &a, 8);
+        memcpy(&y, &b, 8);
+        return x == y || (a != a && b != b);
+    }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            unsigned long long accepted = 0, wrong = 0, declined = 0;
+            unsigned long long state = p.seed + ((unsigned long long)bx * NT + tid) * 0x632BE59BD9B4E019ull;
+            for (int i = 0; i < p.per_thread; ++i) {
+                const unsigned long long a = mix(state), b = mix(a);
+                state = b;
+                const int cls = (int)(i & 3), cls_y = (cls == 3) ? (int)((i >> 2) & 3) : cls;
+                const double x = operand(a, cls), y = operand(b, cls_y);
+                Exact exact;
+#ifdef ASTREA_DEVICE_BUILD
+                { Fast f; const double r = f.div(x, y); if (f.ok) { ++accepted; wrong += same(r, exact.div(x, y)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.safe_div(x, y); if (f.ok) { ++accepted; wrong += same(r, exact.safe_div(x, y)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.root(x); if (f.ok) { ++accepted; wrong += same(r, exact.root(x)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.root(fabs(y)); if (f.ok) { ++accepted; wrong += same(r, exact.root(fabs(y))) ? 0 : 1; } else ++declined; }
+#else
+                (void)x; (void)y; (void)exact; accepted += 4;
+#endif
+            }
+#ifdef __CUDA_ARCH__
+            atomicAdd(p.counts + 0, accepted); atomicAdd(p.counts + 1, wrong); atomicAdd(p.counts + 2, declined);
+#else
+            p.counts[0] += accepted; p.counts[1] += wrong; p.counts[2] += declined;
+#endif
         });
     }
 };

@@ -17,8 +17,8 @@
 namespace astrea {
 
 // ----------------------------------------------------------------------------------------- slope limiters
-template <class A>
-HD double limited_slope(const A& acc, int64_t i, int limiter) {
+template <class A, class G = Exact>
+HD double limited_slope(const A& acc, int64_t i, int limiter, G&& g = G()) {
     const double c = acc.s(i);
     const double a = c - acc.s(acc.b(i - 1));
     const double b = acc.s(acc.b(i + 1)) - c;
@@ -26,19 +26,19 @@ HD double limited_slope(const A& acc, int64_t i, int limiter) {
         if (a * b > 0.0) return (fabs(a) < fabs(b)) ? a : b;
         return 0.0;
     }
-    const double r = sdiv(a, b);
+    const double r = sdiv(a, b, g);
     switch (limiter) {
-        case LIM_VANLEER: return (r + fabs(r)) / (1.0 + fabs(r)) * b;
-        case LIM_OSPRE: return 1.5 * ((r * r + r) / (r * r + r + 1.0)) * b;
-        case LIM_VANALBADA: return (r * r + r) / (r * r + 1.0) * b;
-        case LIM_KOREN: return npmax(0.0, npmin(npmin(2.0 * r, (2.0 + r) / 3.0), 2.0)) * b;
+        case LIM_VANLEER: return ddiv(r + fabs(r), 1.0 + fabs(r), g) * b;
+        case LIM_OSPRE: return 1.5 * ddiv(r * r + r, r * r + r + 1.0, g) * b;
+        case LIM_VANALBADA: return ddiv(r * r + r, r * r + 1.0, g) * b;
+        case LIM_KOREN: return npmax(0.0, npmin(npmin(2.0 * r, ddiv(2.0 + r, 3.0, g)), 2.0)) * b;
         default: return npmax(0.0, npmax(npmin(2.0 * r, 1.0), npmin(r, 2.0))) * b;   // superbee
     }
 }
 
-template <class A>
-HD void cell_faces_plm(const A& acc, int64_t i, int limiter, double& wL, double& wR) {
-    const double half = 0.5 * limited_slope(acc, i, limiter);
+template <class A, class G = Exact>
+HD void cell_faces_plm(const A& acc, int64_t i, int limiter, double& wL, double& wR, G&& g = G()) {
+    const double half = 0.5 * limited_slope(acc, i, limiter, g);
     const double c = acc.s(i);
     wL = c - half;
     wR = c + half;
@@ -64,8 +64,9 @@ HD double ppm_d3(const A& acc, int64_t k) {    // limiters.py:96 at (mapped) cel
 // third differences at i-2, i-1, i, i+2 (limiters.py:126-129 really skips i+1).
 // The reference's grid-wide ``if cell_extrema.any()`` needs no reduction: when no extremum exists anywhere its
 // else-branch produces the same numbers as the if-branch, so the if-branch is always taken here.
+template <class G = Exact>
 HD void ppm_mc_limit(double c, double m1, double p1, double m2, double p2, double faceL, double faceR, double d2c_m1, double d2c,
-                     double d2c_p1, double d3_m2, double d3_m1, double d3, double d3_p2, double& wL, double& wR) {
+                     double d2c_p1, double d3_m2, double d3_m1, double d3, double d3_p2, double& wL, double& wR, G&& g = G()) {
     const double C = 5.0 / 4.0;
     const double dwm = c - faceL, dwp = faceR - c;
     const double d2f = 6.0 * (faceL - 2.0 * c + faceR);
@@ -73,7 +74,7 @@ HD void ppm_mc_limit(double c, double m1, double p1, double m2, double p2, doubl
     double d2lim = 0.0;
     if (extremum) d2lim = npsign(d2c) * npmin(npmin(fabs(d2f), C * fabs(d2c)), npmin(C * fabs(d2c_p1), C * fabs(d2c_m1)));
     const double scale = npmax(fabs(c), npmax(npmax(fabs(m1), fabs(p1)), npmax(fabs(m2), fabs(p2))));
-    const double rho = (fabs(d2f) > 1e-12 * scale) ? sdiv(d2lim, d2f) : 0.0;
+    const double rho = (fabs(d2f) > 1e-12 * scale) ? sdiv(d2lim, d2f, g) : 0.0;
     const double d3min = npmin(npmin(d3_m1, d3), npmin(d3_m2, d3_p2));
     const double d3max = npmax(npmax(d3_m1, d3), npmax(d3_m2, d3_p2));
     const bool act = (rho < (1.0 - 1e-12)) || (0.1 * npmax(fabs(d3max), fabs(d3min)) <= (d3max - d3min));
@@ -90,8 +91,8 @@ HD void ppm_mc_limit(double c, double m1, double p1, double m2, double p2, doubl
 }
 
 // Generic form over an accessor (any boundary map).  ``wF`` returns the face value kept for constrained transport (ppm.py:101).
-template <class A>
-HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, double& wF) {
+template <class A, class G = Exact>
+HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, double& wF, G&& g = G()) {
     const double c = acc.s(i);
     const double m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
     const double faceR = 7.0 / 12.0 * (c + p1) - 1.0 / 12.0 * (m1 + p2);
@@ -101,7 +102,7 @@ HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, doubl
     const double d2c_m1 = ppm_d2c(acc, acc.b(i - 1)), d2c_p1 = ppm_d2c(acc, acc.b(i + 1));
     const double d3 = d2c_p1 - d2c;
     const double d3_m1 = ppm_d3(acc, acc.b(i - 1)), d3_m2 = ppm_d3(acc, acc.b(i - 2)), d3_p2 = ppm_d3(acc, acc.b(i + 2));
-    ppm_mc_limit(c, m1, p1, m2, p2, faceL, faceR, d2c_m1, d2c, d2c_p1, d3_m2, d3_m1, d3, d3_p2, wL, wR);
+    ppm_mc_limit(c, m1, p1, m2, p2, faceL, faceR, d2c_m1, d2c, d2c_p1, d3_m2, d3_m1, d3, d3_p2, wL, wR, g);
 }
 
 // Marching form: the second differences d2c(i-2 .. i+3) and the two face values of the previous cell are carried
@@ -112,7 +113,8 @@ struct PpmWindow {
     double d2[6];      // d2c(i-2), .., d2c(i+3)
     double face[2];    // face value at the left / right face of cell i
 };
-HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF) {
+template <class G = Exact>
+HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF, G&& g = G()) {
     auto d2c = [&](int k) { return w[k - 1] - 2.0 * w[k] + w[k + 1]; };
     auto face = [&](int k) { return 7.0 / 12.0 * (w[k] + w[k + 1]) - 1.0 / 12.0 * (w[k - 1] + w[k + 2]); };
     if (fresh) {
@@ -128,7 +130,7 @@ HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, dou
     win.face[1] = face(0);
     wF = win.face[1];
     ppm_mc_limit(w[0], w[-1], w[1], w[-2], w[2], win.face[0], win.face[1], win.d2[1], win.d2[2], win.d2[3],
-                 win.d2[1] - win.d2[0], win.d2[2] - win.d2[1], win.d2[3] - win.d2[2], win.d2[5] - win.d2[4], wL, wR);
+                 win.d2[1] - win.d2[0], win.d2[2] - win.d2[1], win.d2[3] - win.d2[2], win.d2[5] - win.d2[4], wL, wR, g);
 }
 
 // ----------------------------------------------------------------------------------------- PPM, authors 'c' / 'ph'
@@ -219,40 +221,40 @@ HD void cell_faces_ppm_cph(const A& acc, int64_t i, bool ph, PpmSwitches sw, int
 }
 
 // ----------------------------------------------------------------------------------------- WENO
-template <class A>
-HD void cell_faces_weno3(const A& acc, int64_t i, double& wL, double& wR) {
+template <class A, class G = Exact>
+HD void cell_faces_weno3(const A& acc, int64_t i, double& wL, double& wR, G&& g = G()) {
     const double eps = 1e-6, g0 = 1.0 / 3.0, g1 = 2.0 / 3.0;
     const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1));
     const double b0 = sq(c0 - m1), b1 = sq(p1 - c0);
     const double e0 = sq(b0 + eps), e1 = sq(b1 + eps);
-    const double r0 = g0 / e0, r1 = g1 / e1;         // a0(g0), a1(g1)
-    const double l0 = g1 / e0, l1 = g0 / e1;         // a0(g1), a1(g0)
-    wR = (r0 / (r0 + r1)) * (1.5 * c0 - 0.5 * m1) + (r1 / (r0 + r1)) * (0.5 * c0 + 0.5 * p1);
-    wL = (l1 / (l0 + l1)) * (1.5 * c0 - 0.5 * p1) + (l0 / (l0 + l1)) * (0.5 * c0 + 0.5 * m1);
+    const double r0 = ddiv(g0, e0, g), r1 = ddiv(g1, e1, g);         // a0(g0), a1(g1)
+    const double l0 = ddiv(g1, e0, g), l1 = ddiv(g0, e1, g);         // a0(g1), a1(g0)
+    wR = ddiv(r0, r0 + r1, g) * (1.5 * c0 - 0.5 * m1) + ddiv(r1, r0 + r1, g) * (0.5 * c0 + 0.5 * p1);
+    wL = ddiv(l1, l0 + l1, g) * (1.5 * c0 - 0.5 * p1) + ddiv(l0, l0 + l1, g) * (0.5 * c0 + 0.5 * m1);
 }
 
-template <class A>
-HD void cell_faces_weno5(const A& acc, int64_t i, double& wL, double& wR) {
+template <class A, class G = Exact>
+HD void cell_faces_weno5(const A& acc, int64_t i, double& wL, double& wR, G&& g = G()) {
     const double eps = 1e-6, g0 = 1.0 / 10.0, g1 = 3.0 / 5.0, g2 = 3.0 / 10.0;
     const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2));
     const double b0 = 13.0 / 12.0 * sq(m2 - 2.0 * m1 + c0) + 1.0 / 4.0 * sq(m2 - 4.0 * m1 + 3.0 * c0);
     const double b1 = 13.0 / 12.0 * sq(m1 - 2.0 * c0 + p1) + 1.0 / 4.0 * sq(m1 - p1);
     const double b2 = 13.0 / 12.0 * sq(c0 - 2.0 * p1 + p2) + 1.0 / 4.0 * sq(3.0 * c0 - 4.0 * p1 + p2);
     const double e0 = sq(b0 + eps), e1 = sq(b1 + eps), e2 = sq(b2 + eps);
-    const double r0 = g0 / e0, r1 = g1 / e1, r2 = g2 / e2;
+    const double r0 = ddiv(g0, e0, g), r1 = ddiv(g1, e1, g), r2 = ddiv(g2, e2, g);
     const double sR = r0 + r1 + r2;
-    wR = (r0 / sR) * (1.0 / 3.0 * m2 - 7.0 / 6.0 * m1 + 11.0 / 6.0 * c0)
-       + (r1 / sR) * (-1.0 / 6.0 * m1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * p1)
-       + (r2 / sR) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * p1 - 1.0 / 6.0 * p2);
-    const double l0 = g2 / e0, l1 = g1 / e1, l2 = g0 / e2;
+    wR = ddiv(r0, sR, g) * (1.0 / 3.0 * m2 - 7.0 / 6.0 * m1 + 11.0 / 6.0 * c0)
+       + ddiv(r1, sR, g) * (-1.0 / 6.0 * m1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * p1)
+       + ddiv(r2, sR, g) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * p1 - 1.0 / 6.0 * p2);
+    const double l0 = ddiv(g2, e0, g), l1 = ddiv(g1, e1, g), l2 = ddiv(g0, e2, g);
     const double sL = l0 + l1 + l2;
-    wL = (l0 / sL) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * m1 - 1.0 / 6.0 * m2)
-       + (l1 / sL) * (-1.0 / 6.0 * p1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * m1)
-       + (l2 / sL) * (1.0 / 3.0 * p2 - 7.0 / 6.0 * p1 + 11.0 / 6.0 * c0);
+    wL = ddiv(l0, sL, g) * (1.0 / 3.0 * c0 + 5.0 / 6.0 * m1 - 1.0 / 6.0 * m2)
+       + ddiv(l1, sL, g) * (-1.0 / 6.0 * p1 + 5.0 / 6.0 * c0 + 1.0 / 3.0 * m1)
+       + ddiv(l2, sL, g) * (1.0 / 3.0 * p2 - 7.0 / 6.0 * p1 + 11.0 / 6.0 * c0);
 }
 
-template <class A>
-HD void cell_faces_weno7(const A& acc, int64_t i, double& wL, double& wR) {
+template <class A, class G = Exact>
+HD void cell_faces_weno7(const A& acc, int64_t i, double& wL, double& wR, G&& g = G()) {
     const double eps = 1e-6, g0 = 1.0 / 35.0, g1 = 12.0 / 35.0, g2 = 18.0 / 35.0, g3 = 4.0 / 35.0;
     const double c0 = acc.s(i), m1 = acc.s(acc.b(i - 1)), p1 = acc.s(acc.b(i + 1)), m2 = acc.s(acc.b(i - 2)), p2 = acc.s(acc.b(i + 2)),
                  m3 = acc.s(acc.b(i - 3)), p3 = acc.s(acc.b(i + 3));
@@ -265,39 +267,39 @@ HD void cell_faces_weno7(const A& acc, int64_t i, double& wL, double& wR) {
     const double b3 = c0 * (2107.0 * c0 - 9402.0 * p1 + 7042.0 * p2 - 1854.0 * p3) + p1 * (11003.0 * p1 - 17246.0 * p2 + 4642.0 * p3)
                     + p2 * (7043.0 * p2 - 3882.0 * p3) + p3 * (547.0 * p3);
     const double e0 = sq(b0 + eps), e1 = sq(b1 + eps), e2 = sq(b2 + eps), e3 = sq(b3 + eps);
-    const double r0 = g0 / e0, r1 = g1 / e1, r2 = g2 / e2, r3 = g3 / e3;
+    const double r0 = ddiv(g0, e0, g), r1 = ddiv(g1, e1, g), r2 = ddiv(g2, e2, g), r3 = ddiv(g3, e3, g);
     const double sR = r0 + r1 + r2 + r3;
-    wR = (r0 / sR) * (-1.0 / 4.0 * m3 + 13.0 / 12.0 * m2 - 23.0 / 12.0 * m1 + 25.0 / 12.0 * c0)
-       + (r1 / sR) * (1.0 / 12.0 * m2 - 5.0 / 12.0 * m1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * p1)
-       + (r2 / sR) * (-1.0 / 12.0 * m1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * p1 - 1.0 / 12.0 * p2)
-       + (r3 / sR) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * p1 - 5.0 / 12.0 * p2 + 1.0 / 12.0 * p3);
-    const double l0 = g3 / e0, l1 = g2 / e1, l2 = g1 / e2, l3 = g0 / e3;
+    wR = ddiv(r0, sR, g) * (-1.0 / 4.0 * m3 + 13.0 / 12.0 * m2 - 23.0 / 12.0 * m1 + 25.0 / 12.0 * c0)
+       + ddiv(r1, sR, g) * (1.0 / 12.0 * m2 - 5.0 / 12.0 * m1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * p1)
+       + ddiv(r2, sR, g) * (-1.0 / 12.0 * m1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * p1 - 1.0 / 12.0 * p2)
+       + ddiv(r3, sR, g) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * p1 - 5.0 / 12.0 * p2 + 1.0 / 12.0 * p3);
+    const double l0 = ddiv(g3, e0, g), l1 = ddiv(g2, e1, g), l2 = ddiv(g1, e2, g), l3 = ddiv(g0, e3, g);
     const double sL = l0 + l1 + l2 + l3;
-    wL = (l0 / sL) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * m1 - 5.0 / 12.0 * m2 + 1.0 / 12.0 * m3)
-       + (l1 / sL) * (-1.0 / 12.0 * p1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * m1 - 1.0 / 12.0 * m2)
-       + (l2 / sL) * (1.0 / 12.0 * p2 - 5.0 / 12.0 * p1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * m1)
-       + (l3 / sL) * (-1.0 / 4.0 * p3 + 13.0 / 12.0 * p2 - 23.0 / 12.0 * p1 + 25.0 / 12.0 * c0);
+    wL = ddiv(l0, sL, g) * (1.0 / 4.0 * c0 + 13.0 / 12.0 * m1 - 5.0 / 12.0 * m2 + 1.0 / 12.0 * m3)
+       + ddiv(l1, sL, g) * (-1.0 / 12.0 * p1 + 7.0 / 12.0 * c0 + 7.0 / 12.0 * m1 - 1.0 / 12.0 * m2)
+       + ddiv(l2, sL, g) * (1.0 / 12.0 * p2 - 5.0 / 12.0 * p1 + 13.0 / 12.0 * c0 + 1.0 / 4.0 * m1)
+       + ddiv(l3, sL, g) * (-1.0 / 4.0 * p3 + 13.0 / 12.0 * p2 - 23.0 / 12.0 * p1 + 25.0 / 12.0 * c0);
 }
 
 // Dispatch: wL / wR of cell i (mapped index) for one variable; wF = the face state handed to constrained
 // transport (pcm.py:35, plm.py:57, ppm.py:101, weno.py:184).
-template <int SCHEME, class A>
-HD void cell_faces(const A& acc, int64_t i, int limiter, double& wL, double& wR, double& wF) {
+template <int SCHEME, class A, class G = Exact>
+HD void cell_faces(const A& acc, int64_t i, int limiter, double& wL, double& wR, double& wF, G&& g = G()) {
     if (SCHEME == SCH_PCM) {
         wL = wR = wF = acc.s(i);
     } else if (SCHEME == SCH_PLM) {
-        cell_faces_plm(acc, i, limiter, wL, wR);
+        cell_faces_plm(acc, i, limiter, wL, wR, g);
         wF = wR;
     } else if (SCHEME == SCH_PPM) {
-        cell_faces_ppm_mc(acc, i, wL, wR, wF);
+        cell_faces_ppm_mc(acc, i, wL, wR, wF, g);
     } else if (SCHEME == SCH_WENO3) {
-        cell_faces_weno3(acc, i, wL, wR);
+        cell_faces_weno3(acc, i, wL, wR, g);
         wF = wR;
     } else if (SCHEME == SCH_WENO5) {
-        cell_faces_weno5(acc, i, wL, wR);
+        cell_faces_weno5(acc, i, wL, wR, g);
         wF = wR;
     } else {
-        cell_faces_weno7(acc, i, wL, wR);
+        cell_faces_weno7(acc, i, wL, wR, g);
         wF = wR;
     }
 }

@@ -17,26 +17,26 @@ HD void llf_flux_t(double lam, const double* qp, const double* qm, const double*
     for (int k = 0; k < VarSet<H>::N; ++k) { const int v = VarSet<H>::at(k); out[v] = 0.5 * (fm[v] + fp[v]) - 0.5 * ((qp[v] - qm[v]) * lam); }
 }
 
-template <int SAX, bool H = false>
+template <int SAX, bool H = false, class G = Exact>
 HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* wm, const double* qp, const double* qm,
-                  const double* fp, const double* fm, double* out) {
+                  const double* fp, const double* fm, double* out, G&& g = G()) {
     constexpr int NV = VarSet<H>::N;
     const double rL = wm[0], uL = wm[1 + SAX], pL = wm[4];
     const double rR = wp[0], uR = wp[1 + SAX], pR = wp[4];
-    const double cL = dsqrt(gamma * sdiv(pL, rL)), cR = dsqrt(gamma * sdiv(pR, rR));
-    const double sqL = dsqrt(rL), sqR = dsqrt(rR);
-    const double u_roe = sdiv(uL * sqL + uR * sqR, sqL + sqR);
-    const double c2_roe = sdiv(sqL * (cL * cL) + sqR * (cR * cR), sqL + sqR) + 0.5 * sq(uR - uL) * sdiv(sqL * sqR, sq(sqL + sqR));
-    double sL = npmin(uL - cL, u_roe - dsqrt(c2_roe));
-    double sR = npmax(uR + cR, u_roe + dsqrt(c2_roe));
-    const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR), rL * (sL - uL) - rR * (sR - uR));
+    const double cL = dsqrt(gamma * sdiv(pL, rL, g), g), cR = dsqrt(gamma * sdiv(pR, rR, g), g);
+    const double sqL = dsqrt(rL, g), sqR = dsqrt(rR, g);
+    const double u_roe = sdiv(uL * sqL + uR * sqR, sqL + sqR, g);
+    const double c2_roe = sdiv(sqL * (cL * cL) + sqR * (cR * cR), sqL + sqR, g) + 0.5 * sq(uR - uL) * sdiv(sqL * sqR, sq(sqL + sqR), g);
+    double sL = npmin(uL - cL, u_roe - dsqrt(c2_roe, g));
+    double sR = npmax(uR + cR, u_roe + dsqrt(c2_roe, g));
+    const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR), rL * (sL - uL) - rR * (sR - uR), g);
     if (low_mach) {   // solvers.py:118-122
-        const double mach = npmax(fabs(sdiv(uL, cL)), fabs(sdiv(uR, cR)));
-        const double phi = sin(0.5 * 3.141592653589793 * npmin(1.0, mach / 0.1));
+        const double mach = npmax(fabs(sdiv(uL, cL, g)), fabs(sdiv(uR, cR, g)));
+        const double phi = sin(0.5 * 3.141592653589793 * npmin(1.0, ddiv(mach, 0.1, g)));
         sL = phi * sL;
         sR = phi * sR;
     }
-    const double kL = sdiv(sL - uL, sL - sM), kR = sdiv(sR - uR, sR - sM);
+    const double kL = sdiv(sL - uL, sL - sM, g), kR = sdiv(sR - uR, sR - sM, g);
     const bool useL = (sL <= 0.0) && (0.0 < sM);
     const bool useR = (sM <= 0.0) && (0.0 <= sR);
     const bool sup = sR < 0.0;
@@ -52,7 +52,7 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
             const int v = VarSet<H>::at(k);
             double qs = qp[v] * kR;
             if (v == 1) qs = rR * kR * sM;
-            if (v == 4) qs = qs + kR * (sM - uR) * (rR * sM + sdiv(pR, sR - uR));
+            if (v == 4) qs = qs + kR * (sM - uR) * (rR * sM + sdiv(pR, sR - uR, g));
             out[v] = fp[v] + (qs - qp[v]) * sR;
         }
         return;
@@ -62,37 +62,39 @@ HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* w
         const int v = VarSet<H>::at(k);
         double qs = qm[v] * kL;
         if (v == 1) qs = rL * kL * sM;
-        if (v == 4) qs = qs + kL * (sM - uL) * (rL * sM + sdiv(pL, sL - uL));
+        if (v == 4) qs = qs + kL * (sM - uL) * (rL * sM + sdiv(pL, sL - uL, g));
         out[v] = fm[v] + (qs - qm[v]) * sL;
     }
 }
 
-HD double hlld_fast_speed(const double* w, double gamma) {   // solvers.py:144-153: B[...,0] whatever the axis
+template <class G = Exact>
+HD double hlld_fast_speed(const double* w, double gamma, G&& g = G()) {   // solvers.py:144-153: B[...,0] whatever the axis
     const double rho = w[0];
-    const double a = dsqrt(sdiv(gamma * w[4], rho));
-    const double sr = dsqrt(rho);
-    const double b = sdiv(norm3(w[5], w[6], w[7]), sr);
-    const double bx = sdiv(w[5], sr);
-    return dsqrt(0.5 * (a * a + b * b + dsqrt(sq(a * a + b * b) - (4.0 * (a * a) * (bx * bx)))));
+    const double a = dsqrt(sdiv(gamma * w[4], rho, g), g);
+    const double sr = dsqrt(rho, g);
+    const double b = sdiv(norm3(w[5], w[6], w[7], g), sr, g);
+    const double bx = sdiv(w[5], sr, g);
+    const double inner = dsqrt(sq(a * a + b * b) - (4.0 * (a * a) * (bx * bx)), g);
+    return dsqrt(0.5 * (a * a + b * b + inner), g);
 }
 
 // bn_cell = normal field of the padded *cell* average on the right of the interface, wS[bc(j)][5+SAX] (solvers.py:168)
-template <int SAX>
+template <int SAX, class G = Exact>
 HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* wm, const double* qp, const double* qm,
-                  const double* fp, const double* fm, double* out) {
+                  const double* fp, const double* fm, double* out, G&& g = G()) {
     constexpr int n = SAX % 3, t1 = (SAX + 1) % 3, t2 = (SAX + 2) % 3;
     const double Bn = bn_cell;
     const double rL = wm[0], pL = wm[4], rR = wp[0], pR = wp[4];
     const double uL = wm[1 + SAX], uR = wp[1 + SAX];
-    const double cfL = hlld_fast_speed(wm, gamma), cfR = hlld_fast_speed(wp, gamma);
+    const double cfL = hlld_fast_speed(wm, gamma, g), cfR = hlld_fast_speed(wp, gamma, g);
     const double sL = npmin(uL, uR) - npmax(cfL, cfR);
     const double sR = npmin(uL, uR) + npmax(cfL, cfR);
-    const double b2L = norm3sq(wm[5], wm[6], wm[7]), b2R = norm3sq(wp[5], wp[6], wp[7]);
+    const double b2L = norm3sq(wm[5], wm[6], wm[7], g), b2R = norm3sq(wp[5], wp[6], wp[7], g);
     const double den = rL * (sL - uL) - rR * (sR - uR);
-    const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR) + 0.5 * b2R - 0.5 * b2L, den);
-    const double rLs = rL * sdiv(sL - uL, sL - sM), rRs = rR * sdiv(sR - uR, sR - sM);
-    const double sLs = sM - sdiv(wm[5 + SAX], dsqrt(rLs)), sRs = sM - sdiv(wp[5 + SAX], dsqrt(rRs));
-    const double p_star = sdiv(rL * (pR + 0.5 * b2R) * (sL - uL) - rR * (pL + 0.5 * b2L) * (sR - uR) + rR * rL * (sL - uL) * (sR - uR), den);
+    const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR) + 0.5 * b2R - 0.5 * b2L, den, g);
+    const double rLs = rL * sdiv(sL - uL, sL - sM, g), rRs = rR * sdiv(sR - uR, sR - sM, g);
+    const double sLs = sM - sdiv(wm[5 + SAX], dsqrt(rLs, g), g), sRs = sM - sdiv(wp[5 + SAX], dsqrt(rRs, g), g);
+    const double p_star = sdiv(rL * (pR + 0.5 * b2R) * (sL - uL) - rR * (pL + 0.5 * b2L) * (sR - uR) + rR * rL * (sL - uL) * (sR - uR), den, g);
 
     const bool m1 = (sL <= 0.0) && (0.0 < sLs);
     const bool m2 = (sLs <= 0.0) && (0.0 < sM);
@@ -117,8 +119,8 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
         return;
     }
     const double dL = rL * (sL - uL) * (sL - sM) - Bn * Bn, dR = rR * (sR - uR) * (sR - sM) - Bn * Bn;
-    const double gL = sdiv(sM - uL, dL), gR = sdiv(sM - uR, dR);
-    const double hL = sdiv(rL * sq(sL - uL) - Bn * Bn, dL), hR = sdiv(rR * sq(sR - uR) - Bn * Bn, dR);
+    const double gL = sdiv(sM - uL, dL, g), gR = sdiv(sM - uR, dR, g);
+    const double hL = sdiv(rL * sq(sL - uL) - Bn * Bn, dL, g), hR = sdiv(rR * sq(sR - uR) - Bn * Bn, dR, g);
     const double v1Ls = wm[1 + t1] - Bn * wm[5 + t1] * gL, v1Rs = wp[1 + t1] - Bn * wp[5 + t1] * gR;
     const double v2Ls = wm[1 + t2] - Bn * wm[5 + t2] * gL, v2Rs = wp[1 + t2] - Bn * wp[5 + t2] * gR;
     const double B1Ls = wm[5 + t1] * hL, B1Rs = wp[5 + t1] * hR;
@@ -136,8 +138,8 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
     const double vbR = (wp[1] * wp[5] + wp[2] * wp[6]) + wp[3] * wp[7];
     const double mbLs = (qLs[1] * qLs[5] + qLs[2] * qLs[6]) + qLs[3] * qLs[7];
     const double mbRs = (qRs[1] * qRs[5] + qRs[2] * qRs[6]) + qRs[3] * qRs[7];
-    qLs[4] = sdiv(qm[4] * (sL - uL) - uL * (pL + 0.5 * b2L) + p_star * sM + Bn * (vbL - mbLs), sL - sM);
-    qRs[4] = sdiv(qp[4] * (sR - uR) - uR * (pR + 0.5 * b2R) + p_star * sM + Bn * (vbR - mbRs), sR - sM);
+    qLs[4] = sdiv(qm[4] * (sL - uL) - uL * (pL + 0.5 * b2L) + p_star * sM + Bn * (vbL - mbLs), sL - sM, g);
+    qRs[4] = sdiv(qp[4] * (sR - uR) - uR * (pR + 0.5 * b2R) + p_star * sM + Bn * (vbR - mbRs), sR - sM, g);
 
     if (sel == 1) {
 #pragma unroll
@@ -150,13 +152,13 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
         return;
     }
     const double sgn = npsign(Bn);
-    const double sqL = dsqrt(rLs), sqR = dsqrt(rRs);
+    const double sqL = dsqrt(rLs, g), sqR = dsqrt(rRs, g);
     const double sden = sqL + sqR;
-    const double v1ss = sdiv(v1Rs * sqR + v1Ls * sqL + sgn * (B1Ls - B1Rs), sden);
-    const double v2ss = sdiv(v2Rs * sqR + v2Ls * sqL + sgn * (B2Ls - B2Rs), sden);
-    const double srr = dsqrt(rRs * rLs);
-    const double B1ss = sdiv(B1Ls * sqR + B1Rs * sqL + sgn * (v1Ls - v1Rs) * srr, sden);
-    const double B2ss = sdiv(B2Ls * sqR + B2Rs * sqL + sgn * (v2Ls - v2Rs) * srr, sden);
+    const double v1ss = sdiv(v1Rs * sqR + v1Ls * sqL + sgn * (B1Ls - B1Rs), sden, g);
+    const double v2ss = sdiv(v2Rs * sqR + v2Ls * sqL + sgn * (B2Ls - B2Rs), sden, g);
+    const double srr = dsqrt(rRs * rLs, g);
+    const double B1ss = sdiv(B1Ls * sqR + B1Rs * sqL + sgn * (v1Ls - v1Rs) * srr, sden, g);
+    const double B2ss = sdiv(B2Ls * sqR + B2Rs * sqL + sgn * (v2Ls - v2Rs) * srr, sden, g);
     const double* qs = (sel == 2) ? qLs : qRs;
     const double rs = (sel == 2) ? rLs : rRs;
     double qss[NVAR];
@@ -169,7 +171,7 @@ HD void hlld_flux(double gamma, double bn_cell, const double* wp, const double* 
     qss[5 + t2] = B2ss;
     const double mbs = (sel == 2) ? mbLs : mbRs;
     const double mbss = (qss[1] * qss[5] + qss[2] * qss[6]) + qss[3] * qss[7];
-    qss[4] = qs[4] - dsqrt(rs) * sgn * (mbs - mbss);
+    qss[4] = qs[4] - dsqrt(rs, g) * sgn * (mbs - mbss);
     if (sel == 2) {
 #pragma unroll
         for (int v = 0; v < NVAR; ++v) out[v] = fm[v] + (qss[v] - qLs[v]) * sLs;   // Q4: built on the minus flux

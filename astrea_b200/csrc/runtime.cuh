@@ -53,6 +53,8 @@ struct DeviceExec {
         const double own = get(tid);
         return __shfl_sync(0xffffffffu, own, ((tid & 31) + delta) & 31);
     }
+    __device__ __forceinline__ bool warp_any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
+    __device__ __forceinline__ bool block_any(bool b) const { return __syncthreads_or(b) != 0; }
     // Max of a non-negative, finite per-thread value -> atomicMax on the bit pattern of *dst (for such values the
     // bit pattern orders like the value); ``bad`` (non-finite seen) sets *flag to the bit pattern of 1.0.
     // Warp scope: two 32-bit REDUX steps (high word, then the low words of the lanes that hold the maximal high

@@ -43,6 +43,16 @@ struct PrimStage {
     static size_t smem_bytes(int high_order) { return high_order ? sizeof(double) * 2 * NVAR * SX * SY : 0; }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
+#ifdef ASTREA_DEVICE_BUILD
+        Fast fast;                                  // see FluxStage::block; here the unit of repetition is the block
+        body(p, bx, by, ex, fast);
+        if (!ex.block_any(!fast.ok)) return;
+#endif
+        HostGuard exact;
+        body(p, bx, by, ex, exact);
+    }
+    template <class Ex, class G>
+    static HD void body(const Params& p, int bx, int by, Ex& ex, G& g) {
         const int64_t c0 = p.c_lo + (int64_t)bx * TX, r0 = p.r_lo + (int64_t)by * TY;
         const double gamma = p.gamma;
         if (!p.high_order) {
@@ -52,7 +62,7 @@ struct PrimStage {
                 double q[NVAR], w[NVAR];
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); q[v] = *p.q.at(r, v, c); }
-                prim_of_cons_t<HYDRO>(q, w, gamma);
+                prim_of_cons_t<HYDRO>(q, w, gamma, g);
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); *p.w.at(r, v, c) = w[v]; }
             });
@@ -67,7 +77,7 @@ struct PrimStage {
                 double q[NVAR], w[NVAR];
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); q[v] = *p.q.at(r, v, c); }
-                prim_of_cons_t<HYDRO>(q, w, gamma);
+                prim_of_cons_t<HYDRO>(q, w, gamma, g);
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); Q[(v * SY + y) * SX + x] = q[v]; W[(v * SY + y) * SX + x] = w[v]; }
             }
@@ -92,7 +102,7 @@ struct PrimStage {
                 qa[v] = a;
                 ws[v] = s;
             }
-            prim_of_cons_t<HYDRO>(qa, w, gamma);
+            prim_of_cons_t<HYDRO>(qa, w, gamma, g);
 #pragma unroll
             for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); *p.w.at(r, v, c) = w[v] + ws[v]; }
         });
@@ -121,6 +131,16 @@ struct PrimBothStage {
     static size_t smem_bytes() { return sizeof(double) * VS::N * (2 * SX * SY + TX * PT); }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
+#ifdef ASTREA_DEVICE_BUILD
+        Fast fast;                                  // see FluxStage::block; here the unit of repetition is the block
+        body(p, bx, by, ex, fast);
+        if (!ex.block_any(!fast.ok)) return;
+#endif
+        HostGuard exact;
+        body(p, bx, by, ex, exact);
+    }
+    template <class Ex, class G>
+    static HD void body(const Params& p, int bx, int by, Ex& ex, G& g) {
         const int64_t c0 = p.c_lo + (int64_t)bx * TX, r0 = p.r_lo + (int64_t)by * TY;
         const double gamma = p.gamma, c24 = 1.0 / 24.0;
         double* Q = ex.smem();                     // [N][SY][SX] conservative averages of the tile + 1 halo
@@ -133,7 +153,7 @@ struct PrimBothStage {
                 double q[NVAR], w[NVAR];
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) q[VS::at(k)] = *p.q.at(r, VS::at(k), c);
-                prim_of_cons_t<HYDRO>(q, w, gamma);
+                prim_of_cons_t<HYDRO>(q, w, gamma, g);
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { Q[(k * SY + y) * SX + x] = q[VS::at(k)]; W[(k * SY + y) * SX + x] = w[VS::at(k)]; }
             }
@@ -164,8 +184,8 @@ struct PrimBothStage {
                         qy[v] = (qc - c24 * dq_c) - c24 * dq_r;       // y frame: axis 0 = y first
                         sy[v] = c24 * dw_c + c24 * dw_r;
                     }
-                    prim_of_cons_t<HYDRO>(qx, wx, gamma);
-                    prim_of_cons_t<HYDRO>(qy, wy, gamma);
+                    prim_of_cons_t<HYDRO>(qx, wx, gamma, g);
+                    prim_of_cons_t<HYDRO>(qy, wy, gamma, g);
 #pragma unroll
                     for (int k = 0; k < VS::N; ++k) { const int v = VS::at(k); wx[v] = wx[v] + sx[v]; wy[v] = wy[v] + sy[v]; }
                 }
@@ -235,10 +255,25 @@ struct ReconStage {
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
+    // The threads are independent; on the device a warp marches with the Fast division first and repeats its
+    // segment with Exact if any lane met an operand Fast does not cover (see FluxStage::block, common.cuh).  The
+    // authors 'c' / 'ph' write grid-wide switches on the way and stay with Exact.
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
+#ifdef ASTREA_DEVICE_BUILD
+        if constexpr (!CPH && SCHEME != SCH_PCM) {
+            Fast fast;
+            march(p, bx, by, ex, fast);
+            if (!ex.warp_any(!fast.ok)) return;
+        }
+#endif
+        HostGuard exact;
+        march(p, bx, by, ex, exact);
+    }
+    template <class Ex, class G>
+    static HD void march(const Params& p, int bx, int by, Ex& ex, G& g) {
         const int NT = ex.nthreads();
-        ex.phase([&](int tid) {
+        ex.wphase([&](int tid) {
             const int64_t t = p.c_lo + (int64_t)bx * NT + tid;
             if (t >= p.c_hi) return;
             const int v = p.vars[by % p.nvar];
@@ -291,13 +326,13 @@ struct ReconStage {
                     fresh = true;
                     if (ig < 0 || ig > p.ns_glob - 1) continue;          // no such cell
                     ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
-                    cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf);
+                    cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
                 } else if constexpr (SCHEME == SCH_PPM) {
-                    cell_faces_ppm_mc_march(r + LO, win, fresh, wl, wr, wf);
+                    cell_faces_ppm_mc_march(r + LO, win, fresh, wl, wr, wf, g);
                     fresh = false;
                 } else {
                     StencilAccessor<LO> acc{r};
-                    cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf);
+                    cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
                 }
                 if (p.cell_aligned) {
                     *p.wp.at(i, v, t) = wl;
@@ -374,18 +409,35 @@ struct FluxStage {
         bool live, bad;
     };
 
+    // The warps of a block are independent (warp phases, warp-scope reduction).  On the device the work is done with
+    // the branch-free Fast division / square root first; a warp in which any lane met an operand outside the range
+    // where that sequence is known to be IEEE (common.cuh) repeats its work with Exact before anything is published.
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        typename Ex::template Local<Tls> tls(ex);
+        const bool search = LW && p.lw_pass == 1;
+#ifdef ASTREA_DEVICE_BUILD
+        if constexpr (!LW) {
+            Fast fast;
+            body(p, bx, by, ex, tls, fast);
+            if (ex.warp_any(!fast.ok)) { Exact exact; body(p, bx, by, ex, tls, exact); }
+        } else
+#endif
+        { HostGuard exact; body(p, bx, by, ex, tls, exact); }
+        if (!search) ex.publish_max([&](int k, double& val, bool& bad) { val = tls[k].lam_max; bad = tls[k].bad; }, p.eigmax_bits, p.flag);
+    }
+
+    template <class Ex, class L, class G>
+    static HD void body(const Params& p, int bx, int by, Ex& ex, L& tls, G& g) {
         const int NT = ex.nthreads();
         const int nwarp = NT / 32;
         const double gamma = p.gamma, c24 = 1.0 / 24.0;
         constexpr bool edge = EDGE;      // the launcher picks the instantiation from cfg.boundary
-        typename Ex::template Local<Tls> tls(ex);
         auto smap = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.s_off, 0, p.ns_glob - 1) - p.s_off : r; };
         auto solve = [&](const Tls& st, const double* wp, const double* wm, const double* qp, const double* qm, const double* fp,
                          const double* fm, double* out) {
-            if (SOLVER == SOL_HLLC) hllc_flux<SAX, HYDRO>(gamma, p.low_mach != 0, wp, wm, qp, qm, fp, fm, out);
-            else if (SOLVER == SOL_HLLD) hlld_flux<SAX>(gamma, st.bn, wp, wm, qp, qm, fp, fm, out);
+            if (SOLVER == SOL_HLLC) hllc_flux<SAX, HYDRO>(gamma, p.low_mach != 0, wp, wm, qp, qm, fp, fm, out, g);
+            else if (SOLVER == SOL_HLLD) hlld_flux<SAX>(gamma, st.bn, wp, wm, qp, qm, fp, fm, out, g);
             else llf_flux_t<HYDRO>(st.lam, qp, qm, fp, fm, out);
         };
         // transverse second difference of a per-thread array member produced in an earlier phase; the neighbour of
@@ -410,11 +462,11 @@ struct FluxStage {
         }
         // LLF: max |eigenvalue|; LW: second^2 / max |eigenvalue| (solvers.py:84-87) of an averaged (or PCM cell) state
         auto dissipation = [&](const double* a) -> double {
-            const double lam = spectral_radius_t<AX, HYDRO>(a, gamma);
+            const double lam = spectral_radius_t<AX, HYDRO>(a, gamma, g);
             if (!LW) return lam;
-            const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0]));
+            const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0], g), g);
             const double second = lw_rank == 0 ? u - c : (lw_rank == 1 ? 0.0 : u);
-            return sdiv(second * second, lam);
+            return sdiv(second * second, lam, g);
         };
         // the state of padded entry `jj` (interface row, or cell row for PCM) at this thread's column (fv.py:157-169)
         auto state_at = [&](int64_t jj, int64_t tc, double* a) {
@@ -426,7 +478,7 @@ struct FluxStage {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); x[v] = *p.wp.at(jj, v, tc); y[v] = *p.wm.at(jj, v, tc); }
-                if (KIND == 1) mean_state_t<HYDRO>(x, y, a); else roe_state_t<HYDRO>(x, y, a);
+                if (KIND == 1) mean_state_t<HYDRO>(x, y, a); else roe_state_t<HYDRO>(x, y, a, g);
             }
         };
         auto speed_at = [&](int64_t jj, int64_t tc) -> double {
@@ -446,7 +498,7 @@ struct FluxStage {
                 if (lane_id < H || lane_id >= 32 - H || t < 0 || t >= p.nt || j < first || j > last) return;
                 double a[NVAR];
                 state_at(j, t, a);
-                const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0]));
+                const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0], g), g);
                 const double col[3] = {u - c, u, u + c};
                 // padded rows this entry appears in
                 int64_t rows[3] = {PCM ? j + 1 : j, -1, -1};
@@ -476,7 +528,8 @@ struct FluxStage {
             st.lam = 0.0; st.bn = 0.0; st.lam_max = 0.0; st.bad = false;
             if (!st.live) return;
             const int64_t j = st.j;
-            const int64_t tc = clamp_index(st.t, -(int64_t)GHOST, p.nt + GHOST - 1);
+            // columns the earlier stages filled: [-H, nt + H); lanes beyond them (last warp of a row) feed nobody
+            const int64_t tc = clamp_index(st.t, -(int64_t)H, p.nt + H - 1);
             if (PCM) {
                 const int64_t rp_ = smap(j), rm_ = smap(j - 1);
 #pragma unroll
@@ -489,11 +542,11 @@ struct FluxStage {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
-                cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma);
-                cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma);
+                cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma, g);
+                cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma, g);
             }
-            physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma);
-            physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma);
+            physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma, g);
+            physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma, g);
             if (SOLVER == SOL_HLLD) st.bn = *p.ws.at(smap(j), 5 + SAX, tc);
             // wave speeds: the per-interface estimate feeds the CFL reduction, LLF also uses it as its dissipation
             const int64_t jg = j + p.s_off;
@@ -501,13 +554,13 @@ struct FluxStage {
             bool counts;
             if (PCM) {
                 // pcm.py:30: Jacobian at the padded cells; interface j sees cells b(j-1) and b(j)
-                lam_here = spectral_radius_t<AX, HYDRO>(st.wp, gamma);
+                lam_here = spectral_radius_t<AX, HYDRO>(st.wp, gamma, g);
                 counts = jg >= 0 && jg < p.ns_glob && j < p.ns;
                 if (LLF) st.lam = npmax(dissipation(st.wm), dissipation(st.wp));
             } else {
                 double a[NVAR];
-                if (KIND == 1) mean_state_t<HYDRO>(st.wp, st.wm, a); else roe_state_t<HYDRO>(st.wp, st.wm, a);
-                lam_here = spectral_radius_t<AX, HYDRO>(a, gamma);
+                if (KIND == 1) mean_state_t<HYDRO>(st.wp, st.wm, a); else roe_state_t<HYDRO>(st.wp, st.wm, a, g);
+                lam_here = spectral_radius_t<AX, HYDRO>(a, gamma, g);
                 counts = jg >= 1 && jg <= p.ns_glob && j >= 1;
                 if (LLF) {
                     // entries j and j+1 of the pad-1 array of interface speeds (solvers.py:73-74)
@@ -527,11 +580,10 @@ struct FluxStage {
                 if (LW && !(st.lam == st.lam)) st.bad = true;
             }
         });
-        ex.publish_max([&](int k, double& val, bool& bad) { val = tls[k].lam_max; bad = tls[k].bad; }, p.eigmax_bits, p.flag);
-
         // B: w - d2_t(w)/24, face conversion of q (fv.py:105-122), Riemann flux of the face averages
         ex.wphase([&](int tid) {
             Tls& st = tls[tid];
+            if (!st.live) return;                 // the interface row of a warp: all of its lanes leave together
             double qx[NVAR];
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
@@ -540,10 +592,10 @@ struct FluxStage {
                 st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], [&](int k) { return tls[k].wm[v]; });
             }
             if (HO) {
-                cons_of_prim_t<HYDRO>(st.xp, qx, gamma);
+                cons_of_prim_t<HYDRO>(st.xp, qx, gamma, g);
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], [&](int k) { return tls[k].qp[v]; }); }
-                cons_of_prim_t<HYDRO>(st.xm, qx, gamma);
+                cons_of_prim_t<HYDRO>(st.xm, qx, gamma, g);
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], [&](int k) { return tls[k].qm[v]; }); }
             } else {
@@ -556,6 +608,7 @@ struct FluxStage {
         // C: face-centred q and physical flux (solvers.py:47-52), Riemann flux of the centred states
         ex.wphase([&](int tid) {
             Tls& st = tls[tid];
+            if (!st.live) return;
             double cqp[NVAR], cqm[NVAR], cfp[NVAR], cfm[NVAR];
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
@@ -570,6 +623,7 @@ struct FluxStage {
         // D: F = F_c - d2_t(F_avg)/24 (fv.py:147-153)
         ex.wphase([&](int tid) {
             Tls& st = tls[tid];
+            if (!st.live) return;
             const int lane_id = tid & 31;
             const bool owned = st.live && lane_id >= H && lane_id < 32 - H && st.t >= 0 && st.t < p.nt;
 #pragma unroll

@@ -168,6 +168,14 @@ int astrea_profile_read(astrea_ctx* ctx, double* ms_by_class, int64_t* launches_
  * roofline report can say how far the fp64-bound stages are from the fp64 peak.  0 in the host-simulated build. */
 int astrea_fp64_probe(astrea_ctx* ctx, double* tflops);
 
+/* Self-check of the device arithmetic (no reference counterpart; the reference's divisions and square roots are
+ * numpy's IEEE ones, fv.py:19-20,37-38).  The kernels evaluate every division and square root with a branch-free
+ * fused-multiply-add sequence ("Fast", csrc/common.cuh) that is IEEE-exact for ordinary operands and hand the
+ * warp / block to the compiler's IEEE routines otherwise.  This call runs Fast against those routines on about
+ * ``samples`` generated operand pairs (4 operations each): counts[0] = operations Fast accepted, counts[1] = accepted
+ * operations whose result differs in any bit from IEEE (must be 0), counts[2] = operations Fast declined. */
+int astrea_arith_check(astrea_ctx* ctx, int64_t samples, uint64_t seed, uint64_t* counts);
+
 /* Number of kernels this library launched on the context's stream since creation (bench.py "gpu_launches"). */
 int64_t astrea_launch_count(const astrea_ctx* ctx);
 /* 1 when built by nvcc for sm_100a, 0 for the host-simulated test build. */

@@ -326,3 +326,22 @@ def test_ppm_authors_colella_and_peterson_hammett(lib, config, dim, solver, bc, 
     got, used, _ = run_native(lib, meta, g0, 2)
     assert np.all(rel_l1(got, want) <= 1e-10), rel_l1(got, want)
     assert np.allclose(used, dts, rtol=1e-13, atol=0)
+
+
+def test_fast_division_and_square_root_are_ieee(lib):
+    """The branch-free division / square root of the kernels (csrc/common.cuh, Fast) against the compiler's IEEE
+    routines on 2^26 generated operand pairs: every operation Fast accepts must give the IEEE bits; the ordinary
+    operand classes (half of the samples) must be accepted."""
+    from astrea_b200 import _native as N
+    from astrea_b200.selectors import make_cfg
+    ctx = N.Context(make_cfg(dimension=1, cells=64, boundary="edge", gamma=1.4, dx=1 / 64, cfl=.5, subgrid="plm", solver="lf",
+                             timestep="ssprk(2,2)"), lib=lib)
+    try:
+        accepted = wrong = declined = 0
+        for seed in (1, 2, 3, 4):
+            a, w, d = ctx.arith_check(1 << 24, seed)
+            accepted += a; wrong += w; declined += d
+    finally:
+        ctx.close()
+    assert wrong == 0, (accepted, wrong, declined)
+    assert accepted > 0.45 * (accepted + declined), (accepted, declined)
