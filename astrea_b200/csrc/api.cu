@@ -450,6 +450,11 @@ RateParams rate_params(astrea_ctx* c) {
     r.f0 = c->d0.plane; r.f1t = c->d1t.plane; r.d0 = c->d0.plane;
     r.nrow = c->nrow; r.ncol = c->ncol; r.dimension = g.dimension; r.emf = g.magnetic_2d ? c->emf : nullptr; r.emf_rows = c->emf_rows;
     r.nx_glob = g.nx_global; r.x_off = g.x_offset; r.dx = g.dx; r.bc = g.boundary;
+    {   // dx = 2^k with 1 / dx representable: the update multiplies instead of dividing (aux_kernels.cuh)
+        int e = 0;
+        const double m = std::frexp(g.dx, &e);
+        r.inv_dx_exact = (m == 0.5 && e > -1000 && e < 1000) ? 1.0 / g.dx : 0.0;
+    }
     r.vars = c->vars();
     r.row_lo = 0; r.row_hi = c->nrow;
     return r;

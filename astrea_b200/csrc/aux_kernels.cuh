@@ -130,6 +130,7 @@ struct RateParams {
     int64_t emf_rows;     // rows of emf that hold data: nrow, or nrow + 1 when the row behind the slab was computed from ghost data
     int64_t nx_glob, x_off;
     double dx;
+    double inv_dx_exact;  // 1 / dx when dx is a power of two (x / dx == x * inv_dx_exact bit for bit), else 0
     int bc;
     VarList vars;
     int64_t row_lo, row_hi;   // half-open range of rows to process (slab hosts update the edge rows first)
@@ -272,22 +273,19 @@ struct UpdateKernel {
     static constexpr int VG = ASTREA_UPDATE_VG;           // variables per pass through the tile (4: a hydro state is one pass)
     static constexpr int ROWS = TILE * TILE / MAX_THREADS; // tile rows per thread
     static size_t smem_bytes() { return sizeof(double) * VG * TILE * (TILE + 1); }
-    // The flux differences are divided by dx with the Fast guard first (one shared reciprocal); a block that met a
-    // numerator outside Fast's range repeats its tile with Exact (common.cuh).
+    // Division by dx: when dx is a power of two (every BASELINE configuration: unit-length boxes with 2^k cells) the
+    // IEEE quotient x / dx equals the product x * (1 / dx) for every x (scaling by a power of two is exact), so the
+    // kernel multiplies; otherwise it divides.  The register update is in place (``out`` is one of the terms), so it
+    // cannot be repeated the way the Fast-guarded kernels are.
+    struct DivideByDx { double dx; HD double operator()(double x) const { return x / dx; } };
+    struct TimesInvDx { double inv; HD double operator()(double x) const { return x * inv; } };
     template <class Ex>
     static HD void block(const Params& pp, int bx, int by, Ex& ex) {
-#ifdef ASTREA_DEVICE_BUILD
-        if (pp.rate.dimension == 2) {
-            Fast fast;
-            body(pp, bx, by, ex, fast);
-            if (!ex.block_any(!fast.ok)) return;
-        }
-#endif
-        HostGuard exact;
-        body(pp, bx, by, ex, exact);
+        if (pp.rate.inv_dx_exact != 0.0) body(pp, bx, by, ex, TimesInvDx{pp.rate.inv_dx_exact});
+        else body(pp, bx, by, ex, DivideByDx{pp.rate.dx});
     }
-    template <class Ex, class G>
-    static HD void body(const Params& pp, int bx, int by, Ex& ex, G& g) {
+    template <class Ex, class D>
+    static HD void body(const Params& pp, int bx, int by, Ex& ex, D over_dx) {
         const RateParams& p = pp.rate;
         const CombineParams& cb = pp.comb;
         double* tile = ex.smem();
@@ -365,7 +363,7 @@ struct UpdateKernel {
 #pragma unroll
                     for (int i = 0; i < ROWS; ++i) {
                         const int ty = tid / TILE + i * (MAX_THREADS / TILE);
-                        tile[(gi * TILE + ty) * (TILE + 1) + tx] = ddiv(hi[i] - lo[i], p.dx, g);
+                        tile[(gi * TILE + ty) * (TILE + 1) + tx] = over_dx(hi[i] - lo[i]);
                     }
                 }
             });
@@ -393,17 +391,17 @@ struct UpdateKernel {
                         if (a0 + gi >= p.vars.n) continue;
                         const int v = p.vars.v[a0 + gi];
                         const int64_t o = off + (int64_t)v * cp;
-                        double total = ddiv(fh[gi] - fl[gi], p.dx, g);
+                        double total = over_dx(fh[gi] - fl[gi]);
                         total = total + tile[(gi * TILE + tx) * (TILE + 1) + ty];
                         if (p.emf != nullptr && (v == 5 || v == 6)) {
                             // diff(pad(E_z)[1:]) (evolvers.py:56-57): the +1 neighbour wraps or clamps
                             const double e0 = p.emf[r * p.ncol + c];
                             if (v == 5) {
                                 const int64_t cn = c + 1 < p.ncol ? c + 1 : (wrap ? 0 : p.ncol - 1);
-                                total = ddiv(p.emf[r * p.ncol + cn] - e0, p.dx, g);                 // (-1)^0 dE/dy
+                                total = over_dx(p.emf[r * p.ncol + cn] - e0);                 // (-1)^0 dE/dy
                             } else {
                                 const int64_t rn = r + 1 < p.emf_rows ? r + 1 : (wrap ? 0 : p.nrow - 1);
-                                total = ddiv(-1.0 * (p.emf[rn * p.ncol + c] - e0), p.dx, g);        // (-1)^1 dE/dx
+                                total = over_dx(-1.0 * (p.emf[rn * p.ncol + c] - e0));        // (-1)^1 dE/dx
                             }
                         }
                         const double L = -total;

@@ -147,6 +147,8 @@ struct HostExec {
     void wphase(F&& f) {
         for (int t = 0; t < nthr; ++t) f(t);
     }
+    bool warp_any(bool b) const { return b; }      // the host simulation runs a block thread by thread: one guard per block
+    bool block_any(bool b) const { return b; }
     template <class G>
     double lane(int tid, int delta, G&& get) {
         return get((tid & ~31) + (((tid & 31) + delta) & 31));

@@ -43,12 +43,12 @@ struct PrimStage {
     static size_t smem_bytes(int high_order) { return high_order ? sizeof(double) * 2 * NVAR * SX * SY : 0; }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
-#ifdef ASTREA_DEVICE_BUILD
-        Fast fast;                                  // see FluxStage::block; here the unit of repetition is the block
-        body(p, bx, by, ex, fast);
-        if (!ex.block_any(!fast.ok)) return;
+#ifdef ASTREA_TWO_PASS
+        FirstGuard first;                           // see FluxStage::block; here the unit of repetition is the block
+        body(p, bx, by, ex, first);
+        if (!ex.block_any(!first.good())) return;
 #endif
-        HostGuard exact;
+        Exact exact;
         body(p, bx, by, ex, exact);
     }
     template <class Ex, class G>
@@ -131,12 +131,12 @@ struct PrimBothStage {
     static size_t smem_bytes() { return sizeof(double) * VS::N * (2 * SX * SY + TX * PT); }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
-#ifdef ASTREA_DEVICE_BUILD
-        Fast fast;                                  // see FluxStage::block; here the unit of repetition is the block
-        body(p, bx, by, ex, fast);
-        if (!ex.block_any(!fast.ok)) return;
+#ifdef ASTREA_TWO_PASS
+        FirstGuard first;                           // see FluxStage::block; here the unit of repetition is the block
+        body(p, bx, by, ex, first);
+        if (!ex.block_any(!first.good())) return;
 #endif
-        HostGuard exact;
+        Exact exact;
         body(p, bx, by, ex, exact);
     }
     template <class Ex, class G>
@@ -260,14 +260,14 @@ struct ReconStage {
     // authors 'c' / 'ph' write grid-wide switches on the way and stay with Exact.
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
-#ifdef ASTREA_DEVICE_BUILD
+#ifdef ASTREA_TWO_PASS
         if constexpr (!CPH && SCHEME != SCH_PCM) {
-            Fast fast;
-            march(p, bx, by, ex, fast);
-            if (!ex.warp_any(!fast.ok)) return;
+            FirstGuard first;
+            march(p, bx, by, ex, first);
+            if (!ex.warp_any(!first.good())) return;
         }
 #endif
-        HostGuard exact;
+        Exact exact;
         march(p, bx, by, ex, exact);
     }
     template <class Ex, class G>
@@ -412,23 +412,27 @@ struct FluxStage {
     // The warps of a block are independent (warp phases, warp-scope reduction).  On the device the work is done with
     // the branch-free Fast division / square root first; a warp in which any lane met an operand outside the range
     // where that sequence is known to be IEEE (common.cuh) repeats its work with Exact before anything is published.
+    // (The audit build of the host simulation runs the same two passes with the counting Audit guard.)
+    struct Pub { double lam_max; bool bad; };
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
-        typename Ex::template Local<Tls> tls(ex);
+        typename Ex::template Local<Pub> pub(ex);
         const bool search = LW && p.lw_pass == 1;
-#ifdef ASTREA_DEVICE_BUILD
+        bool done = false;
+#ifdef ASTREA_TWO_PASS
         if constexpr (!LW) {
-            Fast fast;
-            body(p, bx, by, ex, tls, fast);
-            if (ex.warp_any(!fast.ok)) { Exact exact; body(p, bx, by, ex, tls, exact); }
-        } else
+            FirstGuard first;
+            body(p, bx, by, ex, pub, first);
+            done = !ex.warp_any(!first.good());
+        }
 #endif
-        { HostGuard exact; body(p, bx, by, ex, tls, exact); }
-        if (!search) ex.publish_max([&](int k, double& val, bool& bad) { val = tls[k].lam_max; bad = tls[k].bad; }, p.eigmax_bits, p.flag);
+        if (!done) { Exact exact; body(p, bx, by, ex, pub, exact); }
+        if (!search) ex.publish_max([&](int k, double& val, bool& bad) { val = pub[k].lam_max; bad = pub[k].bad; }, p.eigmax_bits, p.flag);
     }
 
     template <class Ex, class L, class G>
-    static HD void body(const Params& p, int bx, int by, Ex& ex, L& tls, G& g) {
+    static HD void body(const Params& p, int bx, int by, Ex& ex, L& pub, G& g) {
+        typename Ex::template Local<Tls> tls(ex);
         const int NT = ex.nthreads();
         const int nwarp = NT / 32;
         const double gamma = p.gamma, c24 = 1.0 / 24.0;
@@ -526,6 +530,7 @@ struct FluxStage {
             st.t = (int64_t)bx * OWN - H + lane_id;
             st.live = st.j <= p.ns;
             st.lam = 0.0; st.bn = 0.0; st.lam_max = 0.0; st.bad = false;
+            pub[tid].lam_max = 0.0; pub[tid].bad = false;
             if (!st.live) return;
             const int64_t j = st.j;
             // columns the earlier stages filled: [-H, nt + H); lanes beyond them (last warp of a row) feed nobody
@@ -579,6 +584,7 @@ struct FluxStage {
                 // (complex eigenvalues); the device path does not follow it there and reports the step as non-finite
                 if (LW && !(st.lam == st.lam)) st.bad = true;
             }
+            pub[tid].lam_max = st.lam_max; pub[tid].bad = st.bad;
         });
         // B: w - d2_t(w)/24, face conversion of q (fv.py:105-122), Riemann flux of the face averages
         ex.wphase([&](int tid) {
