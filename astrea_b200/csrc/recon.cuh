@@ -107,30 +107,34 @@ HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, doubl
 
 // Marching form: the second differences d2c(i-2 .. i+3) and the two face values of the previous cell are carried
 // from one cell to the next (identical expressions, identical bits), so each cell evaluates one new second
-// difference and one new face value instead of six and two.  ``w`` points at the stencil value of the cell itself
-// (w[-3] .. w[4] valid, identity boundary map); ``fresh``: nothing to carry yet.
+// difference and one new face value instead of six and two.  ``acc.s(k)`` is the stencil value at offset k from the
+// cell (k = -3 .. 4, identity boundary map); ``fresh``: nothing to carry yet.
+// The carried values live in circular buffers indexed with the compile-time rotation ROT (the march is unrolled by
+// the window length, stages2d.cuh): entry k of the logical window is slot (k + ROT) mod 8, so moving on by one
+// cell moves no register.
 struct PpmWindow {
-    double d2[6];      // d2c(i-2), .., d2c(i+3)
-    double face[2];    // face value at the left / right face of cell i
+    double d2[8];      // logical d2c(i-2), .., d2c(i+3) in slots (0 .. 5 + ROT) mod 8
+    double face[2];    // face value at the left / right face of cell i in slots (0 / 1 + ROT) mod 2
 };
-template <class G = Exact>
-HD void cell_faces_ppm_mc_march(const double* w, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF, G&& g = G()) {
-    auto d2c = [&](int k) { return w[k - 1] - 2.0 * w[k] + w[k + 1]; };
-    auto face = [&](int k) { return 7.0 / 12.0 * (w[k] + w[k + 1]) - 1.0 / 12.0 * (w[k - 1] + w[k + 2]); };
+template <int ROT, class A, class G = Exact>
+HD void cell_faces_ppm_mc_march(const A& acc, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF, G&& g = G()) {
+    auto d2c = [&](int k) { return acc.s(k - 1) - 2.0 * acc.s(k) + acc.s(k + 1); };
+    auto face = [&](int k) { return 7.0 / 12.0 * (acc.s(k) + acc.s(k + 1)) - 1.0 / 12.0 * (acc.s(k - 1) + acc.s(k + 2)); };
+    constexpr int R = ROT % 8;
+    double* d2 = win.d2;
     if (fresh) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) win.d2[k] = d2c(k - 2);
-        win.face[0] = face(-1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) win.d2[k] = win.d2[k + 1];
-        win.face[0] = win.face[1];
+        for (int k = 0; k < 5; ++k) d2[(k + R) % 8] = d2c(k - 2);
+        win.face[R % 2] = face(-1);
     }
-    win.d2[5] = d2c(3);
-    win.face[1] = face(0);
-    wF = win.face[1];
-    ppm_mc_limit(w[0], w[-1], w[1], w[-2], w[2], win.face[0], win.face[1], win.d2[1], win.d2[2], win.d2[3],
-                 win.d2[1] - win.d2[0], win.d2[2] - win.d2[1], win.d2[3] - win.d2[2], win.d2[5] - win.d2[4], wL, wR, g);
+    d2[(5 + R) % 8] = d2c(3);
+    win.face[(1 + R) % 2] = face(0);
+    const double f0 = win.face[R % 2], f1 = win.face[(1 + R) % 2];
+    wF = f1;
+    const double a0 = d2[R % 8], a1 = d2[(1 + R) % 8], a2 = d2[(2 + R) % 8], a3 = d2[(3 + R) % 8], a4 = d2[(4 + R) % 8],
+                 a5 = d2[(5 + R) % 8];
+    ppm_mc_limit(acc.s(0), acc.s(-1), acc.s(1), acc.s(-2), acc.s(2), f0, f1, a1, a2, a3,
+                 a1 - a0, a2 - a1, a3 - a2, a5 - a4, wL, wR, g);
 }
 
 // ----------------------------------------------------------------------------------------- PPM, authors 'c' / 'ph'

@@ -19,6 +19,7 @@
 // 64 B (q) + 64 B (wS) + 64 B + 128 B (w+-) + 128 B + 64 B (F); see DESIGN.md for the roofline discussion (the
 // path is bound by the fp64 pipe, not by HBM).
 #pragma once
+#include <type_traits>
 #include "physics.cuh"
 #include "recon.cuh"
 #include "riemann.cuh"
@@ -228,13 +229,22 @@ struct ReconStageParams {
     int64_t nt;                // interior columns (the switches look at genuine cells only)
 };
 
-// accessor over the register stencil: logical offset k relative to the cell, identity boundary map
-template <int LO>
+// accessor over the register stencil: logical offset k relative to the cell, identity boundary map.  The window is a
+// circular buffer of NW registers; ROT is the compile-time rotation of the current step of the unrolled march, so
+// every index folds to a constant and advancing by one cell moves no register.
+template <int LO, int NW, int ROT>
 struct StencilAccessor {
     const double* r;
-    HD double s(int64_t k) const { return r[k + LO]; }
+    HD double s(int64_t k) const { return r[(k + LO + ROT) % NW]; }
     HD int64_t b(int64_t k) const { return k; }
 };
+template <int B, int E, class F>
+HD void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 // accessor over a plane column with the clamp of an 'edge' boundary (rows near the physical boundary only)
 struct ColumnAccessor {
     const double* col;         // address of (row 0, var, column)
@@ -288,63 +298,68 @@ struct ReconStage {
             PpmWindow win;                                   // PPM: second differences / face values carried along the march
             bool fresh = true;
 #pragma unroll
-            for (int k = 0; k < NW - 1; ++k) r[k + 1] = col[(first - LO + k) * rp];
-            double ahead = col[(first + HI) * rp];           // row i + HI, requested one iteration early
-            for (int64_t i = first; i <= last; ++i) {
-#pragma unroll
-                for (int k = 0; k < NW - 1; ++k) r[k] = r[k + 1];
-                r[NW - 1] = ahead;
-                if (i < last) ahead = col[(i + 1 + HI) * rp];
-                const int64_t ig = i + p.s_off;
-                double wl, wr, wf;
-                if constexpr (SCHEME == SCH_PPM && CPH) {
-                    {
-                        if (edge && (ig < 0 || ig > p.ns_glob - 1)) continue;
-                        const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
-                        if (p.pass != 0 && !interior) continue;
-                        const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0 || p.force_any3 != 0};
-                        const bool ph = p.ppm_author == PPM_PH;
-                        bool pa = false, pb = false, p3 = false;
-                        if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
-                            ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
-                            cell_faces_ppm_cph(acc, i, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
-                        } else {
-                            StencilAccessor<LO> acc{r};
-                            cell_faces_ppm_cph(acc, 0, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+            for (int k = 0; k < NW; ++k) r[k] = col[(first - LO + k) * rp];
+            // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
+            // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
+            for (int64_t i0 = first; i0 <= last; i0 += NW) {
+                static_for<0, NW>([&](auto uc) {
+                    constexpr int U = decltype(uc)::value;
+                    const int64_t i = i0 + U;
+                    if (i > last) return;
+                    const double ahead = (i < last) ? col[(i + 1 + HI) * rp] : 0.0;      // row (i + 1) + HI
+                    [&]() {
+                        const int64_t ig = i + p.s_off;
+                        double wl, wr, wf;
+                        if constexpr (SCHEME == SCH_PPM && CPH) {
+                            if (edge && (ig < 0 || ig > p.ns_glob - 1)) return;
+                            const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
+                            if (p.pass != 0 && !interior) return;
+                            const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0 || p.force_any3 != 0};
+                            const bool ph = p.ppm_author == PPM_PH;
+                            bool pa = false, pb = false, p3 = false;
+                            if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
+                                ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
+                                cell_faces_ppm_cph(acc, i, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                            } else {
+                                StencilAccessor<LO, NW, U> acc{r};
+                                cell_faces_ppm_cph(acc, 0, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                            }
+                            if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; return; }
+                            if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; return; }
+                            *p.wp.at(i, v, t) = wl;
+                            *p.wm.at(i + 1, v, t) = wr;
+                            if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
+                            if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
+                            if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+                            return;
                         }
-                        if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; continue; }
-                        if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; continue; }
+                        if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
+                            fresh = true;
+                            if (ig < 0 || ig > p.ns_glob - 1) return;            // no such cell
+                            ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
+                            cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
+                        } else if constexpr (SCHEME == SCH_PPM) {
+                            StencilAccessor<LO, NW, U> acc{r};
+                            cell_faces_ppm_mc_march<U>(acc, win, fresh, wl, wr, wf, g);
+                            fresh = false;
+                        } else {
+                            StencilAccessor<LO, NW, U> acc{r};
+                            cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
+                        }
+                        if (p.cell_aligned) {
+                            *p.wp.at(i, v, t) = wl;
+                            *p.wm.at(i, v, t) = wr;
+                            return;
+                        }
+                        // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
                         *p.wp.at(i, v, t) = wl;
                         *p.wm.at(i + 1, v, t) = wr;
-                        if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
-                        if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
+                        if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
+                        if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
                         if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
-                        continue;
-                    }
-                }
-                if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
-                    fresh = true;
-                    if (ig < 0 || ig > p.ns_glob - 1) continue;          // no such cell
-                    ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
-                    cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
-                } else if constexpr (SCHEME == SCH_PPM) {
-                    cell_faces_ppm_mc_march(r + LO, win, fresh, wl, wr, wf, g);
-                    fresh = false;
-                } else {
-                    StencilAccessor<LO> acc{r};
-                    cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
-                }
-                if (p.cell_aligned) {
-                    *p.wp.at(i, v, t) = wl;
-                    *p.wm.at(i, v, t) = wr;
-                    continue;
-                }
-                // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
-                *p.wp.at(i, v, t) = wl;
-                *p.wm.at(i + 1, v, t) = wr;
-                if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
-                if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
-                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+                    }();
+                    r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
+                });
             }
         });
     }
