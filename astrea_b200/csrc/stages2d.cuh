@@ -294,73 +294,103 @@ struct ReconStage {
             const double* col = p.w.at(0, v, t);
             const int64_t rp = p.w.row_pitch;
             const bool edge = p.bc == BC_EDGE;
-            double r[NW];
-            PpmWindow win;                                   // PPM: second differences / face values carried along the march
-            bool fresh = true;
-#pragma unroll
-            for (int k = 0; k < NW; ++k) r[k] = col[(first - LO + k) * rp];
-            // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
-            // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
-            for (int64_t i0 = first; i0 <= last; i0 += NW) {
-                static_for<0, NW>([&](auto uc) {
-                    constexpr int U = decltype(uc)::value;
-                    const int64_t i = i0 + U;
-                    if (i > last) return;
-                    const double ahead = (i < last) ? col[(i + 1 + HI) * rp] : 0.0;      // row (i + 1) + HI
-                    [&]() {
-                        const int64_t ig = i + p.s_off;
+            // what to do with the faces of cell i (ig: its global index); in flag passes of the authors 'c' / 'ph' nothing is stored
+            auto store = [&](int64_t i, int64_t ig, double wl, double wr, double wf) {
+                if (p.cell_aligned) {
+                    *p.wp.at(i, v, t) = wl;
+                    *p.wm.at(i, v, t) = wr;
+                    return;
+                }
+                // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
+                *p.wp.at(i, v, t) = wl;
+                *p.wm.at(i + 1, v, t) = wr;
+                if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
+                if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
+                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+            };
+            // one cell with accessor ``acc`` centred on offset ``at``; CPH: the authors 'c' / 'ph' with their flag passes
+            auto cph_cell = [&](const auto& acc, int64_t at, int64_t i, int64_t ig) {
+                const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
+                if (p.pass != 0 && !interior) return;
+                const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0 || p.force_any3 != 0};
+                const bool ph = p.ppm_author == PPM_PH;
+                bool pa = false, pb = false, p3 = false;
+                double wl, wr, wf;
+                cell_faces_ppm_cph(acc, at, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
+                if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; return; }
+                if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; return; }
+                *p.wp.at(i, v, t) = wl;
+                *p.wm.at(i + 1, v, t) = wr;
+                if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
+                if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
+                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+            };
+            // cells within REACH of a physical 'edge' boundary: generic accessor with the clamp map, straight from memory
+            auto near_boundary = [&](int64_t lo_i, int64_t hi_i) {
+                for (int64_t i = lo_i; i <= hi_i; ++i) {
+                    const int64_t ig = i + p.s_off;
+                    if (ig < 0 || ig > p.ns_glob - 1) continue;                  // no such cell
+                    ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
+                    if constexpr (SCHEME == SCH_PPM && CPH) {
+                        cph_cell(acc, i, i, ig);
+                    } else {
                         double wl, wr, wf;
-                        if constexpr (SCHEME == SCH_PPM && CPH) {
-                            if (edge && (ig < 0 || ig > p.ns_glob - 1)) return;
-                            const bool interior = i >= 0 && i < p.ns && t >= 0 && t < p.nt;
-                            if (p.pass != 0 && !interior) return;
-                            const PpmSwitches sw{p.ppm_flags[0] != 0, p.ppm_flags[1] != 0, p.ppm_flags[2] != 0 || p.force_any3 != 0};
-                            const bool ph = p.ppm_author == PPM_PH;
-                            bool pa = false, pb = false, p3 = false;
-                            if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
-                                ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
-                                cell_faces_ppm_cph(acc, i, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
-                            } else {
-                                StencilAccessor<LO, NW, U> acc{r};
-                                cell_faces_ppm_cph(acc, 0, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
-                            }
-                            if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; return; }
-                            if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; return; }
-                            *p.wp.at(i, v, t) = wl;
-                            *p.wm.at(i + 1, v, t) = wr;
-                            if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
-                            if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
-                            if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
-                            return;
-                        }
-                        if (edge && (ig - REACH < 0 || ig + REACH > p.ns_glob - 1)) {
-                            fresh = true;
-                            if (ig < 0 || ig > p.ns_glob - 1) return;            // no such cell
-                            ColumnAccessor acc{col, rp, 0, p.ns_glob - 1, p.s_off};
-                            cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
-                        } else if constexpr (SCHEME == SCH_PPM) {
-                            StencilAccessor<LO, NW, U> acc{r};
-                            cell_faces_ppm_mc_march<U>(acc, win, fresh, wl, wr, wf, g);
-                            fresh = false;
-                        } else {
-                            StencilAccessor<LO, NW, U> acc{r};
-                            cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
-                        }
-                        if (p.cell_aligned) {
-                            *p.wp.at(i, v, t) = wl;
-                            *p.wm.at(i, v, t) = wr;
-                            return;
-                        }
-                        // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
-                        *p.wp.at(i, v, t) = wl;
-                        *p.wm.at(i + 1, v, t) = wr;
-                        if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
-                        if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
-                        if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
-                    }();
-                    r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
-                });
+                        cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
+                        store(i, ig, wl, wr, wf);
+                    }
+                }
+            };
+            // the segment splits into [first, mid_lo) near the lower boundary, [mid_lo, mid_hi] away from both, (mid_hi, last]
+            int64_t mid_lo = first, mid_hi = last;
+            if (edge) {
+                const int64_t a = REACH - p.s_off, b = p.ns_glob - 1 - REACH - p.s_off;     // first / last cell away from the boundaries
+                if (mid_lo < a) mid_lo = a;
+                if (mid_hi > b) mid_hi = b;
+                if (mid_lo > last + 1) mid_lo = last + 1;
+                if (mid_hi < mid_lo - 1) mid_hi = mid_lo - 1;
+                near_boundary(first, mid_lo - 1);
             }
+            if (mid_lo <= mid_hi) {
+                double r[NW];
+                PpmWindow win;                                   // PPM: second differences / face values carried along the march
+                bool fresh = true;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) r[k] = col[(mid_lo - LO + k) * rp];
+                // running addresses of the march: one pointer increment per plane and cell instead of an index product
+                const double* in = col + (mid_lo + 1 + HI) * rp;
+                double* out_p = p.wp.at(mid_lo, v, t);
+                double* out_m = p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
+                double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? p.wf.at(mid_lo, v, t) : nullptr;
+                const int64_t rp_p = p.wp.row_pitch, rp_m = p.wm.row_pitch, rp_f = p.wf.row_pitch;
+                // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
+                // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
+                for (int64_t i0 = mid_lo; i0 <= mid_hi; i0 += NW) {
+                    static_for<0, NW>([&](auto uc) {
+                        constexpr int U = decltype(uc)::value;
+                        const int64_t i = i0 + U;
+                        if (i > mid_hi) return;
+                        const double ahead = (i < mid_hi) ? *in : 0.0;      // row (i + 1) + HI
+                        in += rp;
+                        StencilAccessor<LO, NW, U> acc{r};
+                        if constexpr (SCHEME == SCH_PPM && CPH) {
+                            cph_cell(acc, 0, i, i + p.s_off);
+                        } else {
+                            double wl, wr, wf;
+                            if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, fresh, wl, wr, wf, g);
+                            else cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
+                            fresh = false;
+                            // away from the physical boundaries: w_plus[i] = wL, w_minus[i + 1] = wR (cell aligned: both at i)
+                            *out_p = wl;
+                            *out_m = wr;
+                            if (out_f != nullptr) { *out_f = wf; out_f += rp_f; }
+                            out_p += rp_p;
+                            out_m += rp_m;
+                        }
+                        r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
+                    });
+                }
+            }
+            if (edge) near_boundary(mid_hi + 1, last);
         });
     }
 };
@@ -397,10 +427,12 @@ struct FluxStage {
 #define ASTREA_FLUX_MIN_BLOCKS 4
 #endif
 #ifndef ASTREA_FLUX_MIN_BLOCKS_HYDRO
-#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 7
+#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 5
 #endif
     // 8-variable kernels: 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5);
-    // hydro kernels: 7 blocks = 28 warps at 72 registers (best of 3..8: the few spills cost less than the warps buy).
+    // hydro kernels: 5 blocks = 20 warps at 96 registers.  With the branch-free division the compiler interleaves
+    // independent chains, so registers buy more than warps: 7 blocks (72 registers, ~70 spill instructions per thread)
+    // 2.06 ms, 6 blocks 2.04 ms, 5 blocks (no spills) 2.01 ms per step of flux stages at 2048^2 (r1l).
     // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
     // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
     static constexpr int MIN_BLOCKS = HYDRO ? ASTREA_FLUX_MIN_BLOCKS_HYDRO : ASTREA_FLUX_MIN_BLOCKS;
