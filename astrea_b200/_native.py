@@ -22,6 +22,19 @@ EDGE, WRAP = 0, 1
 E_ARG, E_CUDA, E_NONFINITE, E_STATE = -1, -2, -3, -4
 
 
+MAX_REGIONS = 8
+REGION_X_LT, REGION_X_LE, REGION_Y_LE, REGION_X_LE_Y_GE, REGION_X_GT_Y_GE, REGION_DISC_LE = range(6)
+
+
+class Region(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("a", C.c_double), ("b", C.c_double), ("state", C.c_double * 8)]
+
+
+class InitSpec(C.Structure):
+    _fields_ = [("cells", C.c_int64), ("start", C.c_double), ("step", C.c_double), ("background", C.c_double * 8),
+                ("nregions", C.c_int32), ("reserved", C.c_int32), ("regions", Region * MAX_REGIONS)]
+
+
 class Cfg(C.Structure):
     """struct astrea_cfg."""
     _fields_ = [
@@ -79,6 +92,7 @@ _SIGNATURES = {
     "astrea_sync": (C.c_int, [C.c_void_p]),
     "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
     "astrea_fp64_probe": (C.c_int, [C.c_void_p, _PD]),
+    "astrea_init_piecewise": (C.c_int, [C.c_void_p, C.POINTER(InitSpec)]),
     "astrea_arith_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "astrea_launch_count": (C.c_int64, [C.c_void_p]),
     "astrea_save_state": (C.c_int, [C.c_void_p]),
@@ -265,6 +279,10 @@ class Context:
         t = C.c_double()
         self._check(self.lib.astrea_fp64_probe(self._h, C.byref(t)))
         return t.value
+
+    def init_piecewise(self, spec):
+        """Initial conditions evaluated on the device (``initial.piecewise_spec``) instead of an upload."""
+        self._check(self.lib.astrea_init_piecewise(self._h, C.byref(spec)))
 
     def arith_check(self, samples=1 << 24, seed=1):
         """(accepted, wrong, declined) of the branch-free division / square root against the IEEE routines."""

@@ -823,6 +823,35 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     return 0;
 }
 
+int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
+    if (!c || !spec) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: NULL argument");
+    if (c->cfg.dimension != 2) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: 2D grids only");
+    if (spec->cells < 1 || spec->cells != c->ncol) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: spec.cells must equal ny");
+    if (spec->nregions < 0 || spec->nregions > ASTREA_MAX_REGIONS) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: too many regions");
+    InitParams p{};
+    p.out = c->regs[c->grid_reg].plane;
+    p.nrow = c->nrow; p.ncol = c->ncol; p.x_off = c->cfg.x_offset; p.n = spec->cells;
+    p.start = spec->start; p.step = spec->step; p.gamma = c->cfg.gamma;
+    p.bc = c->cfg.boundary; p.high_order = scheme_high_order(c->cfg.scheme) ? 1 : 0; p.nregions = spec->nregions;
+    for (int v = 0; v < NVAR; ++v) p.state[0][v] = spec->background[v];
+    for (int k = 0; k < spec->nregions; ++k) {
+        if (spec->regions[k].kind < ASTREA_REGION_X_LT || spec->regions[k].kind > ASTREA_REGION_DISC_LE)
+            return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: unknown region kind");
+        p.kind[k] = spec->regions[k].kind; p.a[k] = spec->regions[k].a; p.b[k] = spec->regions[k].b;
+        for (int v = 0; v < NVAR; ++v) p.state[k + 1][v] = spec->regions[k].state[v];
+    }
+    p.mhd_flag = c->mhd_flag;
+    ASTREA_TRY(dev_zero(c->mhd_flag, sizeof(int), c->st));
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<InitKernel>(p, (int)((c->ncol + 127) / 128), (int)c->nrow, 128, 0, c->st)); }
+    c->next_instr = 0;
+    int has_field = 1;
+    ASTREA_TRY(copy_d2h(&has_field, c->mhd_flag, sizeof(int), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_init_piecewise: stream sync failed");
+    c->field_free = !has_field;        // as astrea_upload: 2D hydro states take the four-variable kernels
+    c->hydro = !has_field && c->cfg.dimension == 2 && !c->cfg.magnetic_2d && c->cfg.solver != SOL_HLLD && !(c->cfg.flags & 1);
+    return 0;
+}
+
 int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     if (!c || !grid_aos) return fail(c, ASTREA_E_ARG, "astrea_download: NULL argument");
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_download: a step is in flight (between evolve_space and evolve_time the scratch planes are live)");

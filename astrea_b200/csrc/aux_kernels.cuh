@@ -557,6 +557,105 @@ struct Fp64ProbeKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ initial conditions
+// constructor.initialise(sim_variables, convert=True) (functions/constructor.py:11-109) for problems whose pointwise
+// primitive state is piecewise constant: the grid starts as ``initial_right`` and a list of regions is painted over
+// it in order, like the reference's sequence of ``grid[np.where(...)] = state`` assignments (:46-60, :72-73).  The
+// pointwise primitives become conservative cell averages as in :105-109 with generic.py:250-255: 4th-order
+// (fv.py:126-143) or pointwise conversion, then ``+ laplacian / 24`` (fv.py:67-85), every sum in the reference's order.
+// The square N x N problem is evaluated on the fly at base cell ((row + x_off) mod N, col), which also tiles it
+// periodically along x for the slab-decomposed weak-scaling runs (initial.initial_slab).
+constexpr int MAX_REGIONS = 8;
+enum RegionKind : int { REG_X_LT = 0, REG_X_LE = 1, REG_Y_LE = 2, REG_X_LE_Y_GE = 3, REG_X_GT_Y_GE = 4, REG_DISC_LE = 5 };
+struct InitParams {
+    Plane out;
+    int64_t nrow, ncol, x_off;
+    int64_t n;                 // cells per side of the square base problem
+    double start, step;        // np.linspace(lo - half, hi + half, n + 2): point k is k * step + start, cell i is point i + 1
+    double gamma;
+    int bc, high_order, nregions;
+    int kind[MAX_REGIONS];
+    double a[MAX_REGIONS], b[MAX_REGIONS];     // threshold(s): shock position, or (centre, radius^2) for a disc
+    double state[MAX_REGIONS + 1][NVAR];       // state[0]: background (initial_right); state[k + 1]: region k
+    int* mhd_flag;
+};
+struct InitKernel {
+    using Params = InitParams;
+    static constexpr int MAX_THREADS = 128;
+    static HD int64_t nb(int64_t i, int64_t n, int bc) { return bc == BC_WRAP ? wrap_index(i, n) : clamp_index(i, 0, n - 1); }
+    static HD void point_prim(const Params& p, int64_t i, int64_t j, double* w) {
+        const double x = (double)(i + 1) * p.step + p.start, y = (double)(j + 1) * p.step + p.start;
+        int pick = 0;
+        for (int k = 0; k < p.nregions; ++k) {
+            bool in;
+            switch (p.kind[k]) {
+                case REG_X_LT: in = x < p.a[k]; break;
+                case REG_X_LE: in = x <= p.a[k]; break;
+                case REG_Y_LE: in = y <= p.a[k]; break;
+                case REG_X_LE_Y_GE: in = x <= p.a[k] && y >= p.a[k]; break;
+                case REG_X_GT_Y_GE: in = x > p.a[k] && y >= p.a[k]; break;
+                default: in = ((x - p.a[k]) * (x - p.a[k]) + (y - p.a[k]) * (y - p.a[k])) <= p.b[k]; break;
+            }
+            if (in) pick = k + 1;
+        }
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) w[v] = p.state[pick][v];
+    }
+    // conservative point / 4th-order value at base cell (i, j) before the final Laplacian (initial._cons_from_point_prim)
+    static HD void cons_at(const Params& p, int64_t i, int64_t j, double* q) {
+        const double c24 = 1.0 / 24.0;
+        double w[NVAR];
+        point_prim(p, i, j, w);
+        if (!p.high_order) { cons_of_prim(w, q, p.gamma); return; }
+        double wacc[NVAR], qacc[NVAR], qc[NVAR];
+        cons_of_prim(w, qc, p.gamma);
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) { wacc[v] = w[v]; qacc[v] = 0.0; }
+        for (int ax = 0; ax < 2; ++ax) {
+            double wu[NVAR], wd[NVAR], qu[NVAR], qd[NVAR];
+            const int64_t iu = ax == 0 ? nb(i + 1, p.n, p.bc) : i, id = ax == 0 ? nb(i - 1, p.n, p.bc) : i;
+            const int64_t ju = ax == 1 ? nb(j + 1, p.n, p.bc) : j, jd = ax == 1 ? nb(j - 1, p.n, p.bc) : j;
+            point_prim(p, iu, ju, wu);
+            point_prim(p, id, jd, wd);
+            cons_of_prim(wu, qu, p.gamma);
+            cons_of_prim(wd, qd, p.gamma);
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                wacc[v] = wacc[v] - c24 * ((wu[v] - w[v]) - (w[v] - wd[v]));
+                qacc[v] = qacc[v] + c24 * ((qu[v] - qc[v]) - (qc[v] - qd[v]));
+            }
+        }
+        double qa[NVAR];
+        cons_of_prim(wacc, qa, p.gamma);
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) q[v] = qa[v] + qacc[v];
+    }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t c = (int64_t)bx * NT + tid, r = by;
+            if (c >= p.ncol) return;
+            const double c24 = 1.0 / 24.0;
+            const int64_t i = wrap_index(r + p.x_off, p.n), j = c;
+            double q[NVAR], out[NVAR];
+            cons_at(p, i, j, q);
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) out[v] = q[v];
+            for (int ax = 0; ax < 2; ++ax) {
+                double qu[NVAR], qd[NVAR];
+                cons_at(p, ax == 0 ? nb(i + 1, p.n, p.bc) : i, ax == 1 ? nb(j + 1, p.n, p.bc) : j, qu);
+                cons_at(p, ax == 0 ? nb(i - 1, p.n, p.bc) : i, ax == 1 ? nb(j - 1, p.n, p.bc) : j, qd);
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) out[v] = out[v] + c24 * ((qu[v] - q[v]) - (q[v] - qd[v]));
+            }
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) *p.out.at(r, v, c) = out[v];
+            if (p.mhd_flag != nullptr && (out[3] != 0.0 || out[5] != 0.0 || out[6] != 0.0 || out[7] != 0.0)) *p.mhd_flag = 1;
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ arithmetic self-check
 // Fast (common.cuh) against the compiler's IEEE division and square root on generated operands.  Operand classes,
 // by the low bits of the sample index: ordinary magnitudes (exponents within +-40 of 1), magnitudes across the

@@ -263,6 +263,10 @@ struct ReconStage {
 #endif
     static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;     // up to 128 registers: the march is latency bound, registers beat warps
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
+#ifndef ASTREA_RECON_PREFETCH
+#define ASTREA_RECON_PREFETCH 3
+#endif
+    static constexpr int PF = ASTREA_RECON_PREFETCH;     // rows in flight beyond the one the next cell needs
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
     // The threads are independent; on the device a warp marches with the Fast division first and repeats its
@@ -357,7 +361,12 @@ struct ReconStage {
 #pragma unroll
                 for (int k = 0; k < NW; ++k) r[k] = col[(mid_lo - LO + k) * rp];
                 // running addresses of the march: one pointer increment per plane and cell instead of an index product
-                const double* in = col + (mid_lo + 1 + HI) * rp;
+                // rows requested PF + 1 cells before their first use, so that a warp has several loads in flight (the march
+                // is bound by load latency at the few warps its registers allow): queue[k] holds row (i + 1) + HI + k
+                double queue[PF];
+#pragma unroll
+                for (int k = 0; k < PF; ++k) queue[k] = (mid_lo + 1 + k <= mid_hi) ? col[(mid_lo + 1 + HI + k) * rp] : 0.0;
+                const double* in = col + (mid_lo + 1 + HI + PF) * rp;
                 double* out_p = p.wp.at(mid_lo, v, t);
                 double* out_m = p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
                 double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? p.wf.at(mid_lo, v, t) : nullptr;
@@ -369,7 +378,10 @@ struct ReconStage {
                         constexpr int U = decltype(uc)::value;
                         const int64_t i = i0 + U;
                         if (i > mid_hi) return;
-                        const double ahead = (i < mid_hi) ? *in : 0.0;      // row (i + 1) + HI
+                        const double ahead = queue[0];                      // row (i + 1) + HI
+#pragma unroll
+                        for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
+                        queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
                         in += rp;
                         StencilAccessor<LO, NW, U> acc{r};
                         if constexpr (SCHEME == SCH_PPM && CPH) {

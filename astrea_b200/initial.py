@@ -248,3 +248,35 @@ def initial_slab(config, cells_x, cells_y, x_offset, cells_x_total, gamma=1.4, h
     base = initial_state(config, cells_y, 2, gamma, high_order)
     rows = (np.arange(x_offset, x_offset + cells_x) % cells_y)
     return np.ascontiguousarray(base[rows])
+
+
+def piecewise_spec(config, cells, gamma=1.4):
+    """The ``astrea_init_spec`` of a 2D problem whose pointwise primitive state is piecewise constant, or None (problems
+    with sine / exponential profiles stay on the host: libm's functions are not reproducible bit for bit on the device).
+    Regions are listed in the order constructor.py:33-75 assigns them; later ones paint over earlier ones."""
+    from . import _native as N
+    c = config.lower()
+    prob = problem(c, cells, gamma)
+    lo, hi, shock, par = prob["start_pos"], prob["end_pos"], prob["shock_pos"], prob["misc"]
+    left, right = prob["initial_left"], prob["initial_right"]
+    mid = (hi + lo) / 2
+    if c == "sedov" or "blast" in c or "rotor" in c:
+        regions = [(N.REGION_DISC_LE, mid, (shock - mid) ** 2, left)]
+    elif c.startswith("gauss") or "kelvin" in c or "helmholtz" in c or c == "khi" or c in ("ivc", "vortex", "isentropic vortex") \
+            or c in ("orszag-tang", "orszag", "tang", "ot"):
+        return None
+    elif "ll" in c or "lax-liu" in c:
+        regions = [(N.REGION_X_LE, shock, 0.0, left), (N.REGION_X_LE_Y_GE, shock, 0.0, par["bottom_left"]),
+                   (N.REGION_X_GT_Y_GE, shock, 0.0, par["bottom_right"])]
+    else:
+        regions = [(N.REGION_X_LT, shock, 0.0, left)]
+    half = abs(hi - lo) / cells / 2
+    start, stop = lo - half, hi + half
+    spec = N.InitSpec()
+    spec.cells, spec.start, spec.step = cells, start, (stop - start) / (cells + 1)       # np.linspace(start, stop, cells + 2)
+    spec.background[:] = list(right)
+    spec.nregions = len(regions)
+    for k, (kind, a, b, state) in enumerate(regions):
+        spec.regions[k].kind, spec.regions[k].a, spec.regions[k].b = kind, a, b
+        spec.regions[k].state[:] = list(state)
+    return spec

@@ -14,7 +14,7 @@ import ctypes
 import numpy as np
 
 from . import _native as N
-from .initial import initial_slab, initial_state, problem
+from .initial import initial_slab, initial_state, piecewise_spec, problem
 from .selectors import MAGNETIC_2D, make_cfg, scheme_enum, stages_of
 
 
@@ -152,7 +152,7 @@ class Simulation:
     """
 
     def __init__(self, config, cells, dimension, subgrid, solver, timestep, cfl=0.5, gamma=1.4, device=0, boundary=None,
-                 rank=0, world=1, cells_x=None, grid=None, overlap=False, _lib=None, **geometry):
+                 rank=0, world=1, cells_x=None, grid=None, overlap=False, device_init=True, _lib=None, **geometry):
         self.config, self.cells, self.dimension = config.lower(), int(cells), int(dimension)
         prob = problem(self.config, self.cells, gamma)
         self.boundary = boundary or prob["boundary"]
@@ -179,9 +179,12 @@ class Simulation:
         self._readers = self.ctx.halo_readers()    # instructions that read ghost rows (operators, refine_grid)
         self._halo_ready = False          # the ghost rows of the grid were already exchanged behind the last update
         self.overlap = overlap
-        if grid is None:
-            grid = self.initial_grid()
-        self.ctx.upload(grid)
+        # piecewise-constant problems are initialised on the device (astrea_init_piecewise): nothing crosses PCIe
+        spec = piecewise_spec(self.config, self.cells, gamma) if (grid is None and dimension == 2 and device_init) else None
+        if spec is not None:
+            self.ctx.init_piecewise(spec)
+        else:
+            self.ctx.upload(self.initial_grid() if grid is None else grid)
 
     def initial_grid(self):
         """constructor.initialise(sim_variables, convert=True) for this rank's rows."""

@@ -168,6 +168,41 @@ int astrea_profile_read(astrea_ctx* ctx, double* ms_by_class, int64_t* launches_
  * roofline report can say how far the fp64-bound stages are from the fp64 peak.  0 in the host-simulated build. */
 int astrea_fp64_probe(astrea_ctx* ctx, double* tflops);
 
+/* Initial conditions on the device for the problems of static/tests.py whose pointwise
+ * primitive state is piecewise constant — the Lax-Liu family (constructor.py:57-60), the discs of Sedov / blast /
+ * rotor (:33-34, :69-73) and the default half-plane (:75): replaces constructor.initialise(sim_variables,
+ * convert=True) (constructor.py:11-109) + astrea_upload, so that a rank's slab never crosses PCIe (4.3 GB at 8192^2).
+ * The grid starts as ``background`` (tests.py ``initial_right``) and the regions are painted over it in order, like the
+ * reference's successive ``grid[np.where(...)] = state`` assignments; the conversion to conservative cell averages
+ * (generic.py:250-255, fv.py:67-85, 126-143) follows the scheme of the context.  Coordinates: cell i sits at
+ * (i + 1) * step + start, the values np.linspace(lo - half, hi + half, cells + 2) produces (constructor.py:13-16).
+ * On a slab, row r of the context is row (r + x_offset) mod cells of the square problem (periodic tiling along x).
+ * Bit-identical to the upload of the reference's array (tests/test_hostsim_parity.py, tests/test_gpu_parity.py). */
+#define ASTREA_MAX_REGIONS 8
+enum astrea_region_kind {
+    ASTREA_REGION_X_LT = 0,          /* x <  a                      constructor.py:75            */
+    ASTREA_REGION_X_LE = 1,          /* x <= a                      :58                          */
+    ASTREA_REGION_Y_LE = 2,          /* y <= a                      :43, :63                     */
+    ASTREA_REGION_X_LE_Y_GE = 3,     /* x <= a and y >= a           :59                          */
+    ASTREA_REGION_X_GT_Y_GE = 4,     /* x >  a and y >= a           :60                          */
+    ASTREA_REGION_DISC_LE = 5        /* (x-a)^2 + (y-a)^2 <= b      :33-34, :70                  */
+};
+typedef struct astrea_region {
+    int32_t kind;
+    int32_t reserved;
+    double a, b;
+    double state[8];                 /* primitive [rho, vx, vy, vz, P, Bx, By, Bz] */
+} astrea_region;
+typedef struct astrea_init_spec {
+    int64_t cells;                   /* cells per side of the square problem (= ny of the context) */
+    double start, step;              /* first point and spacing of np.linspace(lo - half, hi + half, cells + 2) */
+    double background[8];
+    int32_t nregions;
+    int32_t reserved;
+    astrea_region regions[ASTREA_MAX_REGIONS];
+} astrea_init_spec;
+int astrea_init_piecewise(astrea_ctx* ctx, const astrea_init_spec* spec);
+
 /* Self-check of the device arithmetic (no reference counterpart; the reference's divisions and square roots are
  * numpy's IEEE ones, fv.py:19-20,37-38).  The kernels evaluate every division and square root with a branch-free
  * fused-multiply-add sequence ("Fast", csrc/common.cuh) that is IEEE-exact for ordinary operands and hand the

@@ -1,0 +1,76 @@
+"""Initial conditions evaluated on the device (astrea_init_piecewise) against the host-side
+initialiser, which itself is checked bit for bit against the reference's constructor.initialise (golden ``g0``).
+CPU: through the host-simulated build of the same kernel; GPU (marked): through the sm_100a library."""
+import numpy as np
+import pytest
+
+from conftest import golden_case, golden_index
+from astrea_b200 import _native as N
+from astrea_b200.initial import initial_slab, initial_state, piecewise_spec, problem
+from astrea_b200.selectors import make_cfg
+
+CASES = [("ll3", 48, "ppm", None), ("ll6", 40, "plm", None), ("ll12", 33, "weno5", "edge"), ("sedov", 64, "ppm", None),
+         ("mhd rotor", 50, "plm", None), ("toro1", 37, "weno3", None), ("sod", 32, "pcm", "wrap")]
+
+
+def _run(lib, config, cells, subgrid, bc, nx=None, x_offset=0, nx_global=None):
+    prob = problem(config, cells, 1.4)
+    cfg = make_cfg(dimension=2, nx=nx or cells, ny=cells, boundary=bc or prob["boundary"], gamma=1.4, dx=prob["dx"], cfl=.5,
+                   subgrid=subgrid, solver="lf", timestep="ssprk(2,2)", nx_global=nx_global or (nx or cells), x_offset=x_offset)
+    ctx = N.Context(cfg, lib=lib)
+    try:
+        ctx.init_piecewise(piecewise_spec(config, cells, 1.4))
+        return ctx.download()
+    finally:
+        ctx.close()
+
+
+def _check(lib, config, cells, subgrid, bc):
+    high = subgrid in ("ppm", "weno3", "weno5", "weno7")
+    prob = problem(config, cells, 1.4)
+    want = initial_state(config, cells, 2, 1.4, high, boundary=bc or prob["boundary"])
+    got = _run(lib, config, cells, subgrid, bc)
+    assert np.array_equal(got, want)
+    # a slab of a periodically tiled domain (the weak-scaling layout the reference cannot build)
+    if bc is None and prob["boundary"] == "wrap":       # initial_slab tiles the problem with its own boundary mode
+        want = initial_slab(config, 24, cells, 2 * cells - 10, 3 * cells, 1.4, high)
+        got = _run(lib, config, cells, subgrid, bc, nx=24, x_offset=2 * cells - 10, nx_global=3 * cells)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("config,cells,subgrid,bc", CASES, ids=[c[0] + "-" + c[2] for c in CASES])
+def test_device_init_equals_host_init(hostsim_lib, config, cells, subgrid, bc):
+    _check(hostsim_lib, config, cells, subgrid, bc)
+
+
+def test_device_init_equals_reference_golden(hostsim_lib):
+    """Against arrays the unmodified reference produced (tests/golden): every golden 2D case with a piecewise-constant problem."""
+    seen = 0
+    for cid in sorted(golden_index()):
+        meta, data = golden_case(cid)
+        if meta["dimension"] != 2 or meta.get("magnetic_2d") or piecewise_spec(meta["config"], meta["cells"], meta["gamma"]) is None:
+            continue
+        got = _run(hostsim_lib, meta["config"], meta["cells"], meta["subgrid"], meta["boundary"])
+        assert np.array_equal(got, data["g0"]), cid
+        seen += 1
+    assert seen >= 3
+
+
+def test_profiles_with_transcendentals_stay_on_the_host():
+    for config in ("khi", "orszag-tang", "ivc", "gauss"):
+        assert piecewise_spec(config, 32, 1.4) is None
+
+
+def test_simulation_uses_device_init(hostsim_lib):
+    from astrea_b200.simulation import Simulation
+    a = Simulation("ll3", 32, 2, "ppm", "hllc", "ssprk(3,3)", _lib=hostsim_lib)
+    b = Simulation("ll3", 32, 2, "ppm", "hllc", "ssprk(3,3)", _lib=hostsim_lib, device_init=False)
+    assert np.array_equal(a.ctx.download(), b.ctx.download())
+    a.step(); b.step()
+    assert np.array_equal(a.ctx.download(), b.ctx.download())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config,cells,subgrid,bc", CASES + [("ll3", 515, "ppm", None)], ids=[c[0] + "-" + c[2] for c in CASES] + ["ll3-515"])
+def test_device_init_on_gpu(config, cells, subgrid, bc):
+    _check(N.device_library(), config, cells, subgrid, bc)
