@@ -259,9 +259,11 @@ struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
 #ifndef ASTREA_RECON_MIN_BLOCKS
-#define ASTREA_RECON_MIN_BLOCKS 4
+#define ASTREA_RECON_MIN_BLOCKS 5
 #endif
-    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;     // up to 128 registers: the march is latency bound, registers beat warps
+    // the march is bound by load latency: 5 blocks (20 warps, 96 registers, a few spills) measured best of 4 / 5 / 6 / 8
+    // with the prefetch queue (PPM 2048^2: 0.99 / 0.91 / 1.11 ms per step; WENO5 4096^2: 4.93 / 4.42 / 4.47 ms)
+    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
 #ifndef ASTREA_RECON_PREFETCH
 #define ASTREA_RECON_PREFETCH 3
@@ -668,7 +670,7 @@ struct FluxStage {
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); st.ap[v] = st.qp[v]; st.am[v] = st.qm[v]; }
             }
-            if (st.live) solve(st, st.wp, st.wm, st.ap, st.am, st.fp, st.fm, st.fa);
+            solve(st, st.wp, st.wm, st.ap, st.am, st.fp, st.fm, st.fa);
         });
         // C: face-centred q and physical flux (solvers.py:47-52), Riemann flux of the centred states
         ex.wphase([&](int tid) {
@@ -683,7 +685,8 @@ struct FluxStage {
                 cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], [&](int k) { return tls[k].fp[v]; });
                 cfm[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], [&](int k) { return tls[k].fm[v]; });
             }
-            if (st.live) solve(st, st.xp, st.xm, cqp, cqm, cfp, cfm, st.fc);
+            // (solving both Riemann problems of the interface here, side by side, was measured slower: 2.05 vs 2.01 ms)
+            solve(st, st.xp, st.xm, cqp, cqm, cfp, cfm, st.fc);
         });
         // D: F = F_c - d2_t(F_avg)/24 (fv.py:147-153)
         ex.wphase([&](int tid) {
