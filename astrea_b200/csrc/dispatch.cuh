@@ -16,16 +16,21 @@ int launch_flux_pcm(int solver, int ax, int sax, int hydro, const FluxStageParam
 int launch_flux_plm(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
 int launch_flux_ho(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st);
 
+template <class K>
+inline int launch_flux_kernel(const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {
+    return launch<K>(p, gx, gy, nthreads, K::smem_bytes(nthreads), st);
+}
+
 // Body of one inst_flux_*.cu
 #define ASTREA_DEFINE_FLUX(NAME, KIND)                                                                               \
     template <int SOL, int AX, int SAX>                                                                              \
     static int runflux_##NAME(int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {        \
         if (p.bc == BC_EDGE) {                                                                                       \
-            if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, true>>(p, gx, gy, nthreads, 0, st); \
-            return launch<FluxStage<KIND, SOL, AX, SAX, false, true>>(p, gx, gy, nthreads, 0, st);                   \
+            if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, true>>(p, gx, gy, nthreads, st); \
+            return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, true>>(p, gx, gy, nthreads, st);                   \
         }                                                                                                            \
-        if (hydro) return launch<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, false>>(p, gx, gy, nthreads, 0, st); \
-        return launch<FluxStage<KIND, SOL, AX, SAX, false, false>>(p, gx, gy, nthreads, 0, st);                      \
+        if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, false>>(p, gx, gy, nthreads, st); \
+        return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, false>>(p, gx, gy, nthreads, st);                      \
     }                                                                                                                \
     int launch_flux_##NAME(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
         const int key = ax * 2 + sax;                                                                                \
@@ -33,10 +38,10 @@ int launch_flux_ho(int solver, int ax, int sax, int hydro, const FluxStageParams
             case SOL_LW: /* Lax-Wendroff: states without v_z / B only (the launcher checks), no solver axis */         \
                 if (!hydro) return -1;                                                                               \
                 if (p.bc == BC_EDGE)                                                                                 \
-                    return ax == 0 ? launch<FluxStage<KIND, SOL_LW, 0, 0, true, true>>(p, gx, gy, nthreads, 0, st)   \
-                                   : launch<FluxStage<KIND, SOL_LW, 1, 1, true, true>>(p, gx, gy, nthreads, 0, st);  \
-                return ax == 0 ? launch<FluxStage<KIND, SOL_LW, 0, 0, true, false>>(p, gx, gy, nthreads, 0, st)      \
-                               : launch<FluxStage<KIND, SOL_LW, 1, 1, true, false>>(p, gx, gy, nthreads, 0, st);     \
+                    return ax == 0 ? launch_flux_kernel<FluxStage<KIND, SOL_LW, 0, 0, true, true>>(p, gx, gy, nthreads, st)   \
+                                   : launch_flux_kernel<FluxStage<KIND, SOL_LW, 1, 1, true, true>>(p, gx, gy, nthreads, st);  \
+                return ax == 0 ? launch_flux_kernel<FluxStage<KIND, SOL_LW, 0, 0, true, false>>(p, gx, gy, nthreads, st)      \
+                               : launch_flux_kernel<FluxStage<KIND, SOL_LW, 1, 1, true, false>>(p, gx, gy, nthreads, st);     \
             case SOL_LLF: /* LLF ignores the solver axis (solvers.py:69) */                                          \
                 return ax == 0 ? runflux_##NAME<SOL_LLF, 0, 0>(hydro, p, gx, gy, nthreads, st)                       \
                                : runflux_##NAME<SOL_LLF, 1, 1>(hydro, p, gx, gy, nthreads, st);                      \

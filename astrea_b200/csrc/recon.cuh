@@ -108,7 +108,7 @@ HD void cell_faces_ppm_mc(const A& acc, int64_t i, double& wL, double& wR, doubl
 // Marching form: the second differences d2c(i-2 .. i+3) and the two face values of the previous cell are carried
 // from one cell to the next (identical expressions, identical bits), so each cell evaluates one new second
 // difference and one new face value instead of six and two.  ``acc.s(k)`` is the stencil value at offset k from the
-// cell (k = -3 .. 4, identity boundary map); ``fresh``: nothing to carry yet.
+// cell (k = -3 .. 4, identity boundary map); ``ppm_mc_march_prime`` supplies what the first cell finds carried.
 // The carried values live in circular buffers indexed with the compile-time rotation ROT (the march is unrolled by
 // the window length, stages2d.cuh): entry k of the logical window is slot (k + ROT) mod 8, so moving on by one
 // cell moves no register.
@@ -116,17 +116,20 @@ struct PpmWindow {
     double d2[8];      // logical d2c(i-2), .., d2c(i+3) in slots (0 .. 5 + ROT) mod 8
     double face[2];    // face value at the left / right face of cell i in slots (0 / 1 + ROT) mod 2
 };
+// what the first cell of a march finds "carried": d2c(i-2 .. i+2) and the left face value, in the slots of rotation ROT
+template <int ROT, class A>
+HD void ppm_mc_march_prime(const A& acc, PpmWindow& win) {
+    constexpr int R = ROT % 8;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) win.d2[(k + R) % 8] = acc.s(k - 3) - 2.0 * acc.s(k - 2) + acc.s(k - 1);
+    win.face[R % 2] = 7.0 / 12.0 * (acc.s(-1) + acc.s(0)) - 1.0 / 12.0 * (acc.s(-2) + acc.s(1));
+}
 template <int ROT, class A, class G = Exact>
-HD void cell_faces_ppm_mc_march(const A& acc, PpmWindow& win, bool fresh, double& wL, double& wR, double& wF, G&& g = G()) {
+HD void cell_faces_ppm_mc_march(const A& acc, PpmWindow& win, double& wL, double& wR, double& wF, G&& g = G()) {
     auto d2c = [&](int k) { return acc.s(k - 1) - 2.0 * acc.s(k) + acc.s(k + 1); };
     auto face = [&](int k) { return 7.0 / 12.0 * (acc.s(k) + acc.s(k + 1)) - 1.0 / 12.0 * (acc.s(k - 1) + acc.s(k + 2)); };
     constexpr int R = ROT % 8;
     double* d2 = win.d2;
-    if (fresh) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) d2[(k + R) % 8] = d2c(k - 2);
-        win.face[R % 2] = face(-1);
-    }
     d2[(5 + R) % 8] = d2c(3);
     win.face[(1 + R) % 2] = face(0);
     const double f0 = win.face[R % 2], f1 = win.face[(1 + R) % 2];

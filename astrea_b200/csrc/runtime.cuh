@@ -53,6 +53,20 @@ struct DeviceExec {
         const double own = get(tid);
         return __shfl_sync(0xffffffffu, own, ((tid & 31) + delta) & 31);
     }
+    // Exchange of per-lane values inside a warp through shared memory (XS) instead of shuffles: ``put`` publishes this
+    // lane's value in one of the warp's NS slots, ``nbr`` reads the value lane (lane + delta) mod 32 published in an
+    // EARLIER warp phase.  A 64-bit shuffle is two SHFL plus the moves that re-pair the halves; through shared
+    // memory the exchange of one value with both neighbours is one STS.64 and two LDS.64.  With XS = false ``put`` does
+    // nothing and ``nbr`` is ``lane``.
+    template <bool XS, int NS>
+    __device__ __forceinline__ void put(int slot, double v) {
+        if constexpr (XS) smem()[(((int)threadIdx.x >> 5) * NS + slot) * 32 + ((int)threadIdx.x & 31)] = v;
+    }
+    template <bool XS, int NS, class G>
+    __device__ __forceinline__ double nbr(int tid, int slot, int delta, G&& get) {
+        if constexpr (XS) return smem()[((tid >> 5) * NS + slot) * 32 + (((tid & 31) + delta) & 31)];
+        else return lane(tid, delta, get);
+    }
     __device__ __forceinline__ bool warp_any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
     __device__ __forceinline__ bool block_any(bool b) const { return __syncthreads_or(b) != 0; }
     // Max of a non-negative, finite per-thread value -> atomicMax on the bit pattern of *dst (for such values the
@@ -147,6 +161,10 @@ struct HostExec {
     void wphase(F&& f) {
         for (int t = 0; t < nthr; ++t) f(t);
     }
+    template <bool XS, int NS>
+    void put(int, double) {}
+    template <bool XS, int NS, class G>
+    double nbr(int tid, int, int delta, G&& get) { return lane(tid, delta, get); }
     bool warp_any(bool b) const { return b; }      // the host simulation runs a block thread by thread: one guard per block
     bool block_any(bool b) const { return b; }
     template <class G>

@@ -359,9 +359,9 @@ struct ReconStage {
             if (mid_lo <= mid_hi) {
                 double r[NW];
                 PpmWindow win;                                   // PPM: second differences / face values carried along the march
-                bool fresh = true;
 #pragma unroll
                 for (int k = 0; k < NW; ++k) r[k] = col[(mid_lo - LO + k) * rp];
+                if constexpr (SCHEME == SCH_PPM && !CPH) ppm_mc_march_prime<0>(StencilAccessor<LO, NW, 0>{r}, win);
                 // running addresses of the march: one pointer increment per plane and cell instead of an index product
                 // rows requested PF + 1 cells before their first use, so that a warp has several loads in flight (the march
                 // is bound by load latency at the few warps its registers allow): queue[k] holds row (i + 1) + HI + k
@@ -390,9 +390,8 @@ struct ReconStage {
                             cph_cell(acc, 0, i, i + p.s_off);
                         } else {
                             double wl, wr, wf;
-                            if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, fresh, wl, wr, wf, g);
+                            if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, wl, wr, wf, g);
                             else cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
-                            fresh = false;
                             // away from the physical boundaries: w_plus[i] = wL, w_minus[i + 1] = wR (cell aligned: both at i)
                             *out_p = wl;
                             *out_m = wr;
@@ -455,6 +454,16 @@ struct FluxStage {
     static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
     static constexpr bool LW = SOLVER == SOL_LW;
     static constexpr bool LLF = SOLVER == SOL_LLF || LW;     // Lax-Wendroff has LLF's form with another coefficient
+#ifndef ASTREA_FLUX_SMEM_EXCHANGE
+#define ASTREA_FLUX_SMEM_EXCHANGE 1
+#endif
+    // transverse exchange through shared memory instead of shuffles (runtime.cuh put / nbr): hydro kernels only, the
+    // nine exchanged arrays of a four-variable state are 9 KB per warp (37 KB per block, 5 blocks per SM).  Measured at
+    // 2048^2 PPM+HLLC: 2.01 -> 1.89 ms of flux stages per step (-250 of ~2150 static instructions per thread)
+    static constexpr bool XS = HYDRO && !LW && (ASTREA_FLUX_SMEM_EXCHANGE != 0);
+    static constexpr int NS = 9 * VarSet<HYDRO>::N;
+    enum Slot : int { S_WP = 0, S_WM = 1, S_QP = 2, S_QM = 3, S_FP = 4, S_FM = 5, S_AP = 6, S_AM = 7, S_FA = 8 };
+    static size_t smem_bytes(int nthreads) { return XS ? sizeof(double) * (nthreads / 32) * NS * 32 : 0; }
 
     // Per-thread values; a member read by the neighbouring lanes in phase n is never written in phase n.
     struct Tls {
@@ -507,8 +516,8 @@ struct FluxStage {
         };
         // transverse second difference of a per-thread array member produced in an earlier phase; the neighbour of
         // a point on a physical 'edge' boundary is the point itself ("pad the derived array")
-        auto d2t = [&](int tid, const Tls& st, double own, auto get) -> double {
-            double a = ex.lane(tid, -1, get), b = ex.lane(tid, 1, get);
+        auto d2t = [&](int tid, const Tls& st, double own, int slot, auto get) -> double {
+            double a = ex.template nbr<XS, NS>(tid, slot, -1, get), b = ex.template nbr<XS, NS>(tid, slot, 1, get);
             if (edge) {
                 const int64_t tg = st.t + p.t_off;
                 if (tg - 1 < 0) a = own;
@@ -646,6 +655,13 @@ struct FluxStage {
                 if (LW && !(st.lam == st.lam)) st.bad = true;
             }
             pub[tid].lam_max = st.lam_max; pub[tid].bad = st.bad;
+#pragma unroll
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
+                ex.template put<XS, NS>(S_WP * VS::N + kv, st.wp[v]); ex.template put<XS, NS>(S_WM * VS::N + kv, st.wm[v]);
+                ex.template put<XS, NS>(S_QP * VS::N + kv, st.qp[v]); ex.template put<XS, NS>(S_QM * VS::N + kv, st.qm[v]);
+                ex.template put<XS, NS>(S_FP * VS::N + kv, st.fp[v]); ex.template put<XS, NS>(S_FM * VS::N + kv, st.fm[v]);
+            }
         });
         // B: w - d2_t(w)/24, face conversion of q (fv.py:105-122), Riemann flux of the face averages
         ex.wphase([&](int tid) {
@@ -655,22 +671,28 @@ struct FluxStage {
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv);
-                st.xp[v] = st.wp[v] - c24 * d2t(tid, st, st.wp[v], [&](int k) { return tls[k].wp[v]; });
-                st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], [&](int k) { return tls[k].wm[v]; });
+                st.xp[v] = st.wp[v] - c24 * d2t(tid, st, st.wp[v], S_WP * VS::N + kv, [&](int k) { return tls[k].wp[v]; });
+                st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], S_WM * VS::N + kv, [&](int k) { return tls[k].wm[v]; });
             }
             if (HO) {
                 cons_of_prim_t<HYDRO>(st.xp, qx, gamma, g);
 #pragma unroll
-                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], [&](int k) { return tls[k].qp[v]; }); }
+                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], S_QP * VS::N + kv, [&](int k) { return tls[k].qp[v]; }); }
                 cons_of_prim_t<HYDRO>(st.xm, qx, gamma, g);
 #pragma unroll
-                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], [&](int k) { return tls[k].qm[v]; }); }
+                for (int kv = 0; kv < VS::N; ++kv) { const int v = VS::at(kv); st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], S_QM * VS::N + kv, [&](int k) { return tls[k].qm[v]; }); }
             } else {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); st.ap[v] = st.qp[v]; st.am[v] = st.qm[v]; }
             }
             solve(st, st.wp, st.wm, st.ap, st.am, st.fp, st.fm, st.fa);
+#pragma unroll
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
+                ex.template put<XS, NS>(S_AP * VS::N + kv, st.ap[v]); ex.template put<XS, NS>(S_AM * VS::N + kv, st.am[v]);
+                ex.template put<XS, NS>(S_FA * VS::N + kv, st.fa[v]);
+            }
         });
         // C: face-centred q and physical flux (solvers.py:47-52), Riemann flux of the centred states
         ex.wphase([&](int tid) {
@@ -680,10 +702,10 @@ struct FluxStage {
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv);
-                cqp[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], [&](int k) { return tls[k].ap[v]; });
-                cqm[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], [&](int k) { return tls[k].am[v]; });
-                cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], [&](int k) { return tls[k].fp[v]; });
-                cfm[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], [&](int k) { return tls[k].fm[v]; });
+                cqp[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], S_AP * VS::N + kv, [&](int k) { return tls[k].ap[v]; });
+                cqm[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], S_AM * VS::N + kv, [&](int k) { return tls[k].am[v]; });
+                cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], S_FP * VS::N + kv, [&](int k) { return tls[k].fp[v]; });
+                cfm[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], S_FM * VS::N + kv, [&](int k) { return tls[k].fm[v]; });
             }
             // (solving both Riemann problems of the interface here, side by side, was measured slower: 2.05 vs 2.01 ms)
             solve(st, st.xp, st.xm, cqp, cqm, cfp, cfm, st.fc);
@@ -697,7 +719,7 @@ struct FluxStage {
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv);
-                const double f = st.fc[v] - c24 * d2t(tid, st, st.fa[v], [&](int k) { return tls[k].fa[v]; });
+                const double f = st.fc[v] - c24 * d2t(tid, st, st.fa[v], S_FA * VS::N + kv, [&](int k) { return tls[k].fa[v]; });
                 if (owned) *p.f.at(st.j, v, st.t) = f;
             }
         });
