@@ -46,6 +46,12 @@ def _run(cmd, verbose):
     return res.stdout + res.stderr
 
 
+def _compile(cmd, target, verbose):
+    out = _run(cmd, verbose)
+    os.replace(cmd[-1], target)
+    return out
+
+
 def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None, variant=None, defines=()):
     """Compile every translation unit (in parallel) and link the shared library.  Returns its path.
     ``variant`` / ``defines``: a tuning build with extra -D flags, written to astrea_b200/lib/variants/<variant>.so."""
@@ -67,16 +73,18 @@ def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + heads + [os.path.abspath(__file__)]):
-            todo.append([compiler] + flags + ["-c", s, "-o", o])
+            todo.append(([compiler] + flags + ["-c", s, "-o", o + ".%d.tmp" % os.getpid()], o))
     logs = []
     if todo:
         with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as pool:
-            logs = list(pool.map(lambda c: _run(c, verbose), todo))
+            logs = list(pool.map(lambda c: _compile(c[0], c[1], verbose), todo))
     if todo or force or _stale(lib, objs):
-        if hostsim:
-            _run(["g++", "-shared", "-o", lib] + objs, verbose)
+        tmp = lib + ".%d.tmp" % os.getpid()      # written beside the target and renamed: concurrent builders (pytest-xdist
+        if hostsim:                               # workers) never see a half-written library
+            _run(["g++", "-shared", "-o", tmp] + objs, verbose)
         else:
-            _run([compiler, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], verbose)
+            _run([compiler, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], verbose)
+        os.replace(tmp, lib)
     if ptxas_info:
         print("\n".join(logs))
     return lib
