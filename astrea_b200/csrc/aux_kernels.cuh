@@ -710,12 +710,14 @@ struct ArithCheckKernel {
                 const double x = operand(a, cls), y = operand(b, cls_y);
                 Exact exact;
 #ifdef ASTREA_DEVICE_BUILD
-                { Fast f; const double r = f.div(x, y); if (f.ok) { ++accepted; wrong += same(r, exact.div(x, y)) ? 0 : 1; } else ++declined; }
-                { Fast f; const double r = f.safe_div(x, y); if (f.ok) { ++accepted; wrong += same(r, exact.safe_div(x, y)) ? 0 : 1; } else ++declined; }
-                { Fast f; const double r = f.root(x); if (f.ok) { ++accepted; wrong += same(r, exact.root(x)) ? 0 : 1; } else ++declined; }
-                { Fast f; const double r = f.root(fabs(y)); if (f.ok) { ++accepted; wrong += same(r, exact.root(fabs(y))) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.div(x, y); if (f.good()) { ++accepted; wrong += same(r, exact.div(x, y)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.safe_div(x, y); if (f.good()) { ++accepted; wrong += same(r, exact.safe_div(x, y)) ? 0 : 1; } else ++declined; }
+                { FastT<false> f; const double r = f.div(x, y); if (f.good()) { ++accepted; wrong += same(r, exact.div(x, y)) ? 0 : 1; } else ++declined; }
+                { FastT<false> f; const double r = f.safe_div(x, y); if (f.good()) { ++accepted; wrong += same(r, exact.safe_div(x, y)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.root(x); if (f.good()) { ++accepted; wrong += same(r, exact.root(x)) ? 0 : 1; } else ++declined; }
+                { Fast f; const double r = f.root(fabs(y)); if (f.good()) { ++accepted; wrong += same(r, exact.root(fabs(y))) ? 0 : 1; } else ++declined; }
 #else
-                (void)x; (void)y; (void)exact; accepted += 4;
+                (void)x; (void)y; (void)exact; accepted += 6;
 #endif
             }
 #ifdef __CUDA_ARCH__

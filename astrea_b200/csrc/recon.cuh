@@ -31,8 +31,8 @@ HD double limited_slope(const A& acc, int64_t i, int limiter, G&& g = G()) {
         case LIM_VANLEER: return ddiv(r + fabs(r), 1.0 + fabs(r), g) * b;
         case LIM_OSPRE: return 1.5 * ddiv(r * r + r, r * r + r + 1.0, g) * b;
         case LIM_VANALBADA: return ddiv(r * r + r, r * r + 1.0, g) * b;
-        case LIM_KOREN: return npmax(0.0, npmin(npmin(2.0 * r, ddiv(2.0 + r, 3.0, g)), 2.0)) * b;
-        default: return npmax(0.0, npmax(npmin(2.0 * r, 1.0), npmin(r, 2.0))) * b;   // superbee
+        case LIM_KOREN: return g.vmax(0.0, g.vmin(g.vmin(2.0 * r, ddiv(2.0 + r, 3.0, g)), 2.0)) * b;
+        default: return g.vmax(0.0, g.vmax(g.vmin(2.0 * r, 1.0), g.vmin(r, 2.0))) * b;   // superbee
     }
 }
 
@@ -72,12 +72,12 @@ HD void ppm_mc_limit(double c, double m1, double p1, double m2, double p2, doubl
     const double d2f = 6.0 * (faceL - 2.0 * c + faceR);
     const bool extremum = (dwm * dwp <= 0.0) || ((c - m2) * (p2 - c) <= 0.0);
     double d2lim = 0.0;
-    if (extremum) d2lim = npsign(d2c) * npmin(npmin(fabs(d2f), C * fabs(d2c)), npmin(C * fabs(d2c_p1), C * fabs(d2c_m1)));
-    const double scale = npmax(fabs(c), npmax(npmax(fabs(m1), fabs(p1)), npmax(fabs(m2), fabs(p2))));
+    if (extremum) d2lim = g.vsign(d2c) * g.vmin(g.vmin(fabs(d2f), C * fabs(d2c)), g.vmin(C * fabs(d2c_p1), C * fabs(d2c_m1)));
+    const double scale = g.vmax(fabs(c), g.vmax(g.vmax(fabs(m1), fabs(p1)), g.vmax(fabs(m2), fabs(p2))));
     const double rho = (fabs(d2f) > 1e-12 * scale) ? sdiv(d2lim, d2f, g) : 0.0;
-    const double d3min = npmin(npmin(d3_m1, d3), npmin(d3_m2, d3_p2));
-    const double d3max = npmax(npmax(d3_m1, d3), npmax(d3_m2, d3_p2));
-    const bool act = (rho < (1.0 - 1e-12)) || (0.1 * npmax(fabs(d3max), fabs(d3min)) <= (d3max - d3min));
+    const double d3min = g.vmin(g.vmin(d3_m1, d3), g.vmin(d3_m2, d3_p2));
+    const double d3max = g.vmax(g.vmax(d3_m1, d3), g.vmax(d3_m2, d3_p2));
+    const bool act = (rho < (1.0 - 1e-12)) || (0.1 * g.vmax(fabs(d3max), fabs(d3min)) <= (d3max - d3min));
     wL = faceL;
     wR = faceR;
     if (act) {

@@ -45,7 +45,7 @@ struct PrimStage {
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
 #ifdef ASTREA_TWO_PASS
-        FirstGuard first;                           // see FluxStage::block; here the unit of repetition is the block
+        FirstGuardPlain first;                      // see FluxStage::block; here the unit of repetition is the block
         body(p, bx, by, ex, first);
         if (!ex.block_any(!first.good())) return;
 #endif
@@ -133,7 +133,7 @@ struct PrimBothStage {
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
 #ifdef ASTREA_TWO_PASS
-        FirstGuard first;                           // see FluxStage::block; here the unit of repetition is the block
+        FirstGuardPlain first;                      // see FluxStage::block; here the unit of repetition is the block
         body(p, bx, by, ex, first);
         if (!ex.block_any(!first.good())) return;
 #endif
@@ -340,6 +340,7 @@ struct ReconStage {
                     if constexpr (SCHEME == SCH_PPM && CPH) {
                         cph_cell(acc, i, i, ig);
                     } else {
+                        for (int k = -(LO + 1); k <= HI + 1; ++k) g.input(acc.s(acc.b(i + k)));     // everything the cell can read
                         double wl, wr, wf;
                         cell_faces<SCHEME>(acc, i, p.limiter, wl, wr, wf, g);
                         store(i, ig, wl, wr, wf);
@@ -360,7 +361,7 @@ struct ReconStage {
                 double r[NW];
                 PpmWindow win;                                   // PPM: second differences / face values carried along the march
 #pragma unroll
-                for (int k = 0; k < NW; ++k) r[k] = col[(mid_lo - LO + k) * rp];
+                for (int k = 0; k < NW; ++k) { r[k] = col[(mid_lo - LO + k) * rp]; g.input(r[k]); }
                 if constexpr (SCHEME == SCH_PPM && !CPH) ppm_mc_march_prime<0>(StencilAccessor<LO, NW, 0>{r}, win);
                 // running addresses of the march: one pointer increment per plane and cell instead of an index product
                 // rows requested PF + 1 cells before their first use, so that a warp has several loads in flight (the march
@@ -381,6 +382,7 @@ struct ReconStage {
                         const int64_t i = i0 + U;
                         if (i > mid_hi) return;
                         const double ahead = queue[0];                      // row (i + 1) + HI
+                        g.input(ahead);
 #pragma unroll
                         for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
                         queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
@@ -491,7 +493,7 @@ struct FluxStage {
         bool done = false;
 #ifdef ASTREA_TWO_PASS
         if constexpr (!LW) {
-            FirstGuard first;
+            FirstGuardPlain first;
             body(p, bx, by, ex, pub, first);
             done = !ex.warp_any(!first.good());
         }

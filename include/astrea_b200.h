@@ -207,7 +207,7 @@ int astrea_init_piecewise(astrea_ctx* ctx, const astrea_init_spec* spec);
  * numpy's IEEE ones, fv.py:19-20,37-38).  The kernels evaluate every division and square root with a branch-free
  * fused-multiply-add sequence ("Fast", csrc/common.cuh) that is IEEE-exact for ordinary operands and hand the
  * warp / block to the compiler's IEEE routines otherwise.  This call runs Fast against those routines on about
- * ``samples`` generated operand pairs (4 operations each): counts[0] = operations Fast accepted, counts[1] = accepted
+ * ``samples`` generated operand pairs (6 operations each: both policies of the division, two square roots): counts[0] = operations Fast accepted, counts[1] = accepted
  * operations whose result differs in any bit from IEEE (must be 0), counts[2] = operations Fast declined. */
 int astrea_arith_check(astrea_ctx* ctx, int64_t samples, uint64_t seed, uint64_t* counts);
 
