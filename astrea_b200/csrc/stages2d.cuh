@@ -278,7 +278,9 @@ struct ReconStage {
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
 #ifdef ASTREA_TWO_PASS
         if constexpr (!CPH && SCHEME != SCH_PCM) {
-            FirstGuard first;
+            // PLM / PPM divide by way of their limiters, whose numerators are -0 routinely: sign fix on.  The WENO weights
+            // g / (beta + eps)^2 and their normalisation have positive numerators: no sign fix (a -0 would be flagged).
+            std::conditional_t<(SCHEME >= SCH_WENO3), FirstGuardPlain, FirstGuard> first;
             march(p, bx, by, ex, first);
             if (!ex.warp_any(!first.good())) return;
         }
