@@ -1,5 +1,5 @@
 #!/bin/bash
-# Evidence of one round, run on the GPU box from the repo root:  gpurun -- 'bash profiles/capture.sh r1q'
+# Evidence of one round, run on the GPU box from the repo root:  gpurun -- 'bash profiles/capture.sh r1s'
 # Writes bench lines of every configuration, the reference arm, the ncu launch list and one `--set full` capture of the
 # four kernels of a step into gpurun_out/; profiles/summarize.py turns the ncu files into the tables of README.md.
 # Numbers printed by a run under ncu are never bench values: the bench lines come from the unprofiled runs above them.
