@@ -281,9 +281,9 @@ def run_ours(a):
     # the bound that really applies: the fp64 pipe.  Measured FMA peak of this GPU, and how busy ncu saw the pipe.
     sim.restore_state()
     roofline["fp64"] = {"peak_tflops_measured": ctx.fp64_probe(),
-                        "pipe_busy_ncu": "FluxStage 59 %, ReconStage 46 %, PrimBothStage 40 % (profiles/README.md, last section); "
-                                         "the flux stage is bound by issue slots (69 % busy, 41 % of its instructions are "
-                                         "fp64 and take two cycles of the pipe), DESIGN.md"}
+                        "pipe_busy_ncu": "FluxStage 62 %, ReconStage 44 %, PrimBothStage 39 % (profiles/README.md r1s); in the flux "
+                                         "stage 49 % of the instructions are fp64 and hold the pipe for two cycles, so pipe "
+                                         "and issue limits coincide (DESIGN.md)"}
     # DRAM bytes actually moved per sweep, from the committed `ncu --set full` capture (profiles/summarize.py)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
