@@ -54,11 +54,14 @@ def _compile(cmd, target, verbose):
 
 def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None, variant=None, defines=()):
     """Compile every translation unit (in parallel) and link the shared library.  Returns its path.
-    ``variant`` / ``defines``: a tuning build with extra -D flags, written to astrea_b200/lib/variants/<variant>.so."""
+    ``variant`` / ``defines``: a build with extra -D flags, written to astrea_b200/lib/variants/<variant>.so (device) or
+    tests/hostsim/variants/<variant>.so (host simulation, e.g. the audit build of tests/test_two_pass_audit.py)."""
     lib = HOSTSIM_LIB if hostsim else DEVICE_LIB
     objdir = os.path.join(ROOT, "build", "hostsim" if hostsim else "sm_100a")
     if variant:
-        lib = os.path.join(ROOT, "astrea_b200", "lib", "variants", variant + ".so")
+        # device tuning builds beside the product library, host-simulated ones beside the test library
+        lib = (os.path.join(ROOT, "tests", "hostsim", "variants", variant + ".so") if hostsim
+               else os.path.join(ROOT, "astrea_b200", "lib", "variants", variant + ".so"))
         objdir = os.path.join(ROOT, "build", "variant_" + variant)
     os.makedirs(objdir, exist_ok=True)
     os.makedirs(os.path.dirname(lib), exist_ok=True)
