@@ -7,13 +7,19 @@
 //                              (PPM/WENO, fv.py:126-143).  Thread per cell, 34x10 shared-memory tile so that each
 //                              pointwise conversion is evaluated once.
 //   ReconStage  wS -> w+, w-   reconstruction + limiter (schemes/*.py, limiters.py).  Thread per (column, variable)
-//                              marching along the sweep with the stencil in registers: one load and two stores
-//                              per cell and variable, no shared memory, no barrier.
+//                              marching along the sweep with the stencil in a rotating register window (the march is
+//                              unrolled by the window length): one load and two stores per cell and variable, rows
+//                              requested four cells ahead, no shared memory, no barrier.
 //   FluxStage   w+- -> F       face conversion (fv.py:105-122 'face'), physical fluxes (constructor.py:113-125),
 //                              averaged-state wave speed (fv.py:157-169), Riemann flux of the face averages and of
 //                              the face-centred states, F = F_c - d2_t(F_avg)/24 (solvers.py:44-57, fv.py:147-153).
 //                              One warp per 32 transverse points of one interface row; transverse neighbours are
-//                              exchanged by warp shuffle, everything else lives in registers.
+//                              exchanged through per-warp shared-memory slots (four-variable hydro states) or by
+//                              warp shuffle (eight-variable states), everything else lives in registers.
+//
+// Every division and square root goes through a guard (common.cuh): the kernels run a branch-free pass first and a
+// warp (block, for the tiled primitive stages) repeats its work with the compiler's IEEE routines if an operand was
+// outside the range the branch-free sequences cover.  Results never depend on which pass produced them.
 //
 // The flux difference and the Runge-Kutta update follow in aux_kernels.cuh.  HBM traffic per cell and sweep:
 // 64 B (q) + 64 B (wS) + 64 B + 128 B (w+-) + 128 B + 64 B (F); see DESIGN.md for the roofline discussion (the
