@@ -55,3 +55,26 @@ def test_package_refuses_non_device_library(monkeypatch, hostsim_lib):
     monkeypatch.setattr(N, "_device_lib", None)
     with pytest.raises(ImportError):
         N.device_library()
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of astrea_cfg / astrea_region / astrea_init_spec have the size and field offsets a C compiler
+    gives the declarations of include/astrea_b200.h (the header must also compile as plain C)."""
+    import subprocess
+    from astrea_b200 import _native as N
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "astrea_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu\\n", sizeof(astrea_cfg), offsetof(astrea_cfg, gamma), offsetof(astrea_cfg, nx_global), offsetof(astrea_cfg, flags));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(astrea_region), offsetof(astrea_region, a), offsetof(astrea_region, state));\n'
+        '  printf("%zu %zu %zu %zu\\n", sizeof(astrea_init_spec), offsetof(astrea_init_spec, background), offsetof(astrea_init_spec, nregions), offsetof(astrea_init_spec, regions));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [ctypes.sizeof(N.Cfg), N.Cfg.gamma.offset, N.Cfg.nx_global.offset, N.Cfg.flags.offset,
+            ctypes.sizeof(N.Region), N.Region.a.offset, N.Region.state.offset,
+            ctypes.sizeof(N.InitSpec), N.InitSpec.background.offset, N.InitSpec.nregions.offset, N.InitSpec.regions.offset]
+    assert got == want
