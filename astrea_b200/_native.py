@@ -99,6 +99,8 @@ _SIGNATURES = {
     "astrea_restore_state": (C.c_int, [C.c_void_p]),
     "astrea_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_profile_read": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64)]),
+    "astrea_host_alloc": (C.c_void_p, [C.c_int, C.c_uint64]),
+    "astrea_host_free": (None, [C.c_void_p]),
     "astrea_is_device_build": (C.c_int, []),
 }
 EXPORTS = tuple(_SIGNATURES)
@@ -128,6 +130,55 @@ def device_library():
             raise ImportError(f"{DEVICE_LIB} is not an sm_100a device build")
         _device_lib = lib
     return _device_lib
+
+
+class PinnedPool:
+    """numpy arrays in page-locked host memory (``astrea_host_alloc``), recycled when the caller drops them.
+
+    The drop-in's ``evolve_time`` returns its result in such an array; the reference loop rebinds ``grid`` to it and
+    passes it to the next ``evolve_space`` (astrea.py:67,81), so after the first step both transfers are direct DMA.
+    A block goes back to the free list when the last view of its array is garbage collected."""
+
+    def __init__(self, lib, device=0, keep=3):
+        self.lib, self.device, self.keep = lib, device, keep
+        self.free = {}          # bytes -> [address, ...]
+        self.closed = False
+
+    class _Block:
+        def __init__(self, pool, address, nbytes):
+            self.pool, self.address, self.nbytes = pool, address, nbytes
+
+        def __del__(self):
+            try:
+                self.pool._give_back(self.address, self.nbytes)
+            except Exception:
+                pass
+
+    def _give_back(self, address, nbytes):
+        spare = self.free.setdefault(nbytes, [])
+        if self.closed or len(spare) >= self.keep:
+            self.lib.astrea_host_free(address)
+        else:
+            spare.append(address)
+
+    def empty(self, shape):
+        """An uninitialised C-contiguous float64 array of ``shape`` in pinned memory."""
+        count = int(np.prod(shape))
+        nbytes = max(count, 1) * 8
+        spare = self.free.get(nbytes)
+        address = spare.pop() if spare else self.lib.astrea_host_alloc(self.device, nbytes)
+        if not address:
+            return np.empty(shape, dtype=np.float64)       # out of pinned memory: a pageable array still works
+        buf = (C.c_double * max(count, 1)).from_address(address)
+        buf._astrea_block = PinnedPool._Block(self, address, nbytes)      # lives as long as any view of the array
+        return np.frombuffer(buf, dtype=np.float64, count=count).reshape(shape)
+
+    def close(self):
+        self.closed = True
+        for spare in self.free.values():
+            for address in spare:
+                self.lib.astrea_host_free(address)
+        self.free.clear()
 
 
 class Context:
@@ -170,7 +221,11 @@ class Context:
     def download(self, primitive=False, out=None):
         """``primitive``: False = conservative averages, True = the astrea.py:47 snapshot, 2 = the same on a slab whose
         ghost rows the caller has exchanged."""
-        out = np.empty(self.shape, dtype=np.float64) if out is None else out
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        elif (not isinstance(out, np.ndarray) or out.shape != tuple(self.shape) or out.dtype != np.float64
+              or not out.flags.c_contiguous or not out.flags.writeable):
+            raise ValueError(f"out must be a writeable C-contiguous float64 array of shape {tuple(self.shape)}")
         self._check(self.lib.astrea_download(self._h, out.ctypes.data, int(primitive)))
         return out
 

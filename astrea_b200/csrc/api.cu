@@ -154,6 +154,25 @@ std::string cuda_text(int e) { return std::string(cudaGetErrorString((cudaError_
 std::string cuda_text(int e) { return "hostsim error " + std::to_string(e); }
 #endif
 
+// Every entry point that touches CUDA selects the context's device for its duration and restores the caller's
+// afterwards: two contexts on different GPUs may be driven from one host thread, and a context may be called from a
+// thread whose current device is another one.
+struct DeviceGuard {
+#ifdef ASTREA_DEVICE_BUILD
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+#else
+    explicit DeviceGuard(int) {}
+#endif
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ASTREA_ON_DEVICE(c) DeviceGuard _device_guard((c)->cfg.device)
+
 #define ASTREA_TRY(expr)                                                                   \
     do {                                                                                   \
         const int _e = (expr);                                                             \
@@ -719,9 +738,13 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     if (check_cfg(cfg, why) != 0) { g_create_error = why; return nullptr; }
     astrea_ctx* c = new astrea_ctx();
     c->cfg = *cfg;
+    ASTREA_ON_DEVICE(c);            // the caller's current device is restored on return
 #ifdef ASTREA_DEVICE_BUILD
     {
-        cudaError_t e = cudaSetDevice(cfg->device);
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e == cudaSuccess && (cfg->device < 0 || cfg->device >= ndev)) e = cudaErrorInvalidDevice;
+        if (e == cudaSuccess) e = cudaSetDevice(cfg->device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st.s, cudaStreamNonBlocking);
         if (e != cudaSuccess) { g_create_error = std::string("CUDA: ") + cudaGetErrorString(e); delete c; return nullptr; }
         c->stream_owned = true;
@@ -787,6 +810,7 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
 
 void astrea_destroy(astrea_ctx* c) {
     if (!c) return;
+    ASTREA_ON_DEVICE(c);
     stream_sync(c->st);
     for (auto& r : c->regs) dev_free(r.mem);
     for (auto& r : c->rates) dev_free(r.mem);
@@ -807,10 +831,12 @@ const char* astrea_last_error(const astrea_ctx* c) { return c ? c->err.c_str() :
 
 int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     if (!c || !grid_aos) return fail(c, ASTREA_E_ARG, "astrea_upload: NULL argument");
+    ASTREA_ON_DEVICE(c);
     const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
     double* staging = c->d0.mem;     // d0 is scratch between operator evaluations
     ASTREA_TRY(copy_h2d(staging, grid_aos, bytes, c->st));
     ASTREA_TRY(dev_zero(c->mhd_flag, sizeof(int), c->st));
+    ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));      // a new grid starts with a clean non-finite flag
     PackParams p{c->regs[c->grid_reg].plane, staging, c->nrow, c->ncol, 1, c->mhd_flag};
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     c->next_instr = 0;
@@ -825,6 +851,7 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
 
 int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
     if (!c || !spec) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: NULL argument");
+    ASTREA_ON_DEVICE(c);
     if (c->cfg.dimension != 2) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: 2D grids only");
     if (spec->cells < 1 || spec->cells != c->ncol) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: spec.cells must equal ny");
     if (spec->nregions < 0 || spec->nregions > ASTREA_MAX_REGIONS) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: too many regions");
@@ -842,6 +869,7 @@ int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
     }
     p.mhd_flag = c->mhd_flag;
     ASTREA_TRY(dev_zero(c->mhd_flag, sizeof(int), c->st));
+    ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<InitKernel>(p, (int)((c->ncol + 127) / 128), (int)c->nrow, 128, 0, c->st)); }
     c->next_instr = 0;
     int has_field = 1;
@@ -854,6 +882,7 @@ int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
 
 int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     if (!c || !grid_aos) return fail(c, ASTREA_E_ARG, "astrea_download: NULL argument");
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_download: a step is in flight (between evolve_space and evolve_time the scratch planes are live)");
     Plane src = c->regs[c->grid_reg].plane;
     if (as_primitive) {
@@ -875,6 +904,7 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
 
 int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, int external_rows) {
     if (!c || !totals || !total_variation) return fail(c, ASTREA_E_ARG, "astrea_diagnostics: NULL argument");
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_diagnostics: a step is in flight");
     Plane q = c->regs[c->grid_reg].plane;
     if (int e = fill_halo(c, q, external_rows)) return e;
@@ -900,6 +930,7 @@ int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, i
 
 int astrea_fp64_probe(astrea_ctx* c, double* tflops) {
     if (!c || !tflops) return fail(c, ASTREA_E_ARG, "astrea_fp64_probe: NULL argument");
+    ASTREA_ON_DEVICE(c);
     *tflops = 0.0;
 #ifdef ASTREA_DEVICE_BUILD
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_fp64_probe: a step is in flight");
@@ -929,6 +960,7 @@ int astrea_fp64_probe(astrea_ctx* c, double* tflops) {
 
 int astrea_arith_check(astrea_ctx* c, int64_t samples, uint64_t seed, uint64_t* counts) {
     if (!c || !counts || samples < 1) return fail(c, ASTREA_E_ARG, "astrea_arith_check: bad argument");
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_arith_check: a step is in flight");
     unsigned long long* dev = (unsigned long long*)dev_alloc(3 * sizeof(unsigned long long));
     if (!dev) return fail(c, ASTREA_E_CUDA, "astrea_arith_check: allocation failed");
@@ -955,6 +987,7 @@ int astrea_instr_is_operator(const astrea_ctx* c, int i) {
 
 int astrea_set_dt(astrea_ctx* c, double dt) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     ASTREA_TRY(copy_h2d(c->dt_dev, &dt, sizeof(double), c->st));
     // the source is a stack variable: finish the copy before returning
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_set_dt: stream sync failed");
@@ -962,6 +995,7 @@ int astrea_set_dt(astrea_ctx* c, double dt) {
 
 int astrea_run_instr(astrea_ctx* c, int i, int external_rows) {
     if (!c || i < 0 || i >= (int)c->prog.size()) return fail(c, ASTREA_E_ARG, "astrea_run_instr: bad instruction index");
+    ASTREA_ON_DEVICE(c);
     if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_instr: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
     const Instr& ins = c->prog[i];
     const int e = ins.is_operator ? run_operator(c, ins, external_rows, i == 0)
@@ -984,15 +1018,19 @@ int astrea_instr_is_update(const astrea_ctx* c, int i) {
 int astrea_run_update_part(astrea_ctx* c, int i, int part) {
     if (!c || i < 0 || i >= (int)c->prog.size() || astrea_instr_is_update(c, i) != 1)
         return fail(c, ASTREA_E_ARG, "astrea_run_update_part: not a register update");
+    ASTREA_ON_DEVICE(c);
     if (i != c->next_instr) return fail(c, ASTREA_E_STATE, "astrea_run_update_part: instructions must run in order (expected " + std::to_string(c->next_instr) + ")");
-    // the first / last UPDATE_EDGE rows are what the neighbours' ghost rows are made of (GHOST <= UPDATE_EDGE)
-    const int64_t edge = std::min<int64_t>(UPDATE_EDGE, c->nrow / 2);
+    // the first / last UPDATE_EDGE rows are what the neighbours' ghost rows are made of (GHOST <= UPDATE_EDGE); a slab
+    // too short for two disjoint edge blocks of at least GHOST rows is updated whole in part 0
     const Instr& ins = c->prog[i];
+    const bool whole = c->nrow < 2 * (int64_t)GHOST;
+    const int64_t edge = whole ? c->nrow : std::min<int64_t>(UPDATE_EDGE, c->nrow / 2);
     if (part == 0) {
         if (int e = run_combine(c, ins, 0, edge)) return e;
-        return run_combine(c, ins, c->nrow - edge, c->nrow);
+        return whole ? 0 : run_combine(c, ins, std::max<int64_t>(edge, c->nrow - edge), c->nrow);
     }
-    if (int e = run_combine(c, ins, edge, c->nrow - edge)) return e;
+    if (!whole)
+        if (int e = run_combine(c, ins, edge, c->nrow - edge)) return e;
     c->next_instr = i + 1;
     return 0;
 }
@@ -1008,6 +1046,7 @@ int astrea_finish_step(astrea_ctx* c) {
 
 int astrea_read_eigmax(astrea_ctx* c, double* eigmax) {
     if (!c || !eigmax) return fail(c, ASTREA_E_ARG, "astrea_read_eigmax: NULL argument");
+    ASTREA_ON_DEVICE(c);
     unsigned long long bits[3] = {0, 0, 0};
     ASTREA_TRY(copy_d2h(bits, c->eig_bits, sizeof(bits), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_read_eigmax: stream sync failed");
@@ -1016,12 +1055,16 @@ int astrea_read_eigmax(astrea_ctx* c, double* eigmax) {
         const int slot = c->cfg.dimension == 1 ? 0 : a;
         std::memcpy(&eigmax[a], &bits[slot], sizeof(double));
     }
-    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed (the reference raises LinAlgError: Array must not contain infs or NaNs, fv.py:158)");
+    if (flag) {     // sticky until read: reported once, then cleared
+        dev_zero(c->flag, sizeof(unsigned long long), c->st);
+        return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed (the reference raises LinAlgError: Array must not contain infs or NaNs, fv.py:158)");
+    }
     return 0;
 }
 
 int astrea_evolve_space(astrea_ctx* c, int step_parity, double* eigmax) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     c->parity = step_parity & 1;
     c->next_instr = 0;
     if (int e = astrea_run_instr(c, 0, 0)) return e;
@@ -1030,6 +1073,7 @@ int astrea_evolve_space(astrea_ctx* c, int step_parity, double* eigmax) {
 
 int astrea_evolve_time(astrea_ctx* c, double dt) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 1) return fail(c, ASTREA_E_STATE, "astrea_evolve_time: call astrea_evolve_space first");
     if (int e = astrea_set_dt(c, dt)) return e;
     for (int i = 1; i < (int)c->prog.size(); ++i)
@@ -1040,12 +1084,16 @@ int astrea_evolve_time(astrea_ctx* c, double dt) {
     unsigned long long flag = 0;
     ASTREA_TRY(copy_d2h(&flag, c->flag, sizeof(flag), c->st));
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_evolve_time: stream sync failed");
-    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a Runge-Kutta stage (fv.py:158 raises LinAlgError)");
+    if (flag) {
+        dev_zero(c->flag, sizeof(unsigned long long), c->st);
+        return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a Runge-Kutta stage (fv.py:158 raises LinAlgError)");
+    }
     return 0;
 }
 
 int astrea_step(astrea_ctx* c, double t, double t_stop, double* dt_out) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     double eig[2] = {0, 0};
     if (int e = astrea_evolve_space(c, c->parity, eig)) return e;
     double dt = c->cfg.cfl * (c->cfg.dx / eig[0]);
@@ -1060,6 +1108,7 @@ int astrea_step(astrea_ctx* c, double t, double t_stop, double* dt_out) {
 
 int astrea_set_time(astrea_ctx* c, double t, double t_stop) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     ClockParams k{c->clock, c->dt_dev, c->eig_bits, c->dt_history, DT_HISTORY, 0, c->cfg.dimension, c->cfg.cfl, c->cfg.dx, t, t_stop};
     Timed timed(c, CLS_HALO);
     ASTREA_TRY(launch<ClockKernel>(k, 1, 1, 32, 0, c->st));
@@ -1068,6 +1117,7 @@ int astrea_set_time(astrea_ctx* c, double t, double t_stop) {
 
 int astrea_dt_async(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 1) return fail(c, ASTREA_E_STATE, "astrea_dt_async: run instruction 0 (the operator on the grid) first");
     ClockParams k{c->clock, c->dt_dev, c->eig_bits, c->dt_history, DT_HISTORY, 1, c->cfg.dimension, c->cfg.cfl, c->cfg.dx, 0.0, 0.0};
     Timed timed(c, CLS_HALO);
@@ -1086,6 +1136,7 @@ static int enqueue_step(astrea_ctx* c) {
 
 int astrea_step_async(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
 #ifdef ASTREA_DEVICE_BUILD
     // Launch-bound regime (the 1D configurations, small 2D grids): the ~10-40 launches of a step are captured once
     // per (step parity, hydro) and replayed as one CUDA graph.  Large grids gain nothing and launch eagerly.
@@ -1123,6 +1174,7 @@ int astrea_step_async(astrea_ctx* c) {
 
 int astrea_get_time(astrea_ctx* c, double* t, int64_t* steps, double* last_dt) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     double clock[4] = {0, 0, 0, 0};
     unsigned long long flag = 0;
     ASTREA_TRY(copy_d2h(clock, c->clock, sizeof(clock), c->st));
@@ -1131,12 +1183,16 @@ int astrea_get_time(astrea_ctx* c, double* t, int64_t* steps, double* last_dt) {
     if (t) *t = clock[0];
     if (steps) *steps = (int64_t)clock[2];
     if (last_dt) *last_dt = clock[3];
-    if (flag) return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a step since the last check (fv.py:158 raises LinAlgError)");
+    if (flag) {
+        dev_zero(c->flag, sizeof(unsigned long long), c->st);
+        return fail(c, ASTREA_E_NONFINITE, "non-finite wave speed in a step since the last check (fv.py:158 raises LinAlgError)");
+    }
     return 0;
 }
 
 int astrea_dt_history(astrea_ctx* c, double* out, int n) {
     if (!c || !out || n < 0 || n > DT_HISTORY) return fail(c, ASTREA_E_ARG, "astrea_dt_history: n must be within 0..1024");
+    ASTREA_ON_DEVICE(c);
     double clock[4];
     std::vector<double> hist(DT_HISTORY);
     ASTREA_TRY(copy_d2h(clock, c->clock, sizeof(clock), c->st));
@@ -1153,6 +1209,7 @@ int astrea_set_parity(astrea_ctx* c, int p) { if (!c) return ASTREA_E_ARG; c->pa
 
 int astrea_download_face_field(astrea_ctx* c, double* bxy_aos) {
     if (!c || !bxy_aos) return fail(c, ASTREA_E_ARG, "astrea_download_face_field: NULL argument");
+    ASTREA_ON_DEVICE(c);
     if (!c->cfg.magnetic_2d) return fail(c, ASTREA_E_ARG, "astrea_download_face_field: magnetic_2d is off");
     // face averages of the last operator, assembled in a scratch plane and unpacked on the host
     Plane tmp = make_plane(c->ws.mem, c->ncol, GHOST);
@@ -1191,6 +1248,7 @@ int astrea_halo_ptrs(astrea_ctx* c, int i, double** send_lo, double** send_hi, d
 
 int astrea_halo_prepare(astrea_ctx* c, int i) {
     if (!c || i < 0 || i >= (int)c->prog.size() || !needs_ghost_rows(c->prog[i])) return fail(c, ASTREA_E_ARG, "astrea_halo_prepare: the instruction reads no ghost rows");
+    ASTREA_ON_DEVICE(c);
     // only the first / last ghost_r interior rows travel: fill their ghost columns
     HaloParams h{c->regs[halo_register(c->prog[i])].plane, c->nrow, c->ncol, c->cfg.boundary, 0, 0, 0, c->vars(), 0, 0, 0};
     const int rows = (int)std::min<int64_t>(c->ghost_r, c->nrow);
@@ -1208,6 +1266,7 @@ int astrea_eigmax_device(astrea_ctx* c, double** p) {
 
 int astrea_sync(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_sync: stream sync failed");
 }
 
@@ -1224,6 +1283,7 @@ int64_t astrea_launch_count(const astrea_ctx* c) { return c ? c->launches : 0; }
 
 int astrea_save_state(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_save_state: a step is in flight");
     if (!c->saved.mem && !alloc_reg(c, c->saved, c->ncol)) return fail(c, ASTREA_E_CUDA, "astrea_save_state: device allocation failed");
     ASTREA_TRY(copy_d2d(c->saved.mem, c->regs[c->grid_reg].mem, c->plane_doubles * sizeof(double), c->st));
@@ -1235,6 +1295,7 @@ int astrea_save_state(astrea_ctx* c) {
 
 int astrea_restore_state(astrea_ctx* c) {
     if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
     if (!c->saved.mem) return fail(c, ASTREA_E_STATE, "astrea_restore_state: nothing saved");
     ASTREA_TRY(copy_d2d(c->regs[c->grid_reg].mem, c->saved.mem, c->plane_doubles * sizeof(double), c->st));
     ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));
@@ -1253,6 +1314,7 @@ int astrea_profile(astrea_ctx* c, int enable) {
 
 int astrea_profile_read(astrea_ctx* c, double* ms_by_class, int64_t* launches_by_class) {
     if (!c || !ms_by_class || !launches_by_class) return fail(c, ASTREA_E_ARG, "astrea_profile_read: NULL argument");
+    ASTREA_ON_DEVICE(c);
     for (int k = 0; k < CLS_COUNT; ++k) { ms_by_class[k] = 0.0; launches_by_class[k] = 0; }
 #ifdef ASTREA_DEVICE_BUILD
     if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_profile_read: stream sync failed");
@@ -1267,6 +1329,28 @@ int astrea_profile_read(astrea_ctx* c, double* ms_by_class, int64_t* launches_by
     c->spans.clear();
 #endif
     return 0;
+}
+
+void* astrea_host_alloc(int device, uint64_t bytes) {
+    if (bytes == 0) return nullptr;
+#ifdef ASTREA_DEVICE_BUILD
+    DeviceGuard guard(device);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+#else
+    (void)device;
+    return std::malloc((size_t)bytes);
+#endif
+}
+
+void astrea_host_free(void* p) {
+    if (!p) return;
+#ifdef ASTREA_DEVICE_BUILD
+    cudaFreeHost(p);
+#else
+    std::free(p);
+#endif
 }
 
 int astrea_is_device_build(void) {

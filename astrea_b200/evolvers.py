@@ -9,8 +9,10 @@ current iteration order, and ``fluxes[axes]['eigmax']`` is what astrea.py:70-71 
 on the device: ``fluxes[axes]['flux']`` is an opaque handle that only ``evolve_time`` understands.
 
 Each call crosses the host/device boundary (upload in ``evolve_space``, download in ``evolve_time``), which is
-what a maintainer gets by re-pointing the two lines of astrea.py.  ``astrea_b200.Simulation`` keeps the grid
-resident on the device instead.
+what a maintainer gets by re-pointing the two lines of astrea.py.  The array ``evolve_time`` returns lives in
+page-locked memory (``_native.PinnedPool``): the reference loop passes it straight back to the next ``evolve_space``,
+so only the very first upload of a run is a pageable copy.  ``astrea_b200.Simulation`` keeps the grid resident on
+the device instead.
 """
 import numpy as np
 
@@ -18,6 +20,7 @@ from . import _native as N
 from .selectors import cfg_from_sim_variables
 
 _contexts = {}
+_pools = {}
 
 
 class DeviceFlux:
@@ -45,11 +48,21 @@ def _context(sv, device=0, _lib=None):
     return ctx
 
 
+def _pool(ctx, device):
+    key = (id(ctx.lib), device)
+    if key not in _pools:
+        _pools[key] = N.PinnedPool(ctx.lib, device)
+    return _pools[key]
+
+
 def release():
-    """Free every cached device context."""
+    """Free every cached device context and the spare pinned arrays."""
     for ctx in _contexts.values():
         ctx.close()
     _contexts.clear()
+    for pool in _pools.values():
+        pool.close()
+    _pools.clear()
 
 
 def _parity(sv):
@@ -74,5 +87,7 @@ def evolve_time(grid, fluxes, dt, sim_variables, device=0, _lib=None, out=None):
     if not isinstance(handle, DeviceFlux) or handle.ctx is not ctx or handle.token != ctx._token:
         raise ValueError("evolve_time: `fluxes` must come from the latest evolve_space call on this grid")
     ctx.evolve_time(dt)
-    out = ctx.download(out=out)      # `out`: optional preallocated (e.g. pinned) host array for the new grid
+    if out is None:
+        out = _pool(ctx, device).empty(ctx.shape)      # a fresh array, as evolvers.py:206 returns one; page-locked
+    out = ctx.download(out=out)      # `out`: optional caller-provided host array for the new grid
     return out.reshape(np.shape(grid))

@@ -224,10 +224,17 @@ class Simulation:
                 ctx.run_instr(i)
         ctx.finish_step()
 
-    def step(self, t_stop=None):
-        """One pass of astrea.py:67-85.  Returns dt."""
+    def step(self, t_stop=None, dt=None):
+        """One pass of astrea.py:67-85.  Returns dt.  ``dt``: take this time step instead of cfl*min(dx/eigmax) (parity
+        runs that replay the reference's own dt sequence); the wave speeds are still reduced and checked."""
         stop = self.t - 1.0 if t_stop is None else t_stop
-        if self.exchange is None:
+        forced = dt
+        if self.exchange is None and forced is not None:
+            self.ctx.evolve_space(self.ctx.parity)
+            self.ctx.evolve_time(forced)
+            self.ctx.parity = self.ctx.parity ^ 1
+            dt = forced
+        elif self.exchange is None:
             dt = self.ctx.step(self.t, stop)
         else:
             box = {}
@@ -237,6 +244,8 @@ class Simulation:
                 dt = self.cfl * min(self.dx / e for e in eig)
                 if stop > self.t and self.t + dt >= stop:
                     dt = stop - self.t
+                if forced is not None:
+                    dt = forced
                 self.ctx.set_dt(dt)
                 box["dt"] = dt
 
@@ -313,8 +322,9 @@ class Simulation:
             self.exchange.halo(0)
             self._halo_ready = False
             tot, tv = self.ctx.diagnostics(external_rows=True)
-            t = self.exchange.torch.tensor(np.concatenate([tot, tv]), dtype=self.exchange.torch.float64,
-                                           device="cuda" if self.on_device else "cpu")
+            torch = self.exchange.torch
+            where = torch.device("cuda", self.exchange.device_index) if self.on_device else torch.device("cpu")
+            t = torch.tensor(np.concatenate([tot, tv]), dtype=torch.float64, device=where)
             self.exchange.dist.all_reduce(t)
             tot, tv = t[:8].cpu().numpy(), t[8:].cpu().numpy()
         else:

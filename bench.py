@@ -3,10 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
 
-A "step" is one full Runge-Kutta step (all stages) of every cell of the workload.  Default workload (N=1) is
-BASELINE config 2: Lax-Liu 3, 2048^2, PPM + HLLC, SSPRK(3,3), periodic.  With N > 1 (torchrun, one rank per GPU)
-every rank holds a slab of the same size (weak scaling) of a global (N*2048) x 2048 periodic grid; ranks exchange
-ghost rows over NCCL before every spatial operator and all-reduce the wave speeds once per step.
+A "step" is one full Runge-Kutta step (all stages) of every cell of the workload.  Default workload, for every N, is
+the configuration the north star quotes its target on, BASELINE config 5: Lax-Liu 6, 8192^2 PER GPU, PPM + HLLC,
+SSPRK(3,3), periodic (the largest single-GPU configuration: 47 GB of the 180 GB HBM).  With N > 1 (torchrun, one rank
+per GPU) every rank holds a slab of that size (weak scaling) of a global (N*8192) x 8192 periodic grid; ranks exchange
+ghost rows over NVLink before every spatial operator and reduce the wave speeds once per step.  The other BASELINE
+configurations are behind --workload.
+
+Before anything is timed the run checks itself (``parity_check`` in the JSON line): the N ranks advance the 64^2
+golden case of config 5 (tests/golden/, output of the unmodified reference) as N slabs with the halo exchange of the
+timed path, and a 256^2 Lax-Liu 3 grid whose assembled result must equal, bit for bit, the same grid advanced by one
+GPU.  A failed check ends the run with a non-zero exit code.
 
 The reference's own run of this configuration stops with LinAlgError after a few steps (the horizon
 is re-measured here at run time), so the timed loop returns to the initial state every `horizon` steps with a
@@ -160,6 +167,78 @@ def run_reference_arm(a):
     OUT.emit(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ self-check
+def _rel_l1(a, b):
+    axes = tuple(range(a.ndim - 1))
+    den = np.abs(b).sum(axis=axes)
+    return float(np.max(np.abs(a - b).sum(axis=axes) / np.where(den > 0, den, 1)))
+
+
+def parity_check(world, rank, local):
+    """Correctness evidence inside the benchmark run, through the same Simulation / halo-exchange path that is timed.
+
+    golden_c5_64:  BASELINE config 5 at 64^2 (tests/golden/c5_ll6_ppm_hllc_ssprk33.npz: initial grid, dt sequence and
+                   final grid of the unmodified reference), advanced as `world` slabs with the reference's dt sequence;
+                   tolerance 1e-10 relative L1 per variable after its 4 steps (north star).
+    slabs_256:     Lax-Liu 3 at 256^2, PPM + HLLC, SSPRK(3,3), 2 steps with the device-side dt, as `world` slabs against
+                   the same grid on one GPU (rank 0); must be bit-identical, dt sequence included.
+    With world == 1 the second check compares the asynchronous device-clock path with the synchronous one."""
+    import torch
+    import torch.distributed as dist
+    from astrea_b200.initial import initial_state
+    from astrea_b200.simulation import Simulation
+    dev = torch.device("cuda", local)
+
+    def gather(slab):
+        if world == 1:
+            return slab
+        mine = torch.from_numpy(np.ascontiguousarray(slab)).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return np.concatenate([p.cpu().numpy() for p in parts], axis=0)
+
+    out = {}
+    data = np.load(os.path.join(ROOT, "tests", "golden", "c5_ll6_ppm_hllc_ssprk33.npz"))
+    g0, want, dts = data["g0"], data["g"], [float(d) for d in data["dts"]]
+    cells = g0.shape[0]
+    if cells % world == 0 and cells // world >= 8:
+        rows = cells // world
+        sim = Simulation("ll6", cells, 2, "ppm", "hllc", "ssprk(3,3)", device=local, rank=rank, world=world, cells_x=rows,
+                         grid=g0[rank * rows:(rank + 1) * rows])
+        for dt in dts:
+            sim.step(dt=dt)
+        got = gather(sim.state())
+        sim.close()
+        err = _rel_l1(got, want)
+        out["golden_c5_64"] = {"max_rel_l1": err, "bit_identical": bool(np.array_equal(got, want)), "steps": len(dts),
+                               "tolerance": 1e-10, "ok": bool(err <= 1e-10)}
+    cells, steps = 256, 2
+    g0 = initial_state("ll3", cells, 2, 1.4, True)
+    rows = cells // world
+    sim = Simulation("ll3", cells, 2, "ppm", "hllc", "ssprk(3,3)", device=local, rank=rank, world=world, cells_x=rows,
+                     grid=g0[rank * rows:(rank + 1) * rows])
+    sim.set_time(0.0)
+    for _ in range(steps):
+        sim.step_async()
+    sim.time()
+    got, got_dts = gather(sim.state()), sim.ctx.dt_history(steps)
+    sim.close()
+    if rank == 0:
+        one = Simulation("ll3", cells, 2, "ppm", "hllc", "ssprk(3,3)", device=local, grid=g0)
+        want_dts = one.run(steps)
+        want = one.state()
+        one.close()
+        same = bool(np.array_equal(got, want)) and got_dts == want_dts
+        out["slabs_256"] = {"max_rel_l1": _rel_l1(got, want), "bit_identical": same, "steps": steps, "ranks": world, "ok": same}
+    ok = all(v["ok"] for v in out.values())
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.broadcast(flag, src=0)
+        ok = bool(flag.item())
+    out["ok"] = ok
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(a):
     import torch
@@ -178,6 +257,12 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N.device_library()       # fail loudly if the CUDA library is missing
+    check = None if a.no_parity_check else parity_check(world, rank, local)
+    if check is not None and not check["ok"]:
+        if rank == 0:
+            OUT.emit(json.dumps({"metric": "cell-updates/sec (fp64, per RK step)", "value": None, "n_gpus": world,
+                                 "parity_check": check, "error": "parity self-check failed: nothing was timed"}))
+        raise SystemExit(1)
 
     config, cells, dim, subgrid, solver, timestep, desc = WORKLOADS[a.workload]
     if a.cells:
@@ -260,45 +345,59 @@ def run_ours(a):
     peak, peak_src = load_peaks()
     alg = alg_bytes_per_cell_update(stages)
     sweeps_per_step = stages * dim
-    # One sweep = primitive stage + reconstruction stage + flux stage (2D) or the fused sweep kernel (1D); its share
-    # of the algorithmic bytes of a cell-update is 1 / (stages * dimension) (DESIGN.md "Roofline accounting").
+    ms_step = ms / a.steps
+    # Whole step against the HBM roofline: SURVEY 8(d) algorithmic bytes of one cell-update x cells of this GPU / the
+    # measured step time (max over ranks).  This is `frac`.  The per-class split below comes from CUDA events around
+    # every launch of `horizon` further steps on the launching stream (astrea_profile).
+    step_achieved = cells_per_rank * alg / (ms_step * 1e-3) / 1e9
     sweep_ms = prof["flux"][0] + prof["prim"][0] + prof["recon"][0]
-    sweep_n = prof["flux"][1]
+    sweep_n = max(1, prof["flux"][1])
     bytes_per_sweep = cells_per_rank * alg / sweeps_per_step
-    sweep_avg_ms = sweep_ms / max(1, sweep_n)
-    achieved = bytes_per_sweep / (sweep_avg_ms * 1e-3) / 1e9
     flux_avg_ms = prof["flux"][0] / max(1, prof["flux"][1])
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src,
-                "kernel": "one sweep = PrimStage + ReconStage + FluxStage" if dim == 2 else "Sweep1D",
-                "alg_bytes_per_cell_update": alg, "alg_bytes_per_launch": bytes_per_sweep,
-                "kernel_avg_ms": sweep_avg_ms, "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
+    roofline = {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "whole Runge-Kutta step (all kernels of `stages` operator evaluations and register updates)",
+                "alg_bytes_per_cell_update": alg, "alg_bytes_per_launch": cells_per_rank * alg, "kernel_avg_ms": ms_step,
+                "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
+                "class_launches_per_step": {k: v[1] / horizon for k, v in prof.items()},
                 "dominant_kernel": {"name": "FluxStage" if dim == 2 else "Sweep1D", "avg_ms": flux_avg_ms,
                                     "share_of_step": prof["flux"][0] / total_ms if total_ms else None},
-                "class_ms_per_step": {k: v[0] / horizon for k, v in prof.items()},
-                "step_achieved": value / world * alg / 1e9, "step_frac": value / world * alg / 1e9 / peak,
-                "note": "fp64-pipe bound, not HBM bound: see DESIGN.md"}
-    # the bound that really applies: the fp64 pipe.  Measured FMA peak of this GPU, and how busy ncu saw the pipe.
+                # the sweep-only figure of round 1 (all algorithmic bytes of a sweep over the time of its three stages,
+                # register update excluded) is kept for comparison only
+                "sweep_only": {"kernels": "PrimBothStage/2 + ReconStage + FluxStage" if dim == 2 else "Sweep1D",
+                               "alg_bytes": bytes_per_sweep, "avg_ms": sweep_ms / sweep_n,
+                               "frac": bytes_per_sweep / (sweep_ms / sweep_n * 1e-3) / 1e9 / peak if sweep_ms else None},
+                "note": "the path is bound by the fp64 pipe, not by HBM (see the fp64 object and DESIGN.md)"}
+    # The bound that really applies: the fp64 pipe.  FMA rate of this GPU measured now (astrea_fp64_probe), and the
+    # fp64 instructions a step executes (ncu count per cell-update of these kernels, profiles/fp64_work.json, produced
+    # by profiles/summarize.py from the committed capture) -> how busy the pipe is at the measured step time.
     sim.restore_state()
-    roofline["fp64"] = {"peak_tflops_measured": ctx.fp64_probe(),
-                        "pipe_busy_ncu": "FluxStage 62 %, ReconStage 44 %, PrimBothStage 39 % (profiles/README.md r1s); in the flux "
-                                         "stage 49 % of the instructions are fp64 and hold the pipe for two cycles, so pipe "
-                                         "and issue limits coincide (DESIGN.md)"}
-    # DRAM bytes actually moved per sweep, from the committed `ncu --set full` capture (profiles/summarize.py)
+    tflops = ctx.fp64_probe()
+    fp64 = {"peak_tflops_measured": tflops}
+    work_file = os.path.join(ROOT, "profiles", "fp64_work.json")
+    if os.path.exists(work_file) and tflops > 0:
+        with open(work_file) as fh:
+            work = json.load(fh).get(a.workload)
+        if work:
+            warp_inst = work["fp64_warp_inst_per_cell_update"] * cells_per_rank      # per step
+            rate = tflops * 1e12 / 2 / 32                                              # warp-level fp64 instructions per second
+            floor_ms = warp_inst / rate * 1e3
+            fp64.update({"fp64_warp_inst_per_cell_update": work["fp64_warp_inst_per_cell_update"],
+                         "pipe_floor_ms_per_step": floor_ms, "pipe_busy": floor_ms / ms_step, "count_source": work.get("source")})
+    roofline["fp64"] = fp64
+    # DRAM bytes a step really moves, per launch like `achieved`: ncu --set full capture of these kernels
+    # (profiles/traffic.json, written by profiles/summarize.py), launches per step counted live
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as fh:
             tr = json.load(fh).get(a.workload)
-        if tr and not a.cells:
-            per = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tr["kernels"].items()}
-            # one sweep = half a PrimBothStage launch (it serves both directions) + one ReconStage + one FluxStage
-            roofline["traffic"] = sum(b * (0.5 if "PrimBoth" in k else 1.0) for k, b in per.items()
-                                      if any(s in k for s in ("PrimBoth", "PrimStage", "ReconStage", "FluxStage", "Sweep1D")))
-            roofline["traffic_per_kernel_launch"] = per
+        if tr and not a.cells and tr.get("bytes_per_cell_update"):
+            roofline["traffic"] = tr["bytes_per_cell_update"] * cells_per_rank
+            roofline["traffic_per_cell_update"] = tr["bytes_per_cell_update"]
             roofline["traffic_source"] = tr.get("source")
 
     # end to end through the reference-facing calls, host buffers in and out every step
-    e2e = measure_e2e(a, sim, horizon, world, rank, local, stream, barrier)
+    e2e = None if a.no_e2e else measure_e2e(a, sim, horizon, world, rank, local, stream, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -320,7 +419,7 @@ def run_ours(a):
                            "l2": "state per register (%.0f MB) exceeds the 126 MB L2" % (cells_per_rank * 64 / 1e6)
                                  if cells_per_rank * 64 > 126e6 else "working set fits L2 (small workload)",
                            "restore": f"device-to-device return to the initial state every {horizon} steps, inside the timed region"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity_check": check}
         if cpu:
             line["cpu_baseline"] = cpu
         OUT.emit(json.dumps(line))
@@ -332,22 +431,23 @@ def run_ours(a):
 
 
 def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
-    """Same metric with the grid crossing the host/device boundary every step: pinned host array in, host array out.
-    N = 1: the drop-in pair evolvers.evolve_space / evolve_time (astrea.py:67,81).  N > 1: upload / step / download of
-    each rank's slab."""
+    """Same metric with the grid crossing the host/device boundary every step, the way the reference's loop would drive
+    the drop-in: ``grid`` starts as an ordinary (pageable) numpy array, as constructor.initialise returns it
+    (astrea.py:35), every later ``grid`` is the array the previous evolve_time returned (astrea.py:81), which the
+    drop-in allocates page-locked (evolvers.py, _native.PinnedPool).  Every `horizon` steps the loop starts again from
+    the pageable initial array.  N = 1: the pair evolvers.evolve_space / evolve_time (astrea.py:67,81).  N > 1: upload /
+    step / download of each rank's slab with the same memory kinds."""
     import torch
     import torch.distributed as dist
     from collections import namedtuple
+    from astrea_b200 import _native as N
     from astrea_b200 import evolvers
     ctx = sim.ctx
     shape = tuple(ctx.shape)
-    ic = torch.empty(shape, dtype=torch.float64).pin_memory()
-    out = torch.empty(shape, dtype=torch.float64).pin_memory()
     sim.restore_state()
-    ic_np, out_np = ic.numpy(), out.numpy()
-    ctx.download(out=ic_np)
+    ic_np = ctx.download()                     # np.empty: pageable
     nbytes = ic_np.nbytes
-    steps = max(horizon, min(a.steps, 2 * horizon))
+    steps = horizon
     if world == 1:
         SV = namedtuple("simulation_variables", "dimension cells boundary gamma dx cfl subgrid solver solver_category timestep magnetic_2d permutations")
         config, cells, dim, subgrid, solver, timestep, _ = WORKLOADS[a.workload]
@@ -356,44 +456,48 @@ def measure_e2e(a, sim, horizon, world, rank, local, stream, barrier):
         sv0 = SV(dim, cells, sim.boundary, sim.gamma, sim.dx, sim.cfl, subgrid, solver, "hll" if solver.startswith("hll") else "lax",
                  timestep, sim.magnetic_2d, perms)
 
-        def one_pass():
+        def one_pass(n_steps):
             sv, grid = sv0, ic_np
-            for n in range(steps):
-                if n % horizon == 0:
-                    sv, grid = sv0, ic_np
+            for n in range(n_steps):
                 fluxes = evolvers.evolve_space(grid, sv, device=local)
                 dt = sv.cfl * min(sv.dx / f["eigmax"] for f in fluxes.values())
-                grid = evolvers.evolve_time(grid, fluxes, dt, sv, device=local, out=out_np)
+                grid = evolvers.evolve_time(grid, fluxes, dt, sv, device=local)
                 sv = sv._replace(permutations=dict(reversed(list(sv.permutations.items()))))
-        one_pass()                      # warm-up (creates the context)
+            return grid
+        one_pass(min(2, steps))         # warm-up: creates the context and the first pinned arrays
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        one_pass()
+        one_pass(steps)
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
     else:
-        def one_pass():
-            for n in range(steps):
+        pool = N.PinnedPool(ctx.lib, local)
+
+        def one_pass(n_steps):
+            grid = ic_np
+            ctx.parity = 0
+            for n in range(n_steps):
                 sim._halo_ready = False            # a fresh upload: ghost rows are stale
-                if n % horizon == 0:
-                    ctx.upload_ptr(ic_np.ctypes.data)
-                    ctx.parity = 0
-                else:
-                    ctx.upload_ptr(out_np.ctypes.data)
+                ctx.upload_ptr(grid.ctypes.data)
                 sim.step()
-                ctx.download_ptr(out_np.ctypes.data)
-        one_pass()
+                grid = ctx.download(out=pool.empty(shape))
+            return grid
+        one_pass(min(2, steps))
         barrier()
         t0 = time.perf_counter()
-        one_pass()
+        one_pass(steps)
         barrier()
         secs = time.perf_counter() - t0
+        pool.close()
         t = torch.tensor([secs], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t.item())
     cells_per_rank = int(np.prod(shape[:-1]))
     return {"value": world * cells_per_rank * steps / secs, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-            "steps": steps, "api": "evolvers.evolve_space + evolvers.evolve_time (numpy in / numpy out)" if world == 1
+            "steps": steps, "ms_per_step": 1e3 * secs / steps,
+            "host_memory": "step 1 of every pass uploads a pageable numpy array; later steps upload the page-locked array the "
+                           "previous evolve_time returned; every download lands in a fresh page-locked array",
+            "api": "evolvers.evolve_space + evolvers.evolve_time (numpy in / numpy out)" if world == 1
             else "Context.upload + Simulation.step + Context.download per rank", "timer": "host wall clock around synchronised calls"}
 
 
@@ -427,11 +531,13 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c5")
     ap.add_argument("--cells", type=int, default=0, help="override the cells per side (per GPU)")
     ap.add_argument("--threads-2d", type=int, default=0)
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the self-check before the timed region (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--overlap", action="store_true", help="multi-GPU: exchange ghost rows behind the register update (measured slower, see Simulation)")
     a = ap.parse_args()
     with StdoutToStderr() as OUT:

@@ -211,6 +211,14 @@ int astrea_init_piecewise(astrea_ctx* ctx, const astrea_init_spec* spec);
  * operations whose result differs in any bit from IEEE (must be 0), counts[2] = operations Fast declined. */
 int astrea_arith_check(astrea_ctx* ctx, int64_t samples, uint64_t seed, uint64_t* counts);
 
+/* Page-locked host memory for the arrays that cross the seam every step.  evolvers.evolve_time returns a NEW array
+ * (astrea.py:81 rebinds `grid` to it) and the caller hands that array to the next evolve_space (astrea.py:67): when the
+ * drop-in allocates its return value here, every transfer after the first upload is a direct DMA instead of a staged
+ * pageable copy.  astrea_host_alloc returns NULL on failure; astrea_host_free(NULL) is a no-op.  (Host-simulated
+ * build: malloc / free.) */
+void* astrea_host_alloc(int device, uint64_t bytes);
+void astrea_host_free(void* ptr);
+
 /* Number of kernels this library launched on the context's stream since creation (bench.py "gpu_launches"). */
 int64_t astrea_launch_count(const astrea_ctx* ctx);
 /* 1 when built by nvcc for sm_100a, 0 for the host-simulated test build. */

@@ -80,10 +80,47 @@ def full(rep, traffic=None):
     return "\n".join(out)
 
 
+def work(path, workload, cells, steps):
+    """Counters of every launch inside the profiled range of profiles/step_capture.py -> per cell-update figures."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "inst": 1, "ns": 1e-6, "us": 1e-3, "ms": 1.0}
+    tot = collections.defaultdict(float)
+    per_kernel = collections.OrderedDict()
+    ids = set()
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1)
+        tot[row["Metric Name"]] += v
+        k = short(row["Kernel Name"])
+        per_kernel.setdefault(k, collections.defaultdict(float))[row["Metric Name"]] += v
+        ids.add(row["ID"])
+    n = float(cells) * float(steps)
+    src = f"ncu counters of {steps} step(s) at {cells} cells, {os.path.basename(path)} ({len(ids)} launches)"
+    for name, key, value in (("traffic.json", "bytes_per_cell_update", (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) / n),
+                             ("fp64_work.json", "fp64_warp_inst_per_cell_update", tot["smsp__inst_executed_pipe_fp64.sum"] / n)):
+        fpath = os.path.join(HERE, name)
+        store = json.load(open(fpath)) if os.path.exists(fpath) else {}
+        store.setdefault(workload, {})
+        store[workload][key] = value
+        store[workload]["source"] = src
+        if name == "fp64_work.json":
+            store[workload]["warp_inst_per_cell_update"] = tot["smsp__inst_executed.sum"] / n
+        json.dump(store, open(fpath, "w"), indent=1, sort_keys=True)
+    out = ["| kernel | ms | DRAM MB | fp64 warp inst (M) | warp inst (M) |", "|---|---|---|---|---|"]
+    for k, m in sorted(per_kernel.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
+        out.append(f"| {k} | {m['gpu__time_duration.sum']:.3f} | {(m['dram__bytes_read.sum'] + m['dram__bytes_write.sum']) / 1e6:.1f} | "
+                   f"{m['smsp__inst_executed_pipe_fp64.sum'] / 1e6:.2f} | {m['smsp__inst_executed.sum'] / 1e6:.2f} |")
+    out.append(f"\nper cell-update: DRAM {(tot['dram__bytes_read.sum'] + tot['dram__bytes_write.sum']) / n:.1f} B, fp64 warp instructions "
+               f"{tot['smsp__inst_executed_pipe_fp64.sum'] / n:.3f}, all warp instructions {tot['smsp__inst_executed.sum'] / n:.3f}; "
+               f"device time {tot['gpu__time_duration.sum'] / float(steps):.3f} ms/step under ncu ({src})")
+    return "\n".join(out)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
         print(launches(sys.argv[2]))
+    elif mode == "work":
+        print(work(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])))
     else:
         traffic = None
         if "--traffic" in sys.argv:

@@ -486,3 +486,99 @@ def test_ppm_author_switches_off(hostsim_lib, author):
     got, used, _ = run_native(hostsim_lib, meta, g0, 1, tile_1d=23)
     assert used == dts
     assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_clean_grid_after_nonfinite_error(hostsim_lib):
+    """The non-finite flag is sticky until it has been reported, not beyond: a context (the drop-in keeps them in a
+    module-level cache) must accept a clean grid after a bad one."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("sod", 64, 1, "plm", "lf", "ssprk(2,2)", None)
+    good = initial_state("sod", 64, 1, 1.4, False)
+    bad = np.copy(good)
+    bad[10, 4] = np.nan
+    want, dts = run_oracle(meta, good, 2)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(bad)
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.step()
+    # the same context, a clean grid: synchronous and asynchronous stepping both work again
+    ctx.upload(good)
+    ctx.parity = 0
+    assert [ctx.step(), ctx.step()] == dts
+    assert np.array_equal(ctx.download(), want)
+    ctx.upload(bad)
+    ctx.set_time(0.0, 0.0)
+    ctx.step_async()
+    with pytest.raises(np.linalg.LinAlgError):
+        ctx.get_time()
+    ctx.get_time()                              # reported once, then cleared
+    ctx.upload(good)
+    ctx.parity = 0
+    ctx.set_time(0.0, 0.0)
+    ctx.step_async()
+    ctx.step_async()
+    assert ctx.get_time()[1] == 2 and np.array_equal(ctx.download(), want)
+    ctx.close()
+
+
+def test_download_validates_the_output_array(hostsim_lib):
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll3", 12, 2, "plm", "lf", "euler", None)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    g0 = initial_state("ll3", 12, 2, 1.4, False)
+    ctx.upload(g0)
+    for wrong in (np.empty((12, 11, 8)), np.empty((12, 12, 8), dtype=np.float32), np.empty((12, 12, 16))[..., ::2],
+                  np.empty((12, 8, 12)).transpose(0, 2, 1)):
+        with pytest.raises(ValueError):
+            ctx.download(out=wrong)
+    ro = np.empty((12, 12, 8))
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        ctx.download(out=ro)
+    out = np.empty((12, 12, 8))
+    assert ctx.download(out=out) is out and np.array_equal(out, g0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("rows", [8, 9, 11, 15, 16, 17])
+def test_split_update_on_short_slabs(hostsim_lib, rows):
+    """astrea_run_update_part on slabs shorter than two edge blocks: after part 0 every row that travels to a
+    neighbour (the first and last GHOST rows) holds its final value, and parts 0 + 1 update every row exactly once."""
+    import ctypes
+    from astrea_b200 import _native as N
+    from astrea_b200.selectors import make_cfg
+    cells = 24
+    g0 = initial_state("ll6", cells, 2, 1.4, True)[:rows]
+    results, sent = [], []
+    for split in (False, True):
+        cfg = make_cfg(dimension=2, nx=rows, ny=cells, boundary="wrap", gamma=1.4, dx=1.0 / cells, cfl=.5, subgrid="ppm",
+                       solver="hllc", timestep="ssprk(3,3)", nx_global=2 * rows, x_offset=0)
+        ctx = N.Context(cfg, lib=hostsim_lib)
+        on_host = ctx.lib.astrea_is_device_build() == 0
+        ctx.upload(g0)
+        ctx.run_instr(0)
+        ctx.set_dt(1e-3)
+        if split:
+            ctx.run_update_part(1, 0)
+        else:
+            ctx.run_instr(1)
+        if on_host:       # host simulation: the send blocks of the operator that follows are plain memory
+            _, count = ctx.halo_info()
+            sent.append([np.array((ctypes.c_double * count).from_address(p)) for p in ctx.halo_ptrs(2)[:2]])
+        if split:
+            ctx.run_update_part(1, 1)
+        for i in range(2, len(ctx.program())):
+            ctx.run_instr(i)
+        ctx.finish_step()
+        results.append(ctx.download())
+        ctx.close()
+    assert np.array_equal(results[0], results[1], equal_nan=True)
+    if sent:
+        # ghost columns are filled later (halo_prepare); compare the interior columns of the rows that travel
+        g = 8
+        width = cells + 2 * g
+        for whole, part in zip(sent[0], sent[1]):
+            a, b = whole.reshape(-1, 8, width)[..., g:-g], part.reshape(-1, 8, width)[..., g:-g]
+            assert np.array_equal(a, b, equal_nan=True)
