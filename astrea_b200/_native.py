@@ -99,6 +99,8 @@ _SIGNATURES = {
     "astrea_restore_state": (C.c_int, [C.c_void_p]),
     "astrea_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_profile_read": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64)]),
+    "astrea_ppm_flattener": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _PD, C.c_void_p]),
+    "astrea_ppm_viscosity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _PD, C.c_void_p]),
     "astrea_host_alloc": (C.c_void_p, [C.c_int, C.c_uint64]),
     "astrea_host_free": (None, [C.c_void_p]),
     "astrea_is_device_build": (C.c_int, []),
@@ -344,6 +346,26 @@ class Context:
         counts = (C.c_uint64 * 3)()
         self._check(self.lib.astrea_arith_check(self._h, samples, seed, counts))
         return int(counts[0]), int(counts[1]), int(counts[2])
+
+    def ppm_flattener(self, ws, axis, slope_determinants=None):
+        """ppm.apply_flattener (ppm.py:111-134) of primitive averages ``ws`` (sweep frame): chi, shape of the grid."""
+        w = np.ascontiguousarray(ws, dtype=np.float64)
+        if w.shape != tuple(self.shape):
+            raise ValueError(f"wS shape {w.shape} != {tuple(self.shape)}")
+        knobs = None if slope_determinants is None else (C.c_double * 3)(*slope_determinants)
+        out = np.empty(self.shape[:-1], dtype=np.float64)
+        self._check(self.lib.astrea_ppm_flattener(self._h, w.ctypes.data, int(axis), knobs, out.ctypes.data))
+        return out
+
+    def ppm_viscosity(self, ws, axis, viscosity_determinants=None):
+        """ppm.apply_artificial_viscosity (ppm.py:138-170) of primitive averages ``ws``: mu, shape of ``ws`` (1D)."""
+        w = np.ascontiguousarray(ws, dtype=np.float64)
+        if w.shape != tuple(self.shape):
+            raise ValueError(f"wS shape {w.shape} != {tuple(self.shape)}")
+        knobs = None if viscosity_determinants is None else (C.c_double * 2)(*viscosity_determinants)
+        out = np.empty(self.shape, dtype=np.float64)
+        self._check(self.lib.astrea_ppm_viscosity(self._h, w.ctypes.data, int(axis), knobs, out.ctypes.data))
+        return out
 
     def sync(self):
         self._check(self.lib.astrea_sync(self._h))

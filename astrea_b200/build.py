@@ -52,7 +52,7 @@ def _compile(cmd, target, verbose):
     return out
 
 
-def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None, variant=None, defines=()):
+def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None, variant=None, defines=(), fmad=False):
     """Compile every translation unit (in parallel) and link the shared library.  Returns its path.
     ``variant`` / ``defines``: a build with extra -D flags, written to astrea_b200/lib/variants/<variant>.so (device) or
     tests/hostsim/variants/<variant>.so (host simulation, e.g. the audit build of tests/test_two_pass_audit.py)."""
@@ -68,6 +68,8 @@ def build(hostsim=False, force=False, verbose=False, ptxas_info=False, jobs=None
     heads = _headers()
     compiler = "g++" if hostsim else os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = list(GXX_FLAGS if hostsim else NVCC_FLAGS) + ["-D" + d for d in defines]
+    if fmad and not hostsim:       # tolerance-mode experiments: let ptxas contract a*b+c (results no longer bit-identical)
+        flags = [f if f != "-fmad=false" else "-fmad=true" for f in flags]
     if ptxas_info and not hostsim:
         flags += ["-Xptxas", "-v"]
     objs, todo = [], []
@@ -101,6 +103,9 @@ if __name__ == "__main__":
     ap.add_argument("--ptxas-info", action="store_true")
     ap.add_argument("--variant", default=None)
     ap.add_argument("-D", dest="defines", action="append", default=[])
+    ap.add_argument("--fmad", action="store_true", help="variant builds only: compile with -fmad=true")
     a = ap.parse_args()
-    print(build(a.hostsim, a.force, a.verbose, a.ptxas_info, variant=a.variant, defines=a.defines))
+    if a.fmad and not a.variant:
+        ap.error("--fmad needs --variant (the product library is built without contraction)")
+    print(build(a.hostsim, a.force, a.verbose, a.ptxas_info, variant=a.variant, defines=a.defines, fmad=a.fmad))
     sys.exit(0)

@@ -618,7 +618,8 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 fp.gamma = g.gamma; fp.bc = g.boundary; fp.low_mach = g.low_mach;
                 fp.eigmax_bits = eig + ax; fp.flag = c->flag;
                 const int nthreads = (g.threads_2d >= 32 && g.threads_2d <= 128) ? g.threads_2d / 32 * 32 : 128;
-                const int own = 32 - 2 * ht, nwarp = nthreads / 32;
+                int own = 0, nwarp = 0;
+                flux_stage_geometry(kind, g.solver, (lw || c->hydro) ? 1 : 0, nthreads, own, nwarp);
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
                 fp.lw_pass = 0; fp.lw_keys = c->lw_keys;
                 if (lw) {      // search pass of the Lax-Wendroff column pick, per sweep
@@ -926,6 +927,61 @@ int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, i
             total_variation[k] += host[b * 2 * NVAR + NVAR + k];
         }
     return 0;
+}
+
+// schemes/ppm.py:111-170 at function level (aux_kernels.cuh DissipationKernel)
+static int run_dissipation(astrea_ctx* c, const double* ws_aos, int axis, int what, const double* knobs, double* out) {
+    if (!ws_aos || !out) return fail(c, ASTREA_E_ARG, "ppm dissipation: NULL argument");
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "ppm dissipation: a step is in flight");
+    if (axis < 0 || axis >= c->cfg.dimension) return fail(c, ASTREA_E_ARG, "ppm dissipation: axis must be below the dimension");
+    if (c->slab()) return fail(c, ASTREA_E_ARG, "ppm dissipation: whole grids only");
+    if (what == 1 && c->cfg.dimension != 1)
+        return fail(c, ASTREA_E_ARG, "apply_artificial_viscosity: the reference's 2D branch raises (ppm.py:154-156: operands could not be "
+                                     "broadcast together); available in 1D");
+    const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
+    // wS -> a scratch plane (ghost cells = np.pad of wS), result -> another one
+    Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r), res = c->rates[0].plane;
+    double* staging = c->d0.mem;
+    ASTREA_TRY(copy_h2d(staging, ws_aos, bytes, c->st));
+    PackParams pk{w, staging, c->nrow, c->ncol, 1, nullptr};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(pk, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    {
+        HaloParams h{w, c->nrow, c->ncol, c->cfg.boundary, 0, 1, 1, all_vars(), 0, 0, 0};
+        { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<HaloKernel>(h, 1, (int)c->nrow, 64, 0, c->st)); }
+        if (c->ghost_r > 0) {
+            h.phase = 1;
+            Timed timed(c, CLS_HALO);
+            ASTREA_TRY(launch<HaloKernel>(h, (int)((c->ncol + 2 * GHOST + 255) / 256), 2 * GHOST * NVAR, 256, 0, c->st));
+        }
+    }
+    DissipationParams dp{};
+    dp.w = w; dp.out = res; dp.nrow = c->nrow; dp.ncol = c->ncol; dp.dimension = c->cfg.dimension; dp.axis = axis;
+    dp.bc = c->cfg.boundary; dp.what = what; dp.gamma = c->cfg.gamma; dp.dx = c->cfg.dx;
+    if (what == 0) { dp.delta = knobs[0]; dp.z0 = knobs[1]; dp.z1 = knobs[2]; } else { dp.alpha = knobs[0]; dp.beta = knobs[1]; }
+    { Timed timed(c, CLS_RECON); ASTREA_TRY(launch<DissipationKernel>(dp, (int)((c->ncol + 127) / 128), (int)c->nrow, 128, 0, c->st)); }
+    if (what == 0) {
+        ASTREA_TRY(copy_d2h_2d(out, (size_t)c->ncol * sizeof(double), res.at(0, 0, 0), (size_t)res.row_pitch * sizeof(double),
+                               (size_t)c->ncol * sizeof(double), (size_t)c->nrow, c->st));
+    } else {
+        PackParams up{res, staging, c->nrow, c->ncol, 0, nullptr};
+        { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(up, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+        ASTREA_TRY(copy_d2h(out, staging, bytes, c->st));
+    }
+    return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "ppm dissipation: stream sync failed");
+}
+
+int astrea_ppm_flattener(astrea_ctx* c, const double* ws_aos, int axis, const double* slope_determinants, double* chi) {
+    if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
+    const double standard[3] = {.33, .75, .85};                      // ppm.py:112
+    return run_dissipation(c, ws_aos, axis, 0, slope_determinants ? slope_determinants : standard, chi);
+}
+
+int astrea_ppm_viscosity(astrea_ctx* c, const double* ws_aos, int axis, const double* viscosity_determinants, double* mu_aos) {
+    if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
+    const double standard[2] = {.3, .3};                             // ppm.py:139
+    return run_dissipation(c, ws_aos, axis, 1, viscosity_determinants ? viscosity_determinants : standard, mu_aos);
 }
 
 int astrea_fp64_probe(astrea_ctx* c, double* tflops) {

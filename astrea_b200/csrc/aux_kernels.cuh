@@ -435,6 +435,73 @@ struct UpdateKernel {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ PPM dissipation
+// schemes/ppm.py:111-170 — the slope flattener coefficient [Colella 1990] and the artificial-viscosity term
+// [McCorquodale & Colella 2011, eq. 35-38] that ppm.run(dissipate=True) asks for.  The reference cannot run with
+// dissipate=True (ppm.py:67 multiplies arrays whose shapes do not broadcast), so neither is on the time-step path;
+// both functions run standalone and are reproduced at function level: wS (primitive cell averages in the sweep frame,
+// axis 0 = sweep direction) in, coefficient out.  ``axis`` picks the velocity component w[..., axis + 1].
+// Boundary handling as everywhere: ghost cells of wS are np.pad copies ('wrap' | 'edge', filled by HaloKernel); the
+// padded *derived* array chi_bar (ppm.py:126) is evaluated at the mapped index.
+struct DissipationParams {
+    Plane w;              // primitive cell averages, ghost cells filled
+    Plane out;            // flattener: chi in variable slot 0; viscosity: mu in all 8 slots
+    int64_t nrow, ncol;
+    int dimension;        // 1: the sweep runs along the columns of the single row; 2: along the rows
+    int axis;             // velocity component (the reference's permutation key)
+    int bc;
+    int what;             // 0: apply_flattener, 1: apply_artificial_viscosity
+    double delta, z0, z1; // slope_determinants  (ppm.py:112)
+    double alpha, beta;   // viscosity_determinants (ppm.py:139)
+    double gamma, dx;
+};
+struct DissipationKernel {
+    using Params = DissipationParams;
+    static constexpr int MAX_THREADS = 128;
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        ex.phase([&](int tid) {
+            const int64_t c = (int64_t)bx * NT + tid, r = by;
+            if (c >= p.ncol) return;
+            const bool along_rows = p.dimension == 2;
+            const int64_t n = along_rows ? p.nrow : p.ncol, i = along_rows ? r : c;
+            // value of variable v at sweep index i + k (ghost cells hold the padded values)
+            auto at = [&](int64_t k, int v) -> double { return along_rows ? *p.w.at(r + k, v, c) : *p.w.at(r, v, c + k); };
+            if (p.what == 0) {
+                // chi_bar of the cell at sweep offset k from this one (ppm.py:124-125)
+                auto chi_bar = [&](int64_t k) -> double {
+                    const double pp1 = at(k + 1, 4), pm1 = at(k - 1, 4), pp2 = at(k + 2, 4), pm2 = at(k - 2, 4);
+                    const double d1 = fabs(pp1 - pm1), d2 = fabs(pp2 - pm2);
+                    const double z = sdiv(d1, d2);
+                    double zeta = 1.0 - sdiv(z - p.z0, p.z1 - p.z0);
+                    if (z > p.z1) zeta = 0.0;
+                    if (z < p.z0) zeta = 1.0;
+                    const bool compressive_weak = ((at(k - 1, 1 + p.axis) - at(k + 1, 1 + p.axis)) <= 0.0) && (sdiv(d1, npmin(pp1, pm1)) <= p.delta);
+                    return compressive_weak ? 0.0 : zeta;
+                };
+                // pad of the derived array: 'wrap' ghost data are genuine, 'edge' repeats the boundary cell's value
+                auto mapped = [&](int64_t k) -> int64_t { return p.bc == BC_WRAP ? k : clamp_index(i + k, 0, n - 1) - i; };
+                const double own = chi_bar(0);
+                const double sign = npsign(at(1, 4) - at(-1, 4));
+                double chi = own;
+                if (sign < 0.0) chi = npmin(own, chi_bar(mapped(1)));
+                if (sign > 0.0) chi = npmin(own, chi_bar(mapped(-1)));
+                *p.out.at(r, 0, c) = chi;
+            } else {
+                // ppm.py:138-170 read cell by cell (1D): lambda_R, c_min, nu, mu of the face right of cell i
+                const double lam = at(1, 1 + p.axis) - at(0, 1 + p.axis);
+                const double cs0 = dsqrt(sdiv(p.gamma * at(0, 4), at(0, 0))), cs1 = dsqrt(sdiv(p.gamma * at(1, 4), at(1, 0)));
+                const double cmin = npmin(cs0, cs1);
+                double nu = npmin(1.0, sdiv(sq(p.dx * lam), p.beta * sq(cmin))) * lam;
+                if (lam >= 0.0) nu = 0.0;
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v) *p.out.at(r, v, c) = p.alpha * (nu * (at(1, v) - at(0, v)));
+            }
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ device-side clock
 // astrea.py:70-78 without a host round trip: dt = cfl * min(dx / eigmax), clipped so that t + dt does not pass
 // t_stop, written where the register updates read it; t and the step count advance on the device.

@@ -58,15 +58,28 @@ struct DeviceExec {
     // EARLIER warp phase.  A 64-bit shuffle is two SHFL plus the moves that re-pair the halves; through shared
     // memory the exchange of one value with both neighbours is one STS.64 and two LDS.64.  With XS = false ``put`` does
     // nothing and ``nbr`` is ``lane``.
-    template <bool XS, int NS>
+    // BT ("block tile"): the lanes of the whole block form one row of transverse points, so the neighbour of a lane
+    // may sit in another warp; the slots are then block-wide arrays (one pad element at either end: the outermost
+    // lanes are halo lanes whose neighbour values are never used) and the phases are separated by block barriers.
+    template <bool XS, int NS, bool BT = false>
     __device__ __forceinline__ void put(int slot, double v) {
-        if constexpr (XS) smem()[(((int)threadIdx.x >> 5) * NS + slot) * 32 + ((int)threadIdx.x & 31)] = v;
+        if constexpr (XS && BT) smem()[slot * ((int)blockDim.x + 2) + 1 + (int)threadIdx.x] = v;
+        else if constexpr (XS) smem()[(((int)threadIdx.x >> 5) * NS + slot) * 32 + ((int)threadIdx.x & 31)] = v;
     }
-    template <bool XS, int NS, class G>
+    template <bool XS, int NS, bool BT = false, class G>
     __device__ __forceinline__ double nbr(int tid, int slot, int delta, G&& get) {
-        if constexpr (XS) return smem()[((tid >> 5) * NS + slot) * 32 + (((tid & 31) + delta) & 31)];
+        if constexpr (XS && BT) return smem()[slot * ((int)blockDim.x + 2) + 1 + tid + delta];
+        else if constexpr (XS) return smem()[((tid >> 5) * NS + slot) * 32 + (((tid & 31) + delta) & 31)];
         else return lane(tid, delta, get);
     }
+    // phase of a kernel whose unit of cooperation is the warp (BLOCK = false) or the block (BLOCK = true)
+    template <bool BLOCK, class F>
+    __device__ __forceinline__ void xphase(F&& f) {
+        f((int)threadIdx.x);
+        if constexpr (BLOCK) __syncthreads(); else __syncwarp();
+    }
+    template <bool BLOCK>
+    __device__ __forceinline__ bool group_any(bool b) const { if constexpr (BLOCK) return block_any(b); else return warp_any(b); }
     __device__ __forceinline__ bool warp_any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
     __device__ __forceinline__ bool block_any(bool b) const { return __syncthreads_or(b) != 0; }
     // Max of a non-negative, finite per-thread value -> atomicMax on the bit pattern of *dst (for such values the
@@ -137,6 +150,9 @@ inline int dev_ones(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAs
 inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s); }
 inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s); }
 inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st.s); }
+inline int copy_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height, Stream st) {
+    return (int)cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, height, cudaMemcpyDeviceToHost, st.s);
+}
 inline int stream_sync(Stream st) { return (int)cudaStreamSynchronize(st.s); }
 
 #else
@@ -161,10 +177,19 @@ struct HostExec {
     void wphase(F&& f) {
         for (int t = 0; t < nthr; ++t) f(t);
     }
-    template <bool XS, int NS>
+    template <bool XS, int NS, bool BT = false>
     void put(int, double) {}
-    template <bool XS, int NS, class G>
-    double nbr(int tid, int, int delta, G&& get) { return lane(tid, delta, get); }
+    template <bool XS, int NS, bool BT = false, class G>
+    double nbr(int tid, int, int delta, G&& get) {
+        if (XS && BT) { const int k = tid + delta; return get(k < 0 ? 0 : (k >= nthr ? nthr - 1 : k)); }
+        return lane(tid, delta, get);
+    }
+    template <bool BLOCK, class F>
+    void xphase(F&& f) {
+        for (int t = 0; t < nthr; ++t) f(t);
+    }
+    template <bool BLOCK>
+    bool group_any(bool b) const { return b; }
     bool warp_any(bool b) const { return b; }      // the host simulation runs a block thread by thread: one guard per block
     bool block_any(bool b) const { return b; }
     template <class G>
@@ -211,6 +236,10 @@ inline int dev_ones(void* p, size_t bytes, Stream) { std::memset(p, 0xFF, bytes)
 inline int copy_h2d(void* d, const void* h, size_t bytes, Stream) { std::memcpy(d, h, bytes); return 0; }
 inline int copy_d2h(void* h, const void* d, size_t bytes, Stream) { std::memcpy(h, d, bytes); return 0; }
 inline int copy_d2d(void* d, const void* s, size_t bytes, Stream) { std::memcpy(d, s, bytes); return 0; }
+inline int copy_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height, Stream) {
+    for (size_t r = 0; r < height; ++r) std::memcpy((char*)h + r * hpitch, (const char*)d + r * dpitch, width);
+    return 0;
+}
 inline int stream_sync(Stream) { return 0; }
 #endif
 

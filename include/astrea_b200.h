@@ -111,6 +111,22 @@ int astrea_set_parity(astrea_ctx* ctx, int step_parity);
  * (calculate_TV, :48-62).  Deterministic (fixed reduction order).  external_rows as in astrea_run_instr. */
 int astrea_diagnostics(astrea_ctx* ctx, double* totals, double* total_variation, int external_rows);
 
+/* schemes/ppm.py:111-170 at function level: the two pieces ppm.run(dissipate=True) adds to the McCorquodale-Colella
+ * reconstruction.  The reference cannot take a time step with dissipate=True (ppm.py:67 raises a broadcast error), but
+ * both functions run on their own and are reproduced bit for bit.  ``ws_aos``: primitive cell averages in the sweep
+ * frame, host array of the context's grid shape whose axis 0 is the sweep direction (the reference passes
+ * convert_conservative(grid.transpose(axes))); ``axis``: the permutation key, i.e. the velocity component
+ * w[..., axis + 1].  Boundary mode = the context's.
+ *   astrea_ppm_flattener  = ppm.apply_flattener(wS, axis, boundary, slope_determinants) (ppm.py:111-134): chi, host array
+ *                           (nx[,ny]) — the reference returns it repeated over the 8 variables.  slope_determinants =
+ *                           {delta, z0, z1}, NULL for the reference's defaults {.33, .75, .85}.
+ *   astrea_ppm_viscosity  = ppm.apply_artificial_viscosity(wS, axis, sim_variables, viscosity_determinants)
+ *                           (ppm.py:138-170) read cell by cell: mu (nx, 8).  1D only: the reference's 2D branch raises
+ *                           at ppm.py:154-156, and so does this call (ASTREA_E_ARG).  viscosity_determinants = {alpha, beta},
+ *                           NULL for {.3, .3}. */
+int astrea_ppm_flattener(astrea_ctx* ctx, const double* ws_aos, int axis, const double* slope_determinants, double* chi);
+int astrea_ppm_viscosity(astrea_ctx* ctx, const double* ws_aos, int axis, const double* viscosity_determinants, double* mu_aos);
+
 /* magnetic_2d only: evolve_time overwrites the in-plane B of the caller's grid with face averages before the
  * stages (evolvers.py:73-76).  Copies those two components (host array (nx,ny,2): Bx, By). */
 int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);

@@ -216,6 +216,26 @@ def ppm_artificial_viscosity(wS, axis, cfg, knobs=(.3, .3)):
     return alpha * ((nu * np.ones_like(wS)) * np.diff(w[1:], axis=0))
 
 
+def ppm_artificial_viscosity_cellwise(wS, axis, cfg, knobs=(.3, .3)):
+    """ppm.py:138-170 in 1D, read cell by cell: nu_i = min(1, (dx*lambda_i)^2 / (beta*c_min,i^2)) * lambda_i.
+
+    PARITY UNPINNED: the reference's own line (ppm.py:164) multiplies an (N,) by an (N, 1) array and then fails to
+    broadcast against the (N, 8) state for every N != 8 (tests/golden/f_ppm_flattener.json records the errors), so
+    there is no reference output.  This is the formula of that line with both factors on the same index
+    [McCorquodale & Colella 2011, eq. 36-38]; the device kernel (DissipationKernel) is checked against it.
+    """
+    alpha, beta = knobs
+    bc, dx, gamma = cfg.boundary, cfg.dx, cfg.gamma
+    w = extended(wS, 1, 1, bc)
+    vel_w = w[..., axis + 1]
+    lam = vel_w[2:] - vel_w[1:-1]
+    cs = np.sqrt(safe_div(gamma * w[..., 4], w[..., 0]))
+    cmin = np.minimum(cs[1:-1], cs[2:])
+    nu = np.minimum(1, safe_div((dx * lam) ** 2, beta * cmin ** 2)) * lam
+    nu[lam >= 0] = 0
+    return alpha * (nu[..., None] * np.diff(w[1:], axis=0))
+
+
 def cell_states_ppm(wS, axis, cfg):
     """ppm.py:28-79 -> (wL, wR, wF) with wF the (possibly limited / flattened) face-i+1/2 value kept for CT."""
     bc, author = cfg.boundary, cfg.ppm_author.lower()

@@ -44,10 +44,9 @@ def _shift_and_conservation(ctx, g0, shift, steps=1):
     assert dts_a == dts_b
     a = np.roll(a, shift, axis=(0, 1))
     assert np.array_equal(a, b)
-    scale = np.abs(tot0)
-    cells = g0.shape[0] * g0.shape[1]
-    # sums of `cells` terms: relative round-off ~ sqrt(cells) * 2^-53, allow a wide margin
-    assert np.all(np.abs(tot1 - tot0) <= 1e-10 * np.where(scale > 0, scale, float(cells))), (tot0, tot1)
+    # sums of `cells` terms against the size of the terms (a total may cancel to ~0): round-off ~ sqrt(cells) * 2^-53
+    scale = np.abs(g0).sum(axis=(0, 1))
+    assert np.all(np.abs(tot1 - tot0) <= 1e-10 * np.where(scale > 0, scale, 1.0)), (tot0, tot1, scale)
 
 
 def test_config3_khi_4096_weno5_hllc():
