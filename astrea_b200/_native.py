@@ -35,6 +35,13 @@ class InitSpec(C.Structure):
                 ("nregions", C.c_int32), ("reserved", C.c_int32), ("regions", Region * MAX_REGIONS)]
 
 
+MAX_PROFILES = 4
+
+
+class InitProfile(C.Structure):
+    _fields_ = [("variable", C.c_int32), ("along", C.c_int32), ("values", C.POINTER(C.c_double))]
+
+
 class Cfg(C.Structure):
     """struct astrea_cfg."""
     _fields_ = [
@@ -93,12 +100,16 @@ _SIGNATURES = {
     "astrea_stream_handle": (C.c_uint64, [C.c_void_p]),
     "astrea_fp64_probe": (C.c_int, [C.c_void_p, _PD]),
     "astrea_init_piecewise": (C.c_int, [C.c_void_p, C.POINTER(InitSpec)]),
+    "astrea_init_profiles": (C.c_int, [C.c_void_p, C.POINTER(InitSpec), C.c_int, C.POINTER(InitProfile)]),
     "astrea_arith_check": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "astrea_launch_count": (C.c_int64, [C.c_void_p]),
     "astrea_save_state": (C.c_int, [C.c_void_p]),
     "astrea_restore_state": (C.c_int, [C.c_void_p]),
     "astrea_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_profile_read": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64)]),
+    "astrea_snapshot_begin": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int]),
+    "astrea_snapshot_wait": (C.c_int, [C.c_void_p, C.c_int64]),
+    "astrea_solution_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, _PD, C.c_int]),
     "astrea_ppm_flattener": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _PD, C.c_void_p]),
     "astrea_ppm_viscosity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _PD, C.c_void_p]),
     "astrea_host_alloc": (C.c_void_p, [C.c_int, C.c_uint64]),
@@ -231,6 +242,21 @@ class Context:
         self._check(self.lib.astrea_download(self._h, out.ctypes.data, int(primitive)))
         return out
 
+    def snapshot_begin(self, out, external_rows=False):
+        """Start the astrea.py:47 snapshot (primitive, transposed by ortho_axis) into ``out`` — shape (ny, nx, 8) in 2D —
+        and return a ticket; ``snapshot_wait(ticket)`` blocks until ``out`` is complete."""
+        want = (self.shape[1], self.shape[0], 8) if len(self.shape) == 3 else tuple(self.shape)
+        if (not isinstance(out, np.ndarray) or out.shape != want or out.dtype != np.float64 or not out.flags.c_contiguous
+                or not out.flags.writeable):
+            raise ValueError(f"out must be a writeable C-contiguous float64 array of shape {want}")
+        ticket = self.lib.astrea_snapshot_begin(self._h, out.ctypes.data, 1 if external_rows else 0)
+        if ticket < 0:
+            self._check(int(ticket))
+        return int(ticket)
+
+    def snapshot_wait(self, ticket):
+        self._check(self.lib.astrea_snapshot_wait(self._h, int(ticket)))
+
     def diagnostics(self, external_rows=False):
         """(totals[8], total_variation[8]) of the current grid, reduced on the device (functions/analytic.py:48-77)."""
         tot, tv = (C.c_double * 8)(), (C.c_double * 8)()
@@ -337,15 +363,37 @@ class Context:
         self._check(self.lib.astrea_fp64_probe(self._h, C.byref(t)))
         return t.value
 
-    def init_piecewise(self, spec):
-        """Initial conditions evaluated on the device (``initial.piecewise_spec``) instead of an upload."""
-        self._check(self.lib.astrea_init_piecewise(self._h, C.byref(spec)))
+    def init_piecewise(self, spec, profiles=()):
+        """Initial conditions evaluated on the device (``initial.piecewise_spec``) instead of an upload.  ``profiles``:
+        (variable, along, values) triples of separable 1-D profiles (``initial.separable_profiles``)."""
+        if not profiles:
+            self._check(self.lib.astrea_init_piecewise(self._h, C.byref(spec)))
+            return
+        arr = (InitProfile * len(profiles))()
+        keep = []
+        for k, (variable, along, values) in enumerate(profiles):
+            v = np.ascontiguousarray(values, dtype=np.float64)
+            if v.shape != (spec.cells,):
+                raise ValueError("a profile holds one value per cell centre")
+            keep.append(v)
+            arr[k].variable, arr[k].along = int(variable), int(along)
+            arr[k].values = v.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self.lib.astrea_init_profiles(self._h, C.byref(spec), len(profiles), arr))
 
     def arith_check(self, samples=1 << 24, seed=1):
         """(accepted, wrong, declined) of the branch-free division / square root against the IEEE routines."""
         counts = (C.c_uint64 * 3)()
         self._check(self.lib.astrea_arith_check(self._h, samples, seed, counts))
         return int(counts[0]), int(counts[1]), int(counts[2])
+
+    def solution_error(self, w_theo, norm, external_rows=False):
+        """Per-channel reduction of |w_num - w_theo| (functions/analytic.py:24-44) before normalisation: 10 doubles."""
+        w = np.ascontiguousarray(w_theo, dtype=np.float64)
+        if w.shape != tuple(self.shape):
+            raise ValueError(f"w_theo shape {w.shape} != {tuple(self.shape)}")
+        out = (C.c_double * 10)()
+        self._check(self.lib.astrea_solution_error(self._h, w.ctypes.data, float(norm), out, 1 if external_rows else 0))
+        return np.array(out)
 
     def ppm_flattener(self, ws, axis, slope_determinants=None):
         """ppm.apply_flattener (ppm.py:111-134) of primitive averages ``ws`` (sweep frame): chi, shape of the grid."""

@@ -97,6 +97,14 @@ struct astrea_ctx {
     int next_instr = 0;               // 0: nothing run for this step yet
     int tile1d = 0, threads1d = 0;
     bool stream_owned = false;
+    // snapshot path (astrea.py:47-50): device staging buffer, copy stream, events of the tickets in flight
+    static constexpr int SNAP_RING = 4;
+    double* snap_dev = nullptr;
+    int64_t snap_tickets = 0;
+#ifdef ASTREA_DEVICE_BUILD
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t snap_ready = nullptr, snap_done[SNAP_RING] = {nullptr, nullptr, nullptr, nullptr};
+#endif
     Reg saved;                        // astrea_save_state copy of the grid
     int saved_parity = 0;
     // optional per-launch timing (astrea_profile): event pairs per kernel class
@@ -819,7 +827,11 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->ws.mem); dev_free(c->ws2.mem); dev_free(c->wp.mem); dev_free(c->wm.mem);
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags); dev_free(c->lw_keys);
+    dev_free(c->snap_dev);
 #ifdef ASTREA_DEVICE_BUILD
+    if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
+    if (c->snap_ready) cudaEventDestroy(c->snap_ready);
+    for (auto& e : c->snap_done) if (e) cudaEventDestroy(e);
     for (auto& row : c->step_graph)
         for (auto& g : row)
             if (g) cudaGraphExecDestroy(g);
@@ -850,9 +862,13 @@ int astrea_upload(astrea_ctx* c, const double* grid_aos) {
     return 0;
 }
 
-int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
+int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) { return astrea_init_profiles(c, spec, 0, nullptr); }
+
+int astrea_init_profiles(astrea_ctx* c, const astrea_init_spec* spec, int nprofiles, const astrea_init_profile* profiles) {
     if (!c || !spec) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: NULL argument");
     ASTREA_ON_DEVICE(c);
+    if (nprofiles < 0 || nprofiles > ASTREA_MAX_PROFILES || (nprofiles > 0 && !profiles))
+        return fail(c, ASTREA_E_ARG, "astrea_init_profiles: at most 4 profiles");
     if (c->cfg.dimension != 2) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: 2D grids only");
     if (spec->cells < 1 || spec->cells != c->ncol) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: spec.cells must equal ny");
     if (spec->nregions < 0 || spec->nregions > ASTREA_MAX_REGIONS) return fail(c, ASTREA_E_ARG, "astrea_init_piecewise: too many regions");
@@ -869,6 +885,16 @@ int astrea_init_piecewise(astrea_ctx* c, const astrea_init_spec* spec) {
         for (int v = 0; v < NVAR; ++v) p.state[k + 1][v] = spec->regions[k].state[v];
     }
     p.mhd_flag = c->mhd_flag;
+    // the 1-D tables travel through the start of a scratch plane (cells doubles each; the planes are far larger)
+    p.nprofiles = nprofiles;
+    for (int k = 0; k < nprofiles; ++k) {
+        if (profiles[k].variable < 0 || profiles[k].variable >= NVAR || (profiles[k].along != 0 && profiles[k].along != 1) || !profiles[k].values)
+            return fail(c, ASTREA_E_ARG, "astrea_init_profiles: bad profile");
+        double* dst = c->d0.mem + (size_t)k * spec->cells;
+        if ((size_t)(k + 1) * spec->cells > c->plane_doubles) return fail(c, ASTREA_E_ARG, "astrea_init_profiles: grid too small for the tables");
+        ASTREA_TRY(copy_h2d(dst, profiles[k].values, (size_t)spec->cells * sizeof(double), c->st));
+        p.prof_var[k] = profiles[k].variable; p.prof_along[k] = profiles[k].along; p.prof_tab[k] = dst;
+    }
     ASTREA_TRY(dev_zero(c->mhd_flag, sizeof(int), c->st));
     ASTREA_TRY(dev_zero(c->flag, sizeof(unsigned long long), c->st));
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<InitKernel>(p, (int)((c->ncol + 127) / 128), (int)c->nrow, 128, 0, c->st)); }
@@ -901,6 +927,66 @@ int astrea_download(astrea_ctx* c, double* grid_aos, int as_primitive) {
     { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
     ASTREA_TRY(copy_d2h(grid_aos, staging, bytes, c->st));
     return stream_sync(c->st) == 0 ? 0 : fail(c, ASTREA_E_CUDA, "astrea_download: stream sync failed");
+}
+
+int64_t astrea_snapshot_begin(astrea_ctx* c, double* host_dst, int external_rows) {
+    if (!c || !host_dst) return fail(c, ASTREA_E_ARG, "astrea_snapshot_begin: NULL argument");
+    ASTREA_ON_DEVICE(c);
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_snapshot_begin: a step is in flight");
+    if (!external_rows && c->slab() && scheme_high_order(c->cfg.scheme))
+        return fail(c, ASTREA_E_STATE, "astrea_snapshot_begin: the 4th-order primitive snapshot of a slab reads ghost rows: exchange them first and pass external_rows = 1");
+    const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
+    if (!c->snap_dev) {
+        c->snap_dev = (double*)dev_alloc(bytes);
+        if (!c->snap_dev) return fail(c, ASTREA_E_CUDA, "astrea_snapshot_begin: device allocation failed");
+#ifdef ASTREA_DEVICE_BUILD
+        cudaError_t e = cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->snap_ready, cudaEventDisableTiming);
+        for (auto& ev : c->snap_done) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail(c, ASTREA_E_CUDA, std::string("astrea_snapshot_begin: ") + cudaGetErrorString(e));
+#endif
+    }
+    const int64_t ticket = c->snap_tickets;
+#ifdef ASTREA_DEVICE_BUILD
+    // the staging buffer is free once the previous snapshot has left the device; the ticket's event slot once its
+    // previous user (SNAP_RING tickets ago) has been waited for by the host or has simply completed
+    if (ticket > 0) ASTREA_TRY((int)cudaStreamWaitEvent(c->st.s, c->snap_done[(ticket - 1) % astrea_ctx::SNAP_RING], 0));
+#endif
+    Plane src = c->regs[c->grid_reg].plane;
+    if (int e = fill_halo(c, src, external_rows)) return e;
+    Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r);
+    PrimParams pp{src, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    if (c->cfg.dimension == 2) {
+        PackTransposedParams tp{w, c->snap_dev, c->nrow, c->ncol};
+        Timed timed(c, CLS_TRANSPOSE);
+        ASTREA_TRY(launch<PackTransposedKernel>(tp, (int)((c->ncol + 31) / 32), (int)((c->nrow + 31) / 32), 256, PackTransposedKernel::smem_bytes(), c->st));
+    } else {
+        PackParams p{w, c->snap_dev, c->nrow, c->ncol, 0, nullptr};
+        Timed timed(c, CLS_HALO);
+        ASTREA_TRY(launch<PackKernel>(p, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st));
+    }
+#ifdef ASTREA_DEVICE_BUILD
+    ASTREA_TRY((int)cudaEventRecord(c->snap_ready, c->st.s));
+    ASTREA_TRY((int)cudaStreamWaitEvent(c->copy_st, c->snap_ready, 0));
+    ASTREA_TRY((int)cudaMemcpyAsync(host_dst, c->snap_dev, bytes, cudaMemcpyDeviceToHost, c->copy_st));
+    ASTREA_TRY((int)cudaEventRecord(c->snap_done[ticket % astrea_ctx::SNAP_RING], c->copy_st));
+#else
+    std::memcpy(host_dst, c->snap_dev, bytes);
+#endif
+    c->snap_tickets = ticket + 1;
+    return ticket;
+}
+
+int astrea_snapshot_wait(astrea_ctx* c, int64_t ticket) {
+    if (!c) return ASTREA_E_ARG;
+    ASTREA_ON_DEVICE(c);
+    if (ticket < 0 || ticket >= c->snap_tickets) return fail(c, ASTREA_E_ARG, "astrea_snapshot_wait: no such ticket");
+    if (ticket + astrea_ctx::SNAP_RING < c->snap_tickets) return 0;        // its event slot has been reused: long done (stream order)
+#ifdef ASTREA_DEVICE_BUILD
+    if (cudaEventSynchronize(c->snap_done[ticket % astrea_ctx::SNAP_RING]) != cudaSuccess) return fail(c, ASTREA_E_CUDA, "astrea_snapshot_wait: event sync failed");
+#endif
+    return 0;
 }
 
 int astrea_diagnostics(astrea_ctx* c, double* totals, double* total_variation, int external_rows) {
@@ -982,6 +1068,39 @@ int astrea_ppm_viscosity(astrea_ctx* c, const double* ws_aos, int axis, const do
     ASTREA_ON_DEVICE(c);
     const double standard[2] = {.3, .3};                             // ppm.py:139
     return run_dissipation(c, ws_aos, axis, 1, viscosity_determinants ? viscosity_determinants : standard, mu_aos);
+}
+
+int astrea_solution_error(astrea_ctx* c, const double* w_theo_aos, double norm, double* error, int external_rows) {
+    if (!c || !w_theo_aos || !error) return fail(c, ASTREA_E_ARG, "astrea_solution_error: NULL argument");
+    ASTREA_ON_DEVICE(c);
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_solution_error: a step is in flight");
+    Plane q = c->regs[c->grid_reg].plane;
+    if (int e = fill_halo(c, q, external_rows)) return e;
+    // numerical primitives -> qT (as astrea_download(as_primitive)), theoretical primitives -> rates[0]
+    Plane w = make_plane(c->qT.mem, c->ncol, c->ghost_r), theo = c->rates[0].plane;
+    PrimParams pp{q, w, c->nrow, c->ncol, c->cfg.dimension, scheme_high_order(c->cfg.scheme) ? 1 : 0, c->cfg.gamma};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PrimKernel>(pp, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    const size_t bytes = (size_t)c->nrow * c->ncol * NVAR * sizeof(double);
+    double* staging = c->d0.mem;
+    ASTREA_TRY(copy_h2d(staging, w_theo_aos, bytes, c->st));
+    PackParams pk{theo, staging, c->nrow, c->ncol, 1, nullptr};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<PackKernel>(pk, (int)((c->ncol + 255) / 256), (int)c->nrow, 256, 0, c->st)); }
+    const int gx = (int)((c->ncol + 255) / 256), gy = (int)c->nrow;
+    const size_t n = (size_t)gx * gy * ERR_CHANNELS;
+    double* partial = staging;          // the staging copy has been consumed (stream order)
+    ErrorParams ep{w, theo, c->nrow, c->ncol, c->cfg.gamma, norm, partial};
+    { Timed timed(c, CLS_HALO); ASTREA_TRY(launch<ErrorKernel>(ep, gx, gy, 256, ErrorKernel::smem_bytes(), c->st)); }
+    std::vector<double> host(n);
+    ASTREA_TRY(copy_d2h(host.data(), partial, n * sizeof(double), c->st));
+    if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_solution_error: stream sync failed");
+    const bool use_max = norm > 10.0;
+    for (int k = 0; k < ERR_CHANNELS; ++k) error[k] = 0.0;
+    for (size_t b = 0; b < (size_t)gx * gy; ++b)
+        for (int k = 0; k < ERR_CHANNELS; ++k) {
+            const double x = host[b * ERR_CHANNELS + k];
+            error[k] = use_max ? npmax(error[k], x) : error[k] + x;
+        }
+    return 0;
 }
 
 int astrea_fp64_probe(astrea_ctx* c, double* tflops) {

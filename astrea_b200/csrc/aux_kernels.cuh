@@ -38,6 +38,44 @@ struct PackKernel {
     }
 };
 
+// plane -> AoS with the two grid axes swapped: aos[(c * nrow + r) * 8 + v] = plane(r, v, c), the layout astrea.py:47
+// stores (``.transpose(ortho_axis)``, ortho_axis = (1, 0, 2) in 2D).  32 x 32 cell tiles through shared memory so that
+// both the plane reads (along c) and the AoS writes (along r, 64 B per cell) are contiguous.
+struct PackTransposedParams {
+    Plane plane;
+    double* aos;          // device buffer (ncol, nrow, 8) C-order
+    int64_t nrow, ncol;
+};
+struct PackTransposedKernel {
+    using Params = PackTransposedParams;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TILE = 32;
+    static size_t smem_bytes() { return sizeof(double) * NVAR * TILE * (TILE + 1); }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        double* tile = ex.smem();          // [v][r][c + pad]
+        const int64_t c0 = (int64_t)bx * TILE, r0 = (int64_t)by * TILE;
+        ex.phase([&](int tid) {
+            const int tx = tid % TILE;
+            for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
+                const int64_t r = r0 + ty, c = c0 + tx;
+                if (r < p.nrow && c < p.ncol) {
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v) tile[(v * TILE + ty) * (TILE + 1) + tx] = *p.plane.at(r, v, c);
+                }
+            }
+        });
+        ex.phase([&](int tid) {
+            // consecutive threads write consecutive doubles of the output: (c fixed, r running, v fastest)
+            for (int e = tid; e < TILE * TILE * NVAR; e += MAX_THREADS) {
+                const int v = e % NVAR, ty = (e / NVAR) % TILE, tx = e / (NVAR * TILE);
+                const int64_t r = r0 + ty, c = c0 + tx;
+                if (r < p.nrow && c < p.ncol) p.aos[(c * p.nrow + r) * NVAR + v] = tile[(v * TILE + ty) * (TILE + 1) + tx];
+            }
+        });
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ halo fill
 struct HaloParams {
     Plane plane;
@@ -633,6 +671,7 @@ struct Fp64ProbeKernel {
 // The square N x N problem is evaluated on the fly at base cell ((row + x_off) mod N, col), which also tiles it
 // periodically along x for the slab-decomposed weak-scaling runs (initial.initial_slab).
 constexpr int MAX_REGIONS = 8;
+constexpr int MAX_PROFILES = 4;
 enum RegionKind : int { REG_X_LT = 0, REG_X_LE = 1, REG_Y_LE = 2, REG_X_LE_Y_GE = 3, REG_X_GT_Y_GE = 4, REG_DISC_LE = 5 };
 struct InitParams {
     Plane out;
@@ -645,6 +684,12 @@ struct InitParams {
     double a[MAX_REGIONS], b[MAX_REGIONS];     // threshold(s): shock position, or (centre, radius^2) for a disc
     double state[MAX_REGIONS + 1][NVAR];       // state[0]: background (initial_right); state[k + 1]: region k
     int* mhd_flag;
+    // separable profiles painted over the regions (constructor.py:44, :64-67): variable prof_var[k] of the point (i, j)
+    // becomes prof_tab[k][prof_along[k] == 0 ? i : j]; the n-entry tables are evaluated on the host with numpy, so the
+    // transcendental function is the reference's own
+    int nprofiles;
+    int prof_var[MAX_PROFILES], prof_along[MAX_PROFILES];
+    const double* prof_tab[MAX_PROFILES];
 };
 struct InitKernel {
     using Params = InitParams;
@@ -667,6 +712,7 @@ struct InitKernel {
         }
 #pragma unroll
         for (int v = 0; v < NVAR; ++v) w[v] = p.state[pick][v];
+        for (int k = 0; k < p.nprofiles; ++k) w[p.prof_var[k]] = p.prof_tab[k][p.prof_along[k] == 0 ? i : j];
     }
     // conservative point / 4th-order value at base cell (i, j) before the final Laplacian (initial._cons_from_point_prim)
     static HD void cons_at(const Params& p, int64_t i, int64_t j, double* q) {
@@ -841,6 +887,62 @@ struct DiagKernel {
             }
             ex.phase([&](int tid) {
                 if (tid == 0) p.partial[((int64_t)by * ((p.ncol + NT - 1) / NT) + bx) * 2 * NVAR + k] = red[0];
+            });
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ solution error
+// functions/analytic.py:24-44 calculate_solution_error: per-channel norm of (numerical - theoretical) primitive cell
+// averages over the grid, for the 8 primitive variables plus the specific total energy E_tot = e(P -> e_tot) / rho and
+// the specific internal energy E_int = P / (rho (gamma - 1)) (:33-37).  One partial result per block and channel,
+// combined on the host in block order (deterministic; the summation order differs from numpy's pairwise sum).
+constexpr int ERR_CHANNELS = NVAR + 2;
+struct ErrorParams {
+    Plane num, theo;      // primitive snapshots: of the current grid (PrimKernel), of the initial state (uploaded)
+    int64_t nrow, ncol;
+    double gamma, norm;   // norm > 10: maximum; norm <= 0: plain sum of |d|; else sum of |d|^norm
+    double* partial;      // [gridDim.y * gridDim.x][ERR_CHANNELS]
+};
+struct ErrorKernel {
+    using Params = ErrorParams;
+    static constexpr int MAX_THREADS = 256;
+    static size_t smem_bytes() { return sizeof(double) * MAX_THREADS; }
+    static HD void channels(const double* w, double gamma, double* out) {
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) out[v] = w[v];
+        const double e = w[4] / (gamma - 1.0) + 0.5 * (w[0] * norm3sq(w[1], w[2], w[3]) + norm3sq(w[5], w[6], w[7]));   // fv.py:50
+        out[NVAR] = sdiv(e, w[0]);
+        out[NVAR + 1] = sdiv(w[4], w[0] * (gamma - 1.0));
+    }
+    template <class Ex>
+    static HD void block(const Params& p, int bx, int by, Ex& ex) {
+        const int NT = ex.nthreads();
+        double* red = ex.smem();
+        const int64_t r = by;
+        const bool use_max = p.norm > 10.0;
+        for (int k = 0; k < ERR_CHANNELS; ++k) {
+            ex.phase([&](int tid) {
+                const int64_t c = (int64_t)bx * NT + tid;
+                double x = 0.0;
+                if (c < p.ncol) {
+                    double a[NVAR], b[NVAR], ca[ERR_CHANNELS], cb[ERR_CHANNELS];
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v) { a[v] = *p.num.at(r, v, c); b[v] = *p.theo.at(r, v, c); }
+                    channels(a, p.gamma, ca);
+                    channels(b, p.gamma, cb);
+                    const double d = fabs(ca[k] - cb[k]);
+                    x = (use_max || p.norm <= 0.0 || p.norm == 1.0) ? d : (p.norm == 2.0 ? d * d : pow(d, p.norm));
+                }
+                red[tid] = x;
+            });
+            for (int stride = NT / 2; stride > 0; stride >>= 1) {
+                ex.phase([&](int tid) {
+                    if (tid < stride) red[tid] = use_max ? npmax(red[tid], red[tid + stride]) : red[tid] + red[tid + stride];
+                });
+            }
+            ex.phase([&](int tid) {
+                if (tid == 0) p.partial[((int64_t)by * ((p.ncol + NT - 1) / NT) + bx) * ERR_CHANNELS + k] = red[0];
             });
         }
     }

@@ -241,6 +241,19 @@ def initial_state(config, cells, dimension, gamma=1.4, high_order=True, boundary
     return _cons_from_point_prim(w, gamma, bc, high_order, dimension)
 
 
+def theoretical_primitives(config, cells, dimension, gamma=1.4, boundary=None):
+    """constructor.initialise(sim_variables) with its default convert=False: cell averages of the *primitive* initial
+    data (fv.high_order_convert('cntr', ...), constructor.py:109) — what analytic.calculate_solution_error compares the
+    primitive snapshot with (analytic.py:31)."""
+    prob = problem(config, cells, gamma)
+    bc = boundary or prob["boundary"]
+    w = primitive_points(config, cells, dimension, gamma, prob)
+    out = np.copy(w)
+    for ax in range(dimension):
+        out += 1 / 24 * _d2(w, bc, ax)
+    return out
+
+
 def initial_slab(config, cells_x, cells_y, x_offset, cells_x_total, gamma=1.4, high_order=True):
     """Rows [x_offset, x_offset+cells_x) of an (cells_x_total x cells_y) periodic domain tiled from the square
     ``cells_y x cells_y`` problem (period cells_y along x).  Used by the slab-decomposed weak-scaling runs, which the
@@ -250,9 +263,28 @@ def initial_slab(config, cells_x, cells_y, x_offset, cells_x_total, gamma=1.4, h
     return np.ascontiguousarray(base[rows])
 
 
+def separable_profiles(config, cells, gamma=1.4):
+    """(variable, along, values) for the 2D problems whose perturbation is a function of x only or of y only
+    (constructor.py:42-44 Kelvin-Helmholtz, :62-67 Orszag-Tang): the reference's own numpy expression, evaluated on the
+    1-D array of cell centres instead of the meshgrid (elementwise, so every value has the reference's bits); the
+    device expands the tables (``astrea_init_profiles``).  along = 0: function of x (first index), 1: of y."""
+    c = config.lower()
+    prob = problem(c, cells, gamma)
+    lo, hi, par = prob["start_pos"], prob["end_pos"], prob["misc"]
+    pts = cell_centres(lo, hi, cells)
+    pi = np.pi
+    if "kelvin" in c or "helmholtz" in c or c == "khi":
+        return [(2, 0, par["perturb_ampl"] * np.sin(par["freq"] * pi * pts / (hi - lo)))]
+    if c in ("orszag-tang", "orszag", "tang", "ot"):
+        return [(1, 1, -np.sin(2 * pi * pts)), (2, 0, np.sin(2 * pi * pts)),
+                (5, 1, -par["ampl"] * np.sin(2 * pi * pts)), (6, 0, par["ampl"] * np.sin(4 * pi * pts))]
+    return []
+
+
 def piecewise_spec(config, cells, gamma=1.4):
-    """The ``astrea_init_spec`` of a 2D problem whose pointwise primitive state is piecewise constant, or None (problems
-    with sine / exponential profiles stay on the host: libm's functions are not reproducible bit for bit on the device).
+    """The ``astrea_init_spec`` of a 2D problem whose pointwise primitive state is piecewise constant up to separable
+    profiles (``separable_profiles``), or None (radial exponential profiles — Gauss, isentropic vortex — stay on the
+    host: they are not separable and libm's exp is not reproducible bit for bit on the device).
     Regions are listed in the order constructor.py:33-75 assigns them; later ones paint over earlier ones."""
     from . import _native as N
     c = config.lower()
@@ -262,9 +294,10 @@ def piecewise_spec(config, cells, gamma=1.4):
     mid = (hi + lo) / 2
     if c == "sedov" or "blast" in c or "rotor" in c:
         regions = [(N.REGION_DISC_LE, mid, (shock - mid) ** 2, left)]
-    elif c.startswith("gauss") or "kelvin" in c or "helmholtz" in c or c == "khi" or c in ("ivc", "vortex", "isentropic vortex") \
-            or c in ("orszag-tang", "orszag", "tang", "ot"):
+    elif c.startswith("gauss") or c in ("ivc", "vortex", "isentropic vortex"):
         return None
+    elif "kelvin" in c or "helmholtz" in c or c == "khi" or c in ("orszag-tang", "orszag", "tang", "ot"):
+        regions = [(N.REGION_Y_LE, shock, 0.0, left)]
     elif "ll" in c or "lax-liu" in c:
         regions = [(N.REGION_X_LE, shock, 0.0, left), (N.REGION_X_LE_Y_GE, shock, 0.0, par["bottom_left"]),
                    (N.REGION_X_GT_Y_GE, shock, 0.0, par["bottom_right"])]

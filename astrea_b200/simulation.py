@@ -14,7 +14,7 @@ import ctypes
 import numpy as np
 
 from . import _native as N
-from .initial import initial_slab, initial_state, piecewise_spec, problem
+from .initial import initial_slab, initial_state, piecewise_spec, problem, separable_profiles
 from .selectors import MAGNETIC_2D, make_cfg, scheme_enum, stages_of
 
 
@@ -178,11 +178,12 @@ class Simulation:
         self._updates = self.ctx.updates()
         self._readers = self.ctx.halo_readers()    # instructions that read ghost rows (operators, refine_grid)
         self._halo_ready = False          # the ghost rows of the grid were already exchanged behind the last update
+        self._snap_pool = None
         self.overlap = overlap
         # piecewise-constant problems are initialised on the device (astrea_init_piecewise): nothing crosses PCIe
         spec = piecewise_spec(self.config, self.cells, gamma) if (grid is None and dimension == 2 and device_init) else None
         if spec is not None:
-            self.ctx.init_piecewise(spec)
+            self.ctx.init_piecewise(spec, separable_profiles(self.config, self.cells, gamma))
         else:
             self.ctx.upload(self.initial_grid() if grid is None else grid)
 
@@ -310,9 +311,27 @@ class Simulation:
         return self.ctx.download(primitive=primitive)
 
     def snapshot(self):
-        """What astrea.py:47-50 stores per step: the primitive grid transposed by ``ortho_axis`` ((y, x, 8) in 2D)."""
-        w = self.state(primitive=True)
-        return w.transpose(1, 0, 2) if self.dimension == 2 else w
+        """What astrea.py:47-50 stores per step: the primitive grid transposed by ``ortho_axis`` ((y, x, 8) in 2D).
+        Conversion and transpose run on the device; this call waits for the copy (``snapshot_async`` does not)."""
+        out, ticket = self.snapshot_async()
+        self.ctx.snapshot_wait(ticket)
+        return out
+
+    def snapshot_async(self, out=None):
+        """Start a snapshot and return ``(array, ticket)`` at once: the device converts and transposes, a second stream
+        copies into page-locked host memory, and the steps enqueued next run meanwhile.  The array is complete after
+        ``ctx.snapshot_wait(ticket)`` — the moment the reference would hand it to h5py (astrea.py:48-50)."""
+        if out is None:
+            if self._snap_pool is None:
+                self._snap_pool = N.PinnedPool(self.ctx.lib, self.cfg.device)
+            shape = (self.cells, self.nx_local, 8) if self.dimension == 2 else (self.cells, 8)
+            out = self._snap_pool.empty(shape)
+        external = False
+        if self.exchange is not None:
+            self.exchange.halo(0)                  # the 4th-order conversion reads one ghost row
+            self._halo_ready = False
+            external = True
+        return out, self.ctx.snapshot_begin(out, external_rows=external)
 
     def diagnostics(self):
         """Conservation totals (times the box volume, functions/analytic.py:66-77) and total variation (:48-62) of the
@@ -332,8 +351,34 @@ class Simulation:
         box = abs(self.end_pos - self.start_pos) ** self.dimension
         return tot * box, tv
 
+    def solution_error(self, norm=1):
+        """analytic.calculate_solution_error(grid, sim_variables, norm) (functions/analytic.py:24-44) of the current grid
+        against the initial state, reduced on the device: 10 values (8 primitives, E_tot / rho, E_int)."""
+        from .initial import theoretical_primitives
+        theo = theoretical_primitives(self.config, self.cells, self.dimension, self.gamma, self.boundary)
+        if self.exchange is not None:
+            theo = theo[self.x_offset:self.x_offset + self.nx_local] if self.nx_global == self.cells else None
+            if theo is None:
+                raise ValueError("solution_error: the theoretical state exists for the reference's square grids only")
+            self.exchange.halo(0)
+            self._halo_ready = False
+            part = self.ctx.solution_error(theo, norm, external_rows=True)
+            torch = self.exchange.torch
+            where = torch.device("cuda", self.exchange.device_index) if self.on_device else torch.device("cpu")
+            t = torch.tensor(part, dtype=torch.float64, device=where)
+            self.exchange.dist.all_reduce(t, op=self.exchange.dist.ReduceOp.MAX if norm > 10 else self.exchange.dist.ReduceOp.SUM)
+            part = t.cpu().numpy()
+        else:
+            part = self.ctx.solution_error(theo, norm)
+        if norm > 10:
+            return part
+        factor = 1 / (self.cells ** self.dimension)
+        return factor * part if norm <= 0 else (factor * part) ** (1 / norm)
+
     def sync(self):
         self.ctx.sync()
 
     def close(self):
         self.ctx.close()
+        if self._snap_pool is not None:
+            self._snap_pool.close()

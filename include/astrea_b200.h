@@ -79,6 +79,17 @@ int astrea_upload(astrea_ctx* ctx, const double* grid_aos);
  * the ghost rows of instruction 0, which the 4th-order conversion reads. */
 int astrea_download(astrea_ctx* ctx, double* grid_aos, int as_primitive);
 
+/* The per-step snapshot of astrea.py:47-50 off the critical path: sim_variables.convert_conservative(grid) transposed by
+ * ortho_axis — host layout (ny, nx, 8) in 2D, (nx, 8) in 1D, the array the reference hands to h5py.  astrea_snapshot_begin
+ * enqueues the primitive conversion and the transposing pack on the context's stream, then the device-to-host copy on a
+ * second stream, and returns a ticket (>= 0) without waiting: the next steps may be enqueued right away and run while the
+ * snapshot travels.  ``host_dst`` must stay valid until astrea_snapshot_wait(ticket) has returned; give it page-locked
+ * memory (astrea_host_alloc) for the copy to overlap.  One device staging buffer of the grid's size is allocated on first
+ * use; the next snapshot's conversion waits on the device for the previous copy.  external_rows as in astrea_download
+ * (as_primitive == 2).  Negative return: ASTREA_E_*. */
+int64_t astrea_snapshot_begin(astrea_ctx* ctx, double* host_dst, int external_rows);
+int astrea_snapshot_wait(astrea_ctx* ctx, int64_t ticket);
+
 /* evolvers.evolve_space(grid, sim_variables) for the uploaded grid (astrea.py:67).  step_parity = number of
  * permutation reversals so far mod 2 (astrea.py:85).  eigmax[a] receives fluxes[axes_a]['eigmax'] for
  * sweep axis a = 0..dimension-1 (astrea.py:70).  Returns ASTREA_E_NONFINITE where fv.py:158 would raise. */
@@ -110,6 +121,14 @@ int astrea_set_parity(astrea_ctx* ctx, int step_parity);
  * box-width factor); total_variation[8] = sum of |np.diff along every axis in turn| of the primitive snapshot
  * (calculate_TV, :48-62).  Deterministic (fixed reduction order).  external_rows as in astrea_run_instr. */
 int astrea_diagnostics(astrea_ctx* ctx, double* totals, double* total_variation, int external_rows);
+
+/* functions/analytic.py:24-44 calculate_solution_error, reduced on the device: error[10] = over the (local) cells, per
+ * channel (the 8 primitive variables, E_tot / rho, E_int: analytic.py:33-37), the maximum (norm > 10), the sum (norm <= 0)
+ * or the sum of the norm-th powers of |w_num - w_theo|, where w_num is the primitive snapshot of the current grid
+ * (astrea.py:47) and ``w_theo_aos`` the caller's theoretical state (constructor.initialise(sim_variables), host array of
+ * the grid's shape).  The caller applies the normalising factor 1 / cells^dimension and the 1 / norm root
+ * (analytic.py:39-44), after summing over ranks on a decomposed grid.  Deterministic reduction order. */
+int astrea_solution_error(astrea_ctx* ctx, const double* w_theo_aos, double norm, double* error, int external_rows);
 
 /* schemes/ppm.py:111-170 at function level: the two pieces ppm.run(dissipate=True) adds to the McCorquodale-Colella
  * reconstruction.  The reference cannot take a time step with dissipate=True (ppm.py:67 raises a broadcast error), but
@@ -218,6 +237,20 @@ typedef struct astrea_init_spec {
     astrea_region regions[ASTREA_MAX_REGIONS];
 } astrea_init_spec;
 int astrea_init_piecewise(astrea_ctx* ctx, const astrea_init_spec* spec);
+/* The same with up to ASTREA_MAX_PROFILES separable profiles painted over the regions, for the problems whose
+ * perturbation depends on x or on y only — Kelvin-Helmholtz (constructor.py:42-44: v_y = ampl*sin(freq*pi*x/(hi-lo)))
+ * and Orszag-Tang (:62-67: v_x, B_x from sin(2*pi*y); v_y, B_y from sin(2*pi*x), sin(4*pi*x)), BASELINE configs 3 and 4.
+ * ``values`` is the profile on the ``cells`` cell centres, evaluated by the caller with the reference's own numpy
+ * expression on the 1-D coordinate array (so the transcendental function is bit for bit the reference's); primitive
+ * variable ``variable`` of point (i, j) becomes values[along == 0 ? i : j].  Uploads cells doubles per profile instead
+ * of the 8 * cells^2 of the finished grid (1 GB at 4096^2). */
+#define ASTREA_MAX_PROFILES 4
+typedef struct astrea_init_profile {
+    int32_t variable;                /* 0..7: rho, vx, vy, vz, P, Bx, By, Bz */
+    int32_t along;                   /* 0: function of x (row index), 1: function of y (column index) */
+    const double* values;            /* host array, spec->cells entries */
+} astrea_init_profile;
+int astrea_init_profiles(astrea_ctx* ctx, const astrea_init_spec* spec, int nprofiles, const astrea_init_profile* profiles);
 
 /* Self-check of the device arithmetic (no reference counterpart; the reference's divisions and square roots are
  * numpy's IEEE ones, fv.py:19-20,37-38).  The kernels evaluate every division and square root with a branch-free

@@ -9,6 +9,9 @@ f_ppm_flattener.npz   schemes/ppm.py:111-134 ``apply_flattener(wS, axis, boundar
                       the coefficient ``chi = eta[..., 0]`` (the reference repeats it over the 8 variables).
                       Also the same states with strengthened pressure jumps (``sharp``), which reach the
                       z > z1 and the compressive-and-weak branches.
+f_solution_error.npz  functions/analytic.py:24-44 ``calculate_solution_error(w, sim_variables, norm)`` on the primitive
+                      snapshot (astrea.py:47) of a few smooth problems after a few steps of the reference's own loop, for
+                      norm = 0, 1, 2, 3 and 11 (maximum): the conservative grid the snapshot was made of and the 10 errors.
 ``apply_artificial_viscosity`` (ppm.py:138-170) cannot produce vectors: it raises a broadcast error for every 1D grid
 with N != 8 cells and for every 2D grid (ppm.py:164 / :154-156); recorded here as ``viscosity_raises``.
 """
@@ -67,5 +70,34 @@ def main():
         json.dump(meta, fh, indent=1, sort_keys=True)
 
 
+ERROR_CASES = [("sin", 64, 1, "ppm", "hllc", "ssprk(3,3)", 5), ("sin", 50, 1, "plm", "lf", "ssprk(2,2)", 4),
+               ("gauss", 32, 2, "weno5", "lf", "ssprk(3,3)", 3), ("gauss", 96, 1, "weno7", "hllc", "rk4", 3),
+               ("ivc", 24, 2, "ppm", "hllc", "ssprk(3,3)", 2)]
+
+
+def solution_error():
+    rh._import_ref()
+    from functions import analytic
+    out, meta = {}, {}
+    for config, cells, dim, subgrid, solver, timestep, steps in ERROR_CASES:
+        sv = rh.make_sim_variables(config, cells, dim, subgrid, solver, timestep)
+        g0 = rh.initial_grid(sv)
+        grids, dts, _, _ = rh.run_steps(sv, steps, grid=np.copy(g0))
+        g = grids[-1]
+        with np.errstate(all="ignore"):
+            w = sv.convert_conservative(np.copy(g), sv)
+            key = f"{config}|{cells}|{dim}|{subgrid}"
+            out[key + "|g"] = g
+            for norm in (0, 1, 2, 3, 11):
+                out[key + f"|err{norm}"] = analytic.calculate_solution_error(np.copy(w), sv, norm)
+        meta[key] = dict(config=config, cells=cells, dimension=dim, subgrid=subgrid, solver=solver, timestep=timestep, steps=steps,
+                         boundary=sv.boundary, gamma=sv.gamma)
+        print(key, out[key + "|err1"][:5])
+    np.savez_compressed(os.path.join(HERE, "f_solution_error.npz"), **out)
+    with open(os.path.join(HERE, "f_solution_error.json"), "w") as fh:
+        json.dump(meta, fh, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     main()
+    solution_error()

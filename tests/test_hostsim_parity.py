@@ -582,3 +582,29 @@ def test_split_update_on_short_slabs(hostsim_lib, rows):
         for whole, part in zip(sent[0], sent[1]):
             a, b = whole.reshape(-1, 8, width)[..., g:-g], part.reshape(-1, 8, width)[..., g:-g]
             assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_async_snapshots_while_stepping(hostsim_lib):
+    """astrea.py:47-50 off the critical path: a snapshot started before further steps are enqueued holds the state of
+    its own step (primitive, transposed by ortho_axis), for ragged sizes, 1D, and more tickets than event slots."""
+    from astrea_b200.simulation import Simulation
+    from cases import oracle_cfg
+    from oracle.gridops import prim_avg_of_cons_avg
+    for config, cells, dim, subgrid in (("ll6", 45, 2, "ppm"), ("khi", 33, 2, "plm"), ("sod", 77, 1, "weno5")):
+        sim = Simulation(config, cells, dim, subgrid, "hllc", "ssprk(3,3)", _lib=hostsim_lib)
+        meta = _meta(config, cells, dim, subgrid, "hllc", "ssprk(3,3)", None)
+        shots, states = [], []
+        sim.set_time(0.0)
+        for n in range(6):
+            states.append(None)
+            shots.append(sim.snapshot_async())
+            states[-1] = sim.state()                   # the conservative grid the snapshot was taken of
+            sim.step_async()
+        for (out, ticket), q in zip(shots, states):
+            sim.ctx.snapshot_wait(ticket)
+            want = prim_avg_of_cons_avg(q, oracle_cfg(meta))
+            want = want.transpose(1, 0, 2) if dim == 2 else want
+            assert np.array_equal(out, want, equal_nan=True), (config, ticket)
+        with pytest.raises(ValueError):
+            sim.ctx.snapshot_begin(np.empty((3, 3, 8)))
+        sim.close()

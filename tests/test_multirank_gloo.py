@@ -35,6 +35,7 @@ def _worker(rank, world, rendezvous, spec, outdir):
     t, n, last = sim.time()
     assert n == steps and sim.ctx.dt_history(steps) == dts, (sim.ctx.dt_history(steps), dts)
     np.save(os.path.join(outdir, f"aslab{rank}.npy"), sim.state())
+    np.save(os.path.join(outdir, f"snap{rank}.npy"), sim.snapshot())         # astrea.py:47 of this rank's rows: (ny, rows, 8)
     sim.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -67,12 +68,15 @@ def test_two_ranks_equal_one(hostsim_lib, spec, world):
     single = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, grid=g0, _lib=hostsim_lib)
     want_dts = single.run(steps)
     want = single.state()
+    want_snapshot = single.snapshot()
     single.close()
     with tempfile.TemporaryDirectory() as tmp:
         np.save(os.path.join(tmp, "g0.npy"), g0)
         mp.spawn(_worker, args=(world, os.path.join(tmp, "rdv"), spec, tmp), nprocs=world, join=True)
         got = np.concatenate([np.load(os.path.join(tmp, f"slab{r}.npy")) for r in range(world)], axis=0)
         again = np.concatenate([np.load(os.path.join(tmp, f"aslab{r}.npy")) for r in range(world)], axis=0)
+        snapshot = np.concatenate([np.load(os.path.join(tmp, f"snap{r}.npy")) for r in range(world)], axis=1)
+        assert np.array_equal(snapshot, want_snapshot, equal_nan=True)
         for r in range(world):
             assert list(np.load(os.path.join(tmp, f"dts{r}.npy"))) == want_dts
         assert np.array_equal(again, want, equal_nan=True)
