@@ -77,6 +77,7 @@ _SIGNATURES = {
     "astrea_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, _PD]),
     "astrea_set_time": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "astrea_step_async": (C.c_int, [C.c_void_p]),
+    "astrea_run_steps": (C.c_int, [C.c_void_p, C.c_int64]),
     "astrea_get_time": (C.c_int, [C.c_void_p, _PD, C.POINTER(C.c_int64), _PD]),
     "astrea_dt_history": (C.c_int, [C.c_void_p, _PD, C.c_int]),
     "astrea_dt_async": (C.c_int, [C.c_void_p]),
@@ -286,6 +287,10 @@ class Context:
 
     def step_async(self):
         self._check(self.lib.astrea_step_async(self._h))
+
+    def run_steps(self, nsteps):
+        """``nsteps`` x step_async in one call; small 1D grids replay the whole batch in one persistent launch."""
+        self._check(self.lib.astrea_run_steps(self._h, int(nsteps)))
 
     def dt_async(self):
         self._check(self.lib.astrea_dt_async(self._h))

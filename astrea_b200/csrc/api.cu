@@ -13,6 +13,7 @@
 #include "aux_kernels.cuh"
 #include "ct_kernels.cuh"
 #include "dispatch.cuh"
+#include "replay1d.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -105,6 +106,12 @@ struct astrea_ctx {
     cudaStream_t copy_st = nullptr;
     cudaEvent_t snap_ready = nullptr, snap_done[SNAP_RING] = {nullptr, nullptr, nullptr, nullptr};
 #endif
+    // persistent replay of a 1D step (replay1d.cuh): the recorded launch list on the device
+    ReplayOp* replay_ops = nullptr;
+    unsigned char* replay_blob = nullptr;
+    int replay_nops = 0;              // 0: not recorded yet; -1: this context cannot replay
+    size_t replay_smem = 0;
+    int64_t replay_launches = 0;      // recorded kernels per step (astrea_launch_count)
     Reg saved;                        // astrea_save_state copy of the grid
     int saved_parity = 0;
     // optional per-launch timing (astrea_profile): event pairs per kernel class
@@ -188,9 +195,13 @@ struct DeviceGuard {
                                  std::string(#expr) + ": " + (_e < 0 ? "unsupported selector combination" : cuda_text(_e))); \
     } while (0)
 
+// doubles between the variables of one plane row: the columns and their ghosts, rounded up to an even count so that
+// every row segment starting at an even column is 16-byte aligned (what the bulk copies of the TMA engine need)
+int64_t pitch_of(int64_t ncol) { return (ncol + 2 * GHOST + 1) & ~(int64_t)1; }
+
 Plane make_plane(double* mem, int64_t ncol, int ghost_r) {
     Plane p;
-    p.col_pitch = ncol + 2 * GHOST;
+    p.col_pitch = pitch_of(ncol);
     p.row_pitch = NVAR * p.col_pitch;
     p.base = mem + (int64_t)ghost_r * p.row_pitch + GHOST;
     return p;
@@ -424,6 +435,7 @@ int corner_field(astrea_ctx* c) {
         rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
         rp.nvar = NVAR;
         for (int k = 0; k < NVAR; ++k) rp.vars[k] = k;
+        rp.bulk = (g.flags & 4) ? 0 : 1;
         rp.ppm_author = PPM_MC; rp.pass = 0; rp.force_any3 = 0; rp.ppm_flags = c->ppm_flags; rp.nt = nt;   // mag_field.py:11: author='mc'
         const int nthreads = 128;
         const int gx = (int)((nt + nthreads - 1) / nthreads);
@@ -599,6 +611,10 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 }
                 rp.i_lo = i_lo; rp.i_hi = i_hi; rp.bc = g.boundary; rp.limiter = g.limiter;
                 rp.seg = g.segment_2d > 0 ? g.segment_2d : 64;
+                // bulk-copy march (ReconStage BULK): row segments must start at an even column; PLM's range starts at -1 and
+                // may take one more ghost column (the primitive stage fills columns from -(lo + 1) = -2)
+                rp.bulk = (g.flags & 4) ? 0 : 1;
+                if (rp.bulk && (rp.c_lo & 1)) { if (rp.c_lo == -1) rp.c_lo = -2; else rp.bulk = 0; }
                 const VarList vl = c->vars();
                 rp.nvar = vl.n;
                 for (int k = 0; k < NVAR; ++k) rp.vars[k] = vl.v[k];
@@ -626,8 +642,11 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 fp.gamma = g.gamma; fp.bc = g.boundary; fp.low_mach = g.low_mach;
                 fp.eigmax_bits = eig + ax; fp.flag = c->flag;
                 const int nthreads = (g.threads_2d >= 32 && g.threads_2d <= 128) ? g.threads_2d / 32 * 32 : 128;
+                // block-wide rows of transverse points pay off on wide grids only (stages2d.cuh, FluxStage BT);
+                // flags bit 3 / bit 4 force warp rows / block rows (A/B measurements, geometry tests)
+                fp.block_tile = (g.flags & 8) ? 0 : ((g.flags & 16) ? 1 : (nt >= 4096 ? 1 : 0));
                 int own = 0, nwarp = 0;
-                flux_stage_geometry(kind, g.solver, (lw || c->hydro) ? 1 : 0, nthreads, own, nwarp);
+                flux_stage_geometry(kind, g.solver, (!lw && c->hydro) ? 1 : 0, fp.block_tile, nthreads, own, nwarp);
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
                 fp.lw_pass = 0; fp.lw_keys = c->lw_keys;
                 if (lw) {      // search pass of the Lax-Wendroff column pick, per sweep
@@ -763,8 +782,8 @@ astrea_ctx* astrea_create(const astrea_cfg* cfg) {
     if (g.dimension == 1) { c->nrow = 1; c->ncol = g.nx; c->ghost_r = 0; c->cfg.ny = g.nx; c->cfg.nx = 1; c->cfg.nx_global = 1; }
     else { c->nrow = g.nx; c->ncol = g.ny; c->ghost_r = GHOST; }
     // the transposed planes of the y sweep have the same number of elements
-    c->plane_doubles = (size_t)(c->nrow + 2 * c->ghost_r) * NVAR * (size_t)(c->ncol + 2 * GHOST);
-    if (g.dimension == 2) c->plane_doubles = std::max(c->plane_doubles, (size_t)(c->ncol + 2 * GHOST) * NVAR * (size_t)(c->nrow + 2 * GHOST));
+    c->plane_doubles = (size_t)(c->nrow + 2 * c->ghost_r) * NVAR * (size_t)pitch_of(c->ncol);
+    if (g.dimension == 2) c->plane_doubles = std::max(c->plane_doubles, (size_t)(c->ncol + 2 * GHOST) * NVAR * (size_t)pitch_of(c->nrow));
 
     int nregs = 1, nrates = 1;
     build_program(g.integrator, g.magnetic_2d != 0, c->prog, nregs, nrates, c->final_reg);
@@ -828,6 +847,7 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags); dev_free(c->lw_keys);
     dev_free(c->snap_dev);
+    dev_free(c->replay_ops); dev_free(c->replay_blob);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
     if (c->snap_ready) cudaEventDestroy(c->snap_ready);
@@ -1347,6 +1367,51 @@ int astrea_step_async(astrea_ctx* c) {
     return astrea_finish_step(c);
 }
 
+int astrea_run_steps(astrea_ctx* c, int64_t nsteps) {
+    if (!c || nsteps < 0) return fail(c, ASTREA_E_ARG, "astrea_run_steps: bad argument");
+    ASTREA_ON_DEVICE(c);
+    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_run_steps: a step is in flight");
+    const bool candidate = c->cfg.dimension == 1 && c->ncol <= REPLAY_MAX_CELLS && !(c->cfg.flags & 2) && !c->profiling && c->replay_nops >= 0
+                           && c->threads1d <= REPLAY_THREADS;
+    if (candidate && c->replay_nops == 0) {
+        // record one step (1D: the list does not depend on the step parity) and park it on the device
+        Recorder rec;
+        const int64_t launches0 = c->launches;
+        c->st.rec = &rec;
+        const int e = enqueue_step(c);
+        c->st.rec = nullptr;
+        c->next_instr = 0;
+        c->replay_launches = c->launches - launches0;
+        c->launches = launches0;
+        if (e) return e;
+        if (rec.unsupported || rec.ops.empty() || rec.smem > 200 * 1024) {
+            c->replay_nops = -1;
+        } else {
+            c->replay_ops = (ReplayOp*)dev_alloc(rec.ops.size() * sizeof(ReplayOp));
+            c->replay_blob = (unsigned char*)dev_alloc(rec.blob.size() + 16);
+            if (!c->replay_ops || !c->replay_blob) return fail(c, ASTREA_E_CUDA, "astrea_run_steps: device allocation failed");
+            ASTREA_TRY(copy_h2d(c->replay_ops, rec.ops.data(), rec.ops.size() * sizeof(ReplayOp), c->st));
+            ASTREA_TRY(copy_h2d(c->replay_blob, rec.blob.data(), rec.blob.size(), c->st));
+            if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_run_steps: stream sync failed");   // the sources are locals
+            c->replay_nops = (int)rec.ops.size();
+            c->replay_smem = rec.smem;
+        }
+    }
+    if (candidate && c->replay_nops > 0) {
+        if (nsteps == 0) return 0;
+        const int e = launch_replay1d(c->cfg.scheme, c->cfg.solver, c->replay_ops, c->replay_nops, c->replay_blob, (int)std::min<int64_t>(nsteps, 1 << 30),
+                                      c->replay_smem, c->st);
+        if (e) return fail(c, e < 0 ? ASTREA_E_ARG : ASTREA_E_CUDA, "astrea_run_steps: replay launch failed" + (e > 0 ? ": " + cuda_text(e) : std::string()));
+        c->launches += 1;
+        if (nsteps & 1) c->parity ^= 1;
+        c->grid_reg = c->final_reg;
+        return 0;
+    }
+    for (int64_t k = 0; k < nsteps; ++k)
+        if (int e = astrea_step_async(c)) return e;
+    return 0;
+}
+
 int astrea_get_time(astrea_ctx* c, double* t, int64_t* steps, double* last_dt) {
     if (!c) return ASTREA_E_ARG;
     ASTREA_ON_DEVICE(c);
@@ -1404,7 +1469,7 @@ int astrea_download_face_field(astrea_ctx* c, double* bxy_aos) {
 int astrea_halo_info(const astrea_ctx* c, int64_t* ghost_rows, int64_t* doubles_per_block) {
     if (!c) return ASTREA_E_ARG;
     if (ghost_rows) *ghost_rows = c->ghost_r;
-    if (doubles_per_block) *doubles_per_block = (int64_t)c->ghost_r * NVAR * (c->ncol + 2 * GHOST);
+    if (doubles_per_block) *doubles_per_block = (int64_t)c->ghost_r * NVAR * pitch_of(c->ncol);
     return 0;
 }
 

@@ -25,12 +25,16 @@ inline int launch_flux_kernel(const FluxStageParams& p, int gx, int gy, int nthr
 #define ASTREA_DEFINE_FLUX(NAME, KIND)                                                                               \
     template <int SOL, int AX, int SAX>                                                                              \
     static int runflux_##NAME(int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) {        \
+        constexpr bool HY = SOL != SOL_HLLD;                                                                         \
+        const bool bt = flux_stage_block_tile(SOL, hydro && HY, p.block_tile);                                       \
         if (p.bc == BC_EDGE) {                                                                                       \
-            if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, true>>(p, gx, gy, nthreads, st); \
-            return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, true>>(p, gx, gy, nthreads, st);                   \
+            if (hydro && bt) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, HY, true, HY>>(p, gx, gy, nthreads, st); \
+            if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, HY, true>>(p, gx, gy, nthreads, st);  \
+            return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, true>>(p, gx, gy, nthreads, st);          \
         }                                                                                                            \
-        if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, SOL != SOL_HLLD, false>>(p, gx, gy, nthreads, st); \
-        return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, false>>(p, gx, gy, nthreads, st);                      \
+        if (hydro && bt) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, HY, false, HY>>(p, gx, gy, nthreads, st); \
+        if (hydro) return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, HY, false>>(p, gx, gy, nthreads, st);     \
+        return launch_flux_kernel<FluxStage<KIND, SOL, AX, SAX, false, false>>(p, gx, gy, nthreads, st);             \
     }                                                                                                                \
     int launch_flux_##NAME(int solver, int ax, int sax, int hydro, const FluxStageParams& p, int gx, int gy, int nthreads, Stream st) { \
         const int key = ax * 2 + sax;                                                                                \

@@ -1,7 +1,27 @@
 // ReconStage instantiations, one per reconstruction scheme (PCM needs none: its faces are the cell averages).
 #include "dispatch.cuh"
 namespace astrea {
+#ifdef ASTREA_DEVICE_BUILD
+template <int SCHEME>
+static int launch_bulk(const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
+    using K = ReconStage<SCHEME, false, true>;
+    return launch<K>(p, gx, gy, nthreads, K::smem_bytes(nthreads), st);
+}
+#endif
 int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
+#ifdef ASTREA_DEVICE_BUILD
+    // the march fed by the TMA engine's bulk copies (stages2d.cuh): aligned row segments, default author
+    if (p.bulk && (p.c_lo & 1) == 0 && (p.w.col_pitch & 1) == 0 && (scheme != SCH_PPM || p.ppm_author == PPM_MC)) {
+        switch (scheme) {
+            case SCH_PLM: return launch_bulk<SCH_PLM>(p, gx, gy, nthreads, st);
+            case SCH_PPM: return launch_bulk<SCH_PPM>(p, gx, gy, nthreads, st);
+            case SCH_WENO3: return launch_bulk<SCH_WENO3>(p, gx, gy, nthreads, st);
+            case SCH_WENO5: return launch_bulk<SCH_WENO5>(p, gx, gy, nthreads, st);
+            case SCH_WENO7: return launch_bulk<SCH_WENO7>(p, gx, gy, nthreads, st);
+            default: return -1;
+        }
+    }
+#endif
     switch (scheme) {
         case SCH_PLM: return launch<ReconStage<SCH_PLM>>(p, gx, gy, nthreads, 0, st);
         case SCH_PPM:

@@ -233,6 +233,7 @@ struct ReconStageParams {
     int ppm_author, pass, force_any3;
     int* ppm_flags;
     int64_t nt;                // interior columns (the switches look at genuine cells only)
+    int bulk;                  // 1: march fed by bulk asynchronous copies (device, aligned row segments; ReconStage BULK)
 };
 
 // accessor over the register stencil: logical offset k relative to the cell, identity boundary map.  The window is a
@@ -260,7 +261,11 @@ struct ColumnAccessor {
 };
 
 // CPH: the PPM authors 'c' / 'ph' (a separate instantiation keeps the default 'mc' march lean)
-template <int SCHEME, bool CPH = false>
+// BULK (device only): the rows ahead of the march are brought into a per-warp shared-memory ring by the TMA engine's
+// bulk copies (cp.async.bulk, one 256-byte row segment per copy, NW rows per mbarrier) instead of being requested
+// PF cells ahead into registers: a warp then has 2-3 x NW rows in flight whatever its register budget, and the march
+// reads them with LDS.  Needs 16-byte aligned row segments (even column pitch, even first column): the launcher checks.
+template <int SCHEME, bool CPH = false, bool BULK = false>
 struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
@@ -269,12 +274,26 @@ struct ReconStage {
 #endif
     // the march is bound by load latency: 5 blocks (20 warps, 96 registers, a few spills) measured best of 4 / 5 / 6 / 8
     // with the prefetch queue (PPM 2048^2: 0.99 / 0.91 / 1.11 ms per step; WENO5 4096^2: 4.93 / 4.42 / 4.47 ms)
-    static constexpr int MIN_BLOCKS = ASTREA_RECON_MIN_BLOCKS;
+#ifndef ASTREA_RECON_MIN_BLOCKS_BULK
+#define ASTREA_RECON_MIN_BLOCKS_BULK 4
+#endif
+    // with the bulk-copy ring the rows in flight no longer depend on the number of warps: 4 blocks (128 registers, no
+    // spills) beat 5 (PPM 8192^2: 11.1 vs 12.5 ms per step; the register-prefetch march takes 12.0 at 5 blocks)
+    static constexpr int MIN_BLOCKS = BULK ? ASTREA_RECON_MIN_BLOCKS_BULK : ASTREA_RECON_MIN_BLOCKS;
     static constexpr int LO = recon_lo(SCHEME), HI = recon_hi(SCHEME), NW = LO + HI + 1;
 #ifndef ASTREA_RECON_PREFETCH
 #define ASTREA_RECON_PREFETCH 3
 #endif
     static constexpr int PF = ASTREA_RECON_PREFETCH;     // rows in flight beyond the one the next cell needs
+#ifndef ASTREA_RECON_BULK_SLOTS
+#define ASTREA_RECON_BULK_SLOTS 3
+#endif
+    static constexpr int NSLOT = ASTREA_RECON_BULK_SLOTS; // BULK: groups of NW rows in the ring of a warp
+    static size_t smem_bytes(int nthreads) {
+        if (!BULK) return 0;
+        const size_t nwarp = nthreads / 32, bars = (nwarp * NSLOT * sizeof(uint64_t) + 15) / 16 * 16;
+        return bars + nwarp * NSLOT * NW * 32 * sizeof(double);
+    }
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
     // The threads are independent; on the device a warp marches with the Fast division first and repeats its
@@ -371,46 +390,104 @@ struct ReconStage {
 #pragma unroll
                 for (int k = 0; k < NW; ++k) { r[k] = col[(mid_lo - LO + k) * rp]; g.input(r[k]); }
                 if constexpr (SCHEME == SCH_PPM && !CPH) ppm_mc_march_prime<0>(StencilAccessor<LO, NW, 0>{r}, win);
-                // running addresses of the march: one pointer increment per plane and cell instead of an index product
-                // rows requested PF + 1 cells before their first use, so that a warp has several loads in flight (the march
-                // is bound by load latency at the few warps its registers allow): queue[k] holds row (i + 1) + HI + k
-                double queue[PF];
-#pragma unroll
-                for (int k = 0; k < PF; ++k) queue[k] = (mid_lo + 1 + k <= mid_hi) ? col[(mid_lo + 1 + HI + k) * rp] : 0.0;
-                const double* in = col + (mid_lo + 1 + HI + PF) * rp;
                 double* out_p = p.wp.at(mid_lo, v, t);
                 double* out_m = p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
                 double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? p.wf.at(mid_lo, v, t) : nullptr;
                 const int64_t rp_p = p.wp.row_pitch, rp_m = p.wm.row_pitch, rp_f = p.wf.row_pitch;
-                // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
-                // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
-                for (int64_t i0 = mid_lo; i0 <= mid_hi; i0 += NW) {
-                    static_for<0, NW>([&](auto uc) {
-                        constexpr int U = decltype(uc)::value;
-                        const int64_t i = i0 + U;
-                        if (i > mid_hi) return;
-                        const double ahead = queue[0];                      // row (i + 1) + HI
-                        g.input(ahead);
+                // one cell of the march: `ahead` is row (i + 1) + HI, which replaces the oldest window entry afterwards
+                auto step = [&](auto uc, int64_t i, double ahead) {
+                    constexpr int U = decltype(uc)::value;
+                    g.input(ahead);
+                    StencilAccessor<LO, NW, U> acc{r};
+                    if constexpr (SCHEME == SCH_PPM && CPH) {
+                        cph_cell(acc, 0, i, i + p.s_off);
+                    } else {
+                        double wl, wr, wf;
+                        if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, wl, wr, wf, g);
+                        else cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
+                        // away from the physical boundaries: w_plus[i] = wL, w_minus[i + 1] = wR (cell aligned: both at i)
+                        *out_p = wl;
+                        *out_m = wr;
+                        if (out_f != nullptr) { *out_f = wf; out_f += rp_f; }
+                        out_p += rp_p;
+                        out_m += rp_m;
+                    }
+                    r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
+                };
+#ifdef ASTREA_DEVICE_BUILD
+                if constexpr (BULK) {
+                    // ring of NSLOT groups of NW row segments (the 32 columns of this warp) fed by cp.async.bulk; group k
+                    // holds the `ahead` rows of the cells mid_lo + k NW .. + NW - 1 and completes on its own mbarrier
+                    const int lane = tid & 31, warp = tid >> 5, nwarp = NT / 32;
+                    const unsigned mask = warp_mask();
+                    uint64_t* bars = reinterpret_cast<uint64_t*>(ex.smem()) + warp * NSLOT;
+                    double* ring = ex.smem() + ((size_t)nwarp * NSLOT * sizeof(uint64_t) + 15) / 16 * 2 + (size_t)warp * NSLOT * NW * 32;
+                    const int64_t t0 = t - lane;                                     // first column of the warp
+                    const int64_t c_end = p.w.col_pitch - GHOST;                      // columns of a plane row: [-GHOST, c_end)
+                    const uint32_t rowbytes = (uint32_t)(8 * (c_end - t0 < 32 ? c_end - t0 : 32));
+                    const double* src0 = p.w.at(0, v, t0);
+                    auto arm = [&](int64_t k) {
+                        const int64_t first_i = mid_lo + k * NW;
+                        const int64_t n = mid_hi - first_i < NW ? mid_hi - first_i : NW;      // cells first_i .. mid_hi - 1 need a row
+                        if (n <= 0) return;
+                        uint64_t* b = bars + k % NSLOT;
+                        mbar_expect_tx(b, (uint32_t)n * rowbytes);
+                        for (int64_t u = 0; u < n; ++u)
+                            bulk_load(ring + ((k % NSLOT) * NW + u) * 32, src0 + (first_i + 1 + HI + u) * rp, rowbytes, b);
+                    };
+                    if (lane == 0) {
 #pragma unroll
-                        for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
-                        queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
-                        in += rp;
-                        StencilAccessor<LO, NW, U> acc{r};
-                        if constexpr (SCHEME == SCH_PPM && CPH) {
-                            cph_cell(acc, 0, i, i + p.s_off);
-                        } else {
-                            double wl, wr, wf;
-                            if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, wl, wr, wf, g);
-                            else cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
-                            // away from the physical boundaries: w_plus[i] = wL, w_minus[i + 1] = wR (cell aligned: both at i)
-                            *out_p = wl;
-                            *out_m = wr;
-                            if (out_f != nullptr) { *out_f = wf; out_f += rp_f; }
-                            out_p += rp_p;
-                            out_m += rp_m;
+                        for (int sl = 0; sl < NSLOT; ++sl) mbar_init(bars + sl, 1);
+                        mbar_init_fence();
+                        for (int k = 0; k < NSLOT; ++k) arm(k);
+                    }
+                    warp_sync(mask);
+                    int64_t k = 0;
+                    for (int64_t i0 = mid_lo; i0 <= mid_hi; i0 += NW, ++k) {
+                        if (k > 0) {                          // every lane has read the previous group: its slot takes group k - 1 + NSLOT
+                            warp_sync(mask);
+                            if (lane == 0) arm(k - 1 + NSLOT);
                         }
-                        r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
-                    });
+                        if (i0 < mid_hi) mbar_wait(bars + k % NSLOT, (uint32_t)((k / NSLOT) & 1));
+                        const double* grp = ring + (k % NSLOT) * NW * 32 + lane;
+                        static_for<0, NW>([&](auto uc) {
+                            constexpr int U = decltype(uc)::value;
+                            const int64_t i = i0 + U;
+                            if (i > mid_hi) return;
+                            step(uc, i, i < mid_hi ? grp[U * 32] : 0.0);
+                        });
+                    }
+                    warp_sync(mask);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int sl = 0; sl < NSLOT; ++sl) mbar_inval(bars + sl);
+                    }
+                    warp_sync(mask);
+                } else
+#endif
+                {
+                    // rows requested PF + 1 cells before their first use, so that a warp has several loads in flight (the march
+                    // is bound by load latency at the few warps its registers allow): queue[k] holds row (i + 1) + HI + k
+                    double queue[PF];
+#pragma unroll
+                    for (int k = 0; k < PF; ++k) queue[k] = (mid_lo + 1 + k <= mid_hi) ? col[(mid_lo + 1 + HI + k) * rp] : 0.0;
+                    // running address of the march: one pointer increment per cell instead of an index product
+                    const double* in = col + (mid_lo + 1 + HI + PF) * rp;
+                    // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
+                    // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
+                    for (int64_t i0 = mid_lo; i0 <= mid_hi; i0 += NW) {
+                        static_for<0, NW>([&](auto uc) {
+                            constexpr int U = decltype(uc)::value;
+                            const int64_t i = i0 + U;
+                            if (i > mid_hi) return;
+                            const double ahead = queue[0];                      // row (i + 1) + HI
+#pragma unroll
+                            for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
+                            queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
+                            in += rp;
+                            step(uc, i, ahead);
+                        });
+                    }
                 }
             }
             if (edge) near_boundary(mid_hi + 1, last);
@@ -434,6 +511,7 @@ struct FluxStageParams {
     // (lw_keys[k] = 2 * flat index + (entry > 0)); the flux pass ranks the all-zero column among them.
     int lw_pass;
     unsigned long long* lw_keys;
+    int block_tile;            // 1: the hydro kernels of LLF / HLLC take the block-wide row of transverse points (FluxStage BT)
 };
 
 // KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)
@@ -441,7 +519,8 @@ struct FluxStageParams {
 // SAX = the solver's axis argument.
 // HYDRO: v_z and B are identically zero, only [rho, v_x, v_y, P] are processed (physics.cuh).
 // EDGE: the boundary mode ('edge' needs index clamps and the "own value" rule, 'wrap' reads ghost data as is).
-template <int KIND, int SOLVER, int AX, int SAX, bool HYDRO = false, bool EDGE = true>
+// BTILE: the block, not the warp, is the row of transverse points (see BT below)
+template <int KIND, int SOLVER, int AX, int SAX, bool HYDRO = false, bool EDGE = true, bool BTILE = false>
 struct FluxStage {
     using Params = FluxStageParams;
     using VS = VarSet<HYDRO>;
@@ -476,8 +555,10 @@ struct FluxStage {
 #endif
     // BT: with the shared-memory exchange the row of transverse points a group of lanes works on is the whole block
     // (one interface row per block, NT - 2H owned points) instead of one warp (32 - 2H): the halo lanes, whose work is
-    // redundant, drop from 4 of 32 to 4 of NT (12.5 % -> 3.1 % at 128 threads); the phases then end in a block barrier.
-    static constexpr bool BT = XS && (ASTREA_FLUX_BLOCK_TILE != 0);
+    // redundant, drop from 4 of 32 to 4 of NT (12.5 % -> 3.1 % at 128 threads); the phases then end in a block barrier,
+    // which costs more than the lanes save on small grids (measured, PPM + HLLC flux stages per step: 2048^2 1.85 ms
+    // with warp rows / 1.97 ms with block rows; 8192^2 28.5 / 27.5 ms), so the launcher picks it for wide grids only.
+    static constexpr bool BT = XS && BTILE && (ASTREA_FLUX_BLOCK_TILE != 0);
     static constexpr int NS = 9 * VarSet<HYDRO>::N;
     enum Slot : int { S_WP = 0, S_WM = 1, S_QP = 2, S_QM = 3, S_FP = 4, S_FM = 5, S_AP = 6, S_AM = 7, S_FA = 8 };
     static size_t smem_bytes(int nthreads) {
@@ -752,9 +833,12 @@ struct FluxStage {
 
 // launch geometry of the flux stage the dispatcher will pick (dispatch.cuh): transverse points a block owns and
 // interface rows it covers.  Mirrors FluxStage::BT: the block is the tile for the hydro kernels of LLF / HLLC.
-inline void flux_stage_geometry(int kind, int solver, int hydro, int nthreads, int& own, int& rows) {
+inline bool flux_stage_block_tile(int solver, int hydro, int wanted) {
+    return wanted && hydro && (solver == SOL_LLF || solver == SOL_HLLC) && (ASTREA_FLUX_SMEM_EXCHANGE != 0) && (ASTREA_FLUX_BLOCK_TILE != 0);
+}
+inline void flux_stage_geometry(int kind, int solver, int hydro, int wanted, int nthreads, int& own, int& rows) {
     const int h = kind == 2 ? 2 : 1;
-    const bool bt = hydro && (solver == SOL_LLF || solver == SOL_HLLC) && (ASTREA_FLUX_SMEM_EXCHANGE != 0) && (ASTREA_FLUX_BLOCK_TILE != 0);
+    const bool bt = flux_stage_block_tile(solver, hydro, wanted);
     own = (bt ? nthreads : 32) - 2 * h;
     rows = bt ? 1 : nthreads / 32;
 }

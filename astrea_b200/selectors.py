@@ -96,7 +96,8 @@ def stages_of(integrator):
 
 def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cfl, subgrid, solver, timestep,
              solver_category_name=None, magnetic_2d=False, limiter="minmod", low_mach=False, device=0,
-             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False, ppm_author="mc"):
+             nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False, ppm_author="mc",
+             step_graph=True, recon_bulk=True, flux_block_tile=None):
     cfg = N.Cfg()
     cfg.dimension = int(dimension)
     cfg.boundary = boundary_enum(boundary)
@@ -114,7 +115,11 @@ def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cf
     cfg.nx_global = int(nx_global if nx_global is not None else cfg.nx)
     cfg.x_offset = int(x_offset)
     cfg.threads_2d, cfg.segment_2d, cfg.tile_1d = int(threads_2d), int(segment_2d), int(tile_1d)
-    cfg.flags = 1 if general_path else 0      # keep the 8-variable kernels for a grid without v_z / B (testing)
+    # bit 0: keep the 8-variable kernels for a grid without v_z / B (testing); bit 1: no CUDA-graph replay of small steps;
+    # bit 2: reconstruction march with register prefetch instead of the TMA engine's bulk copies (A/B measurements)
+    # bit 3 / 4: flux stage with warp-wide / block-wide rows of transverse points (None: by grid width)
+    cfg.flags = ((1 if general_path else 0) | (0 if step_graph else 2) | (0 if recon_bulk else 4)
+                 | (0 if flux_block_tile is None else (16 if flux_block_tile else 8)))
     return cfg
 
 

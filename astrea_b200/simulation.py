@@ -269,6 +269,16 @@ class Simulation:
             self._walk(device_dt)
         self.steps_done += 1
 
+    def run_steps(self, nsteps):
+        """``nsteps`` x ``step_async``; on one GPU a small 1D grid replays the whole batch in one persistent launch
+        (``astrea_run_steps``)."""
+        if self.exchange is None:
+            self.ctx.run_steps(nsteps)
+            self.steps_done += nsteps
+        else:
+            for _ in range(nsteps):
+                self.step_async()
+
     def upload(self, grid):
         self._halo_ready = False
         self.ctx.upload(grid)

@@ -63,7 +63,10 @@ typedef struct astrea_cfg {
     int32_t segment_2d;    /* 0 = default (64); cells a thread of the 2D reconstruction stage marches along the sweep */
     int32_t tile_1d;       /* 0 = default; cells per block of the 1D sweep kernel */
     int32_t flags;         /* bit 0: keep the general 8-variable kernels even when the grid has no v_z / B (testing);
-                              bit 1: never replay astrea_step_async as a CUDA graph (small grids do by default) */
+                              bit 1: never replay astrea_step_async as a CUDA graph (small grids do by default);
+                              bit 2: reconstruction march with register prefetch instead of bulk asynchronous copies (A/B runs);
+                              bit 3 / bit 4: flux stage with warp-wide / block-wide rows of transverse points whatever the
+                              grid width (default: block-wide from 4096 columns) */
 } astrea_cfg;
 
 /* sim_variables -> device context.  Stands in for the namedtuple built at astrea.py:132-133. */
@@ -108,6 +111,11 @@ int astrea_step(astrea_ctx* ctx, double t, double t_stop, double* dt_out);
  * astrea_dt_history returns the dt of the last n steps (n <= 1024), oldest first. */
 int astrea_set_time(astrea_ctx* ctx, double t, double t_stop);
 int astrea_step_async(astrea_ctx* ctx);
+/* nsteps passes of the loop body (astrea.py:67-85) enqueued at once: the same as nsteps calls of astrea_step_async.
+ * For 1D grids up to 16384 cells (BASELINE config 1) the launches of one step are recorded once and replayed on the
+ * device by one persistent thread block, nsteps times in ONE launch — a step of the 1024-cell Sod tube is launch latency,
+ * not work.  Other grids fall back to astrea_step_async.  The t_stop clip of astrea_set_time applies as usual. */
+int astrea_run_steps(astrea_ctx* ctx, int64_t nsteps);
 int astrea_get_time(astrea_ctx* ctx, double* t, int64_t* steps, double* last_dt);
 int astrea_dt_history(astrea_ctx* ctx, double* out, int n);
 /* multi-GPU hosts: after instruction 0 and the all-reduce(MAX) of the three doubles at astrea_eigmax_device

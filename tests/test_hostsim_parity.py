@@ -169,6 +169,17 @@ def test_geometry_does_not_change_results(hostsim_lib):
     for threads, seg in ((32, 7), (48, 40), (64, 16)):
         got, _, _ = run_native(hostsim_lib, meta, g0, 2, threads_2d=threads, segment_2d=seg)
         assert np.array_equal(got, base, equal_nan=True)
+    # flux stage with block-wide / warp-wide rows of transverse points, reconstruction without the bulk-copy ring
+    for kw in (dict(flux_block_tile=True), dict(flux_block_tile=True, threads_2d=96), dict(flux_block_tile=False),
+               dict(recon_bulk=False), dict(flux_block_tile=True, recon_bulk=False, segment_2d=11)):
+        got, _, _ = run_native(hostsim_lib, meta, g0, 2, **kw)
+        assert np.array_equal(got, base, equal_nan=True), kw
+    for bc in ("edge", "wrap"):
+        meta2 = _meta("ll4", 37, 2, "weno5", "lf", "ssprk(2,2)", bc)
+        g2 = initial_state("ll4", 37, 2, 1.4, True, boundary=bc)
+        a, _, _ = run_native(hostsim_lib, meta2, g2, 2)
+        b, _, _ = run_native(hostsim_lib, meta2, g2, 2, flux_block_tile=True, recon_bulk=False)
+        assert np.array_equal(a, b, equal_nan=True), bc
 
 
 def test_primitive_download(hostsim_lib):
@@ -608,3 +619,61 @@ def test_async_snapshots_while_stepping(hostsim_lib):
         with pytest.raises(ValueError):
             sim.ctx.snapshot_begin(np.empty((3, 3, 8)))
         sim.close()
+
+
+@pytest.mark.parametrize("spec", [("sod", "plm", "lf", "ssprk(2,2)", 1024, None), ("sod", "ppm", "hllc", "ssprk(3,3)", 300, None),
+                                  ("shu-osher", "weno5", "lf", "rk4", 257, None), ("brio-wu", "plm", "hlld", "ssprk(5,4)", 200, None),
+                                  ("sod", "pcm", "lw", "euler", 64, None), ("square", "weno7", "lf", "ssprk(10,4)", 90, None),
+                                  ("sod", "weno3", "hllc", "ssprk(5,3)", 130, "wrap"), ("ryu-jones", "ppm", "hlld", "ssprk(4,3)", 128, None)],
+                         ids=lambda s: "-".join(map(str, s[:5])))
+def test_run_steps_persistent_replay(hostsim_lib, spec):
+    """astrea_run_steps on 1D grids: the recorded launch list of a step replayed by one persistent block (replay1d.cuh)
+    gives the same grid, clock and dt history as step-by-step stepping, for every integrator family, and continues
+    correctly across calls and after a new upload."""
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    config, subgrid, solver, timestep, cells, bc = spec
+    meta = _meta(config, cells, 1, subgrid, solver, timestep, bc)
+    g0 = initial_state(config, cells, 1, 1.4, subgrid in ("ppm", "weno3", "weno5", "weno7"), boundary=meta["boundary"])
+    ref = N.Context(native_cfg(meta, step_graph=False), lib=hostsim_lib)          # plain launches
+    ref.upload(g0)
+    ref.set_time(0.0, 0.0)
+    for _ in range(7):
+        ref.step_async()
+    want, want_clock, want_dts = ref.download(), ref.get_time(), ref.dt_history(7)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    ctx.set_time(0.0, 0.0)
+    ctx.run_steps(3)
+    ctx.run_steps(0)
+    ctx.run_steps(4)
+    assert ctx.get_time() == want_clock and ctx.dt_history(7) == want_dts
+    assert np.array_equal(ctx.download(), want, equal_nan=True)
+    # t_stop clip inside a replayed batch, after a fresh upload (astrea.py:74-75)
+    t_stop = want_dts[0] + want_dts[1] + 0.3 * want_dts[2]
+    for c in (ref, ctx):
+        c.upload(g0)
+        c.parity = 0
+        c.set_time(0.0, t_stop)
+    for _ in range(3):
+        ref.step_async()
+    ctx.run_steps(3)
+    assert ctx.get_time() == ref.get_time() and ctx.get_time()[0] == t_stop
+    assert np.array_equal(ctx.download(), ref.download(), equal_nan=True)
+    ref.close()
+    ctx.close()
+
+
+def test_run_steps_falls_back_in_2d(hostsim_lib):
+    from astrea_b200 import _native as N
+    from cases import native_cfg
+    meta = _meta("ll6", 24, 2, "ppm", "hllc", "ssprk(3,3)", None)
+    g0 = initial_state("ll6", 24, 2, 1.4, True)
+    want, dts = run_oracle(meta, g0, 3)
+    ctx = N.Context(native_cfg(meta), lib=hostsim_lib)
+    ctx.upload(g0)
+    ctx.set_time(0.0, 0.0)
+    ctx.run_steps(3)
+    assert ctx.get_time()[1] == 3 and ctx.dt_history(3) == dts
+    assert np.array_equal(ctx.download(), want, equal_nan=True)
+    ctx.close()
