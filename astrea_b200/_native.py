@@ -289,7 +289,7 @@ class Context:
         self._check(self.lib.astrea_step_async(self._h))
 
     def run_steps(self, nsteps):
-        """``nsteps`` x step_async in one call; small 1D grids replay the whole batch in one persistent launch."""
+        """``nsteps`` x step_async in one call."""
         self._check(self.lib.astrea_run_steps(self._h, int(nsteps)))
 
     def dt_async(self):

@@ -14,9 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "astrea_b200", "csrc")
-SOURCES = ["api.cu", "inst_sweep1d.cu", "inst_recon.cu", "inst_flux_pcm.cu", "inst_flux_plm.cu", "inst_flux_ho.cu", "inst_replay1d.cu",
-           "inst_replay1d_pcm.cu", "inst_replay1d_plm.cu", "inst_replay1d_ppm.cu", "inst_replay1d_weno3.cu", "inst_replay1d_weno5.cu",
-           "inst_replay1d_weno7.cu"]
+SOURCES = ["api.cu", "inst_sweep1d.cu", "inst_recon.cu", "inst_flux_pcm.cu", "inst_flux_plm.cu", "inst_flux_ho.cu"]
 DEVICE_LIB = os.path.join(ROOT, "astrea_b200", "lib", "libastrea_b200.so")
 HOSTSIM_LIB = os.path.join(ROOT, "tests", "hostsim", "libastrea_hostsim.so")
 

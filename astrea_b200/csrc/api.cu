@@ -13,7 +13,6 @@
 #include "aux_kernels.cuh"
 #include "ct_kernels.cuh"
 #include "dispatch.cuh"
-#include "replay1d.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -106,12 +105,6 @@ struct astrea_ctx {
     cudaStream_t copy_st = nullptr;
     cudaEvent_t snap_ready = nullptr, snap_done[SNAP_RING] = {nullptr, nullptr, nullptr, nullptr};
 #endif
-    // persistent replay of a 1D step (replay1d.cuh): the recorded launch list on the device
-    ReplayOp* replay_ops = nullptr;
-    unsigned char* replay_blob = nullptr;
-    int replay_nops = 0;              // 0: not recorded yet; -1: this context cannot replay
-    size_t replay_smem = 0;
-    int64_t replay_launches = 0;      // recorded kernels per step (astrea_launch_count)
     Reg saved;                        // astrea_save_state copy of the grid
     int saved_parity = 0;
     // optional per-launch timing (astrea_profile): event pairs per kernel class
@@ -847,7 +840,6 @@ void astrea_destroy(astrea_ctx* c) {
     dev_free(c->wfx.mem); dev_free(c->wfy.mem); dev_free(c->ct0.mem); dev_free(c->emf);
     dev_free(c->eig_bits); dev_free(c->clock); dev_free(c->dt_dev); dev_free(c->saved.mem); dev_free(c->mhd_flag); dev_free(c->ppm_flags); dev_free(c->lw_keys);
     dev_free(c->snap_dev);
-    dev_free(c->replay_ops); dev_free(c->replay_blob);
 #ifdef ASTREA_DEVICE_BUILD
     if (c->copy_st) { cudaStreamSynchronize(c->copy_st); cudaStreamDestroy(c->copy_st); }
     if (c->snap_ready) cudaEventDestroy(c->snap_ready);
@@ -1369,44 +1361,6 @@ int astrea_step_async(astrea_ctx* c) {
 
 int astrea_run_steps(astrea_ctx* c, int64_t nsteps) {
     if (!c || nsteps < 0) return fail(c, ASTREA_E_ARG, "astrea_run_steps: bad argument");
-    ASTREA_ON_DEVICE(c);
-    if (c->next_instr != 0) return fail(c, ASTREA_E_STATE, "astrea_run_steps: a step is in flight");
-    const bool candidate = c->cfg.dimension == 1 && c->ncol <= REPLAY_MAX_CELLS && !(c->cfg.flags & 2) && !c->profiling && c->replay_nops >= 0
-                           && c->threads1d <= REPLAY_THREADS;
-    if (candidate && c->replay_nops == 0) {
-        // record one step (1D: the list does not depend on the step parity) and park it on the device
-        Recorder rec;
-        const int64_t launches0 = c->launches;
-        c->st.rec = &rec;
-        const int e = enqueue_step(c);
-        c->st.rec = nullptr;
-        c->next_instr = 0;
-        c->replay_launches = c->launches - launches0;
-        c->launches = launches0;
-        if (e) return e;
-        if (rec.unsupported || rec.ops.empty() || rec.smem > 200 * 1024) {
-            c->replay_nops = -1;
-        } else {
-            c->replay_ops = (ReplayOp*)dev_alloc(rec.ops.size() * sizeof(ReplayOp));
-            c->replay_blob = (unsigned char*)dev_alloc(rec.blob.size() + 16);
-            if (!c->replay_ops || !c->replay_blob) return fail(c, ASTREA_E_CUDA, "astrea_run_steps: device allocation failed");
-            ASTREA_TRY(copy_h2d(c->replay_ops, rec.ops.data(), rec.ops.size() * sizeof(ReplayOp), c->st));
-            ASTREA_TRY(copy_h2d(c->replay_blob, rec.blob.data(), rec.blob.size(), c->st));
-            if (stream_sync(c->st) != 0) return fail(c, ASTREA_E_CUDA, "astrea_run_steps: stream sync failed");   // the sources are locals
-            c->replay_nops = (int)rec.ops.size();
-            c->replay_smem = rec.smem;
-        }
-    }
-    if (candidate && c->replay_nops > 0) {
-        if (nsteps == 0) return 0;
-        const int e = launch_replay1d(c->cfg.scheme, c->cfg.solver, c->replay_ops, c->replay_nops, c->replay_blob, (int)std::min<int64_t>(nsteps, 1 << 30),
-                                      c->replay_smem, c->st);
-        if (e) return fail(c, e < 0 ? ASTREA_E_ARG : ASTREA_E_CUDA, "astrea_run_steps: replay launch failed" + (e > 0 ? ": " + cuda_text(e) : std::string()));
-        c->launches += 1;
-        if (nsteps & 1) c->parity ^= 1;
-        c->grid_reg = c->final_reg;
-        return 0;
-    }
     for (int64_t k = 0; k < nsteps; ++k)
         if (int e = astrea_step_async(c)) return e;
     return 0;

@@ -948,11 +948,4 @@ struct ErrorKernel {
     }
 };
 
-// kernels the persistent 1D replay block (replay1d.cuh) knows how to run
-template <> struct replay_kind<HaloKernel> { static constexpr int kind = RK_HALO, sub = 0; };
-template <> struct replay_kind<CombineKernel> { static constexpr int kind = RK_COMBINE, sub = 0; };
-template <> struct replay_kind<RateKernel> { static constexpr int kind = RK_RATE, sub = 0; };
-template <> struct replay_kind<ClockKernel> { static constexpr int kind = RK_CLOCK, sub = 0; };
-template <int NTERMS, bool BRACKET> struct replay_kind<UpdateKernel<NTERMS, BRACKET>> { static constexpr int kind = RK_UPDATE, sub = NTERMS * 2 + (BRACKET ? 1 : 0); };
-
 }  // namespace astrea

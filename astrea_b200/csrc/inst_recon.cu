@@ -10,15 +10,15 @@ static int launch_bulk(const ReconStageParams& p, int gx, int gy, int nthreads, 
 #endif
 int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
 #ifdef ASTREA_DEVICE_BUILD
-    // the march fed by the TMA engine's bulk copies (stages2d.cuh): aligned row segments, default author
+    // The march fed by the TMA engine's bulk copies (stages2d.cuh): aligned row segments, default author.  PLM and PPM
+    // only: measured on a B200 (ms of reconstruction per step, bulk at 4 blocks per SM / register prefetch at 5) PPM
+    // 8192^2 11.1 / 12.0, PLM + transverse PPM 4096^2 10.9 / 12.6, but WENO5 4096^2 4.86 / 4.41 — the WENO march is bound
+    // by its divisions, not by load latency, and loses more to the lower occupancy than the ring gains.
     if (p.bulk && (p.c_lo & 1) == 0 && (p.w.col_pitch & 1) == 0 && (scheme != SCH_PPM || p.ppm_author == PPM_MC)) {
         switch (scheme) {
             case SCH_PLM: return launch_bulk<SCH_PLM>(p, gx, gy, nthreads, st);
             case SCH_PPM: return launch_bulk<SCH_PPM>(p, gx, gy, nthreads, st);
-            case SCH_WENO3: return launch_bulk<SCH_WENO3>(p, gx, gy, nthreads, st);
-            case SCH_WENO5: return launch_bulk<SCH_WENO5>(p, gx, gy, nthreads, st);
-            case SCH_WENO7: return launch_bulk<SCH_WENO7>(p, gx, gy, nthreads, st);
-            default: return -1;
+            default: break;
         }
     }
 #endif

@@ -21,41 +21,6 @@
 
 namespace astrea {
 
-// ------------------------------------------------------------------------------------------- launch recording
-// A step of a small 1D grid is a dozen launches of a few microseconds each: launch latency, not work.  Instead of
-// launching, ``launch`` / ``dev_zero`` / ``dev_ones`` can append what they were asked to do to a Recorder (kernel kind,
-// parameter block, grid); the recorded list is then replayed, step after step, by ONE persistent thread block
-// (replay1d.cuh) — the blocks of each recorded launch run one after the other, launches are separated by block barriers,
-// and the time step never leaves the device (ClockKernel is part of the list).
-enum ReplayKind : int { RK_NONE = -1, RK_MEMSET = 0, RK_HALO, RK_SWEEP1D, RK_UPDATE, RK_COMBINE, RK_RATE, RK_CLOCK };
-struct ReplayOp {
-    int kind, sub;                    // sub: RK_UPDATE: terms * 2 + bracket; RK_MEMSET: the byte value
-    int gx, gy, nthreads;
-    unsigned offset;                  // of the kernel's parameter block in the blob
-    unsigned long long ptr, bytes;    // RK_MEMSET: destination and size
-};
-struct Recorder {
-    std::vector<ReplayOp> ops;
-    std::vector<unsigned char> blob;
-    size_t smem = 0;
-    bool unsupported = false;         // something was asked for that the replay kernel cannot do
-};
-template <class K> struct replay_kind { static constexpr int kind = RK_NONE, sub = 0; };
-template <class K>
-inline int record_launch(Recorder& rec, const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes) {
-    if (replay_kind<K>::kind == RK_NONE) { rec.unsupported = true; return 0; }
-    const size_t at = (rec.blob.size() + 15) / 16 * 16;
-    rec.blob.resize(at + sizeof(p));
-    std::memcpy(rec.blob.data() + at, &p, sizeof(p));
-    rec.ops.push_back(ReplayOp{replay_kind<K>::kind, replay_kind<K>::sub, gx, gy, nthreads, (unsigned)at, 0ull, 0ull});
-    if (smem_bytes > rec.smem) rec.smem = smem_bytes;
-    return 0;
-}
-inline int record_memset(Recorder& rec, void* p, int value, size_t bytes) {
-    rec.ops.push_back(ReplayOp{RK_MEMSET, value, 1, 1, 0, 0u, (unsigned long long)(uintptr_t)p, (unsigned long long)bytes});
-    return 0;
-}
-
 #ifdef ASTREA_DEVICE_BUILD
 // ------------------------------------------------------------------------------------------- device back end
 struct DeviceExec {
@@ -218,11 +183,10 @@ __global__ void __launch_bounds__(K::MAX_THREADS, min_blocks_of<K>::value) kerne
     K::block(p, (int)blockIdx.x, (int)blockIdx.y, ex);
 }
 
-struct Stream { cudaStream_t s; Recorder* rec = nullptr; };
+struct Stream { cudaStream_t s; };
 
 template <class K>
 inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream st) {
-    if (st.rec) return record_launch<K>(*st.rec, p, gx, gy, nthreads, smem_bytes);
     static size_t configured_bytes = 48 * 1024;     // per kernel: the opt-in dynamic shared-memory size set so far
     if (smem_bytes > configured_bytes) {
         cudaError_t e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -235,11 +199,11 @@ inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, siz
 
 inline void* dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr; }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
-inline int dev_zero(void* p, size_t bytes, Stream st) { return st.rec ? record_memset(*st.rec, p, 0, bytes) : (int)cudaMemsetAsync(p, 0, bytes, st.s); }
-inline int dev_ones(void* p, size_t bytes, Stream st) { return st.rec ? record_memset(*st.rec, p, 0xFF, bytes) : (int)cudaMemsetAsync(p, 0xFF, bytes, st.s); }
-inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s); }
-inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s); }
-inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } return (int)cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st.s); }
+inline int dev_zero(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAsync(p, 0, bytes, st.s); }
+inline int dev_ones(void* p, size_t bytes, Stream st) { return (int)cudaMemsetAsync(p, 0xFF, bytes, st.s); }
+inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s); }
+inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s); }
+inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { return (int)cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st.s); }
 inline int copy_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height, Stream st) {
     return (int)cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, height, cudaMemcpyDeviceToHost, st.s);
 }
@@ -307,11 +271,10 @@ struct HostExec {
     }
 };
 
-struct Stream { int s; Recorder* rec = nullptr; };
+struct Stream { int s; };
 
 template <class K>
-inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream st) {
-    if (st.rec) return record_launch<K>(*st.rec, p, gx, gy, nthreads, smem_bytes);
+inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream) {
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
             HostExec ex(nthreads, smem_bytes);
@@ -322,11 +285,11 @@ inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, siz
 
 inline void* dev_alloc(size_t bytes) { return std::malloc(bytes); }
 inline void dev_free(void* p) { std::free(p); }
-inline int dev_zero(void* p, size_t bytes, Stream st) { if (st.rec) return record_memset(*st.rec, p, 0, bytes); std::memset(p, 0, bytes); return 0; }
-inline int dev_ones(void* p, size_t bytes, Stream st) { if (st.rec) return record_memset(*st.rec, p, 0xFF, bytes); std::memset(p, 0xFF, bytes); return 0; }
-inline int copy_h2d(void* d, const void* h, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } std::memcpy(d, h, bytes); return 0; }
-inline int copy_d2h(void* h, const void* d, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } std::memcpy(h, d, bytes); return 0; }
-inline int copy_d2d(void* d, const void* s, size_t bytes, Stream st) { if (st.rec) { st.rec->unsupported = true; return 0; } std::memcpy(d, s, bytes); return 0; }
+inline int dev_zero(void* p, size_t bytes, Stream) { std::memset(p, 0, bytes); return 0; }
+inline int dev_ones(void* p, size_t bytes, Stream) { std::memset(p, 0xFF, bytes); return 0; }
+inline int copy_h2d(void* d, const void* h, size_t bytes, Stream) { std::memcpy(d, h, bytes); return 0; }
+inline int copy_d2h(void* h, const void* d, size_t bytes, Stream) { std::memcpy(h, d, bytes); return 0; }
+inline int copy_d2d(void* d, const void* s, size_t bytes, Stream) { std::memcpy(d, s, bytes); return 0; }
 inline int copy_d2h_2d(void* h, size_t hpitch, const void* d, size_t dpitch, size_t width, size_t height, Stream) {
     for (size_t r = 0; r < height; ++r) std::memcpy((char*)h + r * hpitch, (const char*)d + r * dpitch, width);
     return 0;

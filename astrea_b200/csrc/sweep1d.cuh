@@ -227,6 +227,4 @@ struct Sweep1D {
     }
 };
 
-template <int SCHEME, int SOLVER> struct replay_kind<Sweep1D<SCHEME, SOLVER>> { static constexpr int kind = RK_SWEEP1D, sub = 0; };
-
 }  // namespace astrea

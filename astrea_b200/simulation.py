@@ -270,8 +270,7 @@ class Simulation:
         self.steps_done += 1
 
     def run_steps(self, nsteps):
-        """``nsteps`` x ``step_async``; on one GPU a small 1D grid replays the whole batch in one persistent launch
-        (``astrea_run_steps``)."""
+        """``nsteps`` x ``step_async`` (one call into the library on a single GPU)."""
         if self.exchange is None:
             self.ctx.run_steps(nsteps)
             self.steps_done += nsteps

@@ -312,8 +312,8 @@ def run_ours(a):
     batch = 256 if (horizon == MAX_HORIZON and dim == 1) else horizon
 
     def run_steps(n):
-        # steps are enqueued back to back: dt = cfl*min(dx/eigmax) is evaluated on the device (astrea_step_async /
-        # astrea_run_steps; small 1D grids replay each batch in one persistent launch)
+        # steps are enqueued back to back: dt = cfl*min(dx/eigmax) is evaluated on the device (astrea_step_async;
+        # small grids replay each step as one CUDA graph)
         done = 0
         while done < n:
             sim.restore_state()

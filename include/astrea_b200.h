@@ -111,10 +111,8 @@ int astrea_step(astrea_ctx* ctx, double t, double t_stop, double* dt_out);
  * astrea_dt_history returns the dt of the last n steps (n <= 1024), oldest first. */
 int astrea_set_time(astrea_ctx* ctx, double t, double t_stop);
 int astrea_step_async(astrea_ctx* ctx);
-/* nsteps passes of the loop body (astrea.py:67-85) enqueued at once: the same as nsteps calls of astrea_step_async.
- * For 1D grids up to 16384 cells (BASELINE config 1) the launches of one step are recorded once and replayed on the
- * device by one persistent thread block, nsteps times in ONE launch — a step of the 1024-cell Sod tube is launch latency,
- * not work.  Other grids fall back to astrea_step_async.  The t_stop clip of astrea_set_time applies as usual. */
+/* nsteps passes of the loop body (astrea.py:67-85) enqueued at once: nsteps calls of astrea_step_async (small grids
+ * replay a CUDA graph per step).  The t_stop clip of astrea_set_time applies as usual. */
 int astrea_run_steps(astrea_ctx* ctx, int64_t nsteps);
 int astrea_get_time(astrea_ctx* ctx, double* t, int64_t* steps, double* last_dt);
 int astrea_dt_history(astrea_ctx* ctx, double* out, int n);

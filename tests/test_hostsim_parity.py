@@ -626,10 +626,9 @@ def test_async_snapshots_while_stepping(hostsim_lib):
                                   ("sod", "pcm", "lw", "euler", 64, None), ("square", "weno7", "lf", "ssprk(10,4)", 90, None),
                                   ("sod", "weno3", "hllc", "ssprk(5,3)", 130, "wrap"), ("ryu-jones", "ppm", "hlld", "ssprk(4,3)", 128, None)],
                          ids=lambda s: "-".join(map(str, s[:5])))
-def test_run_steps_persistent_replay(hostsim_lib, spec):
-    """astrea_run_steps on 1D grids: the recorded launch list of a step replayed by one persistent block (replay1d.cuh)
-    gives the same grid, clock and dt history as step-by-step stepping, for every integrator family, and continues
-    correctly across calls and after a new upload."""
+def test_run_steps_equals_single_steps(hostsim_lib, spec):
+    """astrea_run_steps on 1D grids (on the device: CUDA-graph replay of each step) gives the same grid, clock and dt
+    history as plainly launched single steps, for every integrator family, across calls and after a new upload."""
     from astrea_b200 import _native as N
     from cases import native_cfg
     config, subgrid, solver, timestep, cells, bc = spec
