@@ -65,6 +65,7 @@ class NonFiniteError(AstreaError, np.linalg.LinAlgError):
 
 
 _PD = C.POINTER(C.c_double)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
 _SIGNATURES = {
     "astrea_create": (C.c_void_p, [C.POINTER(Cfg)]),
     "astrea_destroy": (None, [C.c_void_p]),
@@ -84,6 +85,7 @@ _SIGNATURES = {
     "astrea_get_parity": (C.c_int, [C.c_void_p]),
     "astrea_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "astrea_set_flag_reducer": (C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
     "astrea_program_length": (C.c_int, [C.c_void_p]),
     "astrea_instr_is_operator": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_instr_needs_halo": (C.c_int, [C.c_void_p, C.c_int]),
@@ -313,6 +315,18 @@ class Context:
     @parity.setter
     def parity(self, p):
         self._check(self.lib.astrea_set_parity(self._h, int(p)))
+
+    def set_flag_reducer(self, fn):
+        """``fn(device_ptr, count)``: in-place cross-rank maximum of ``count`` int32 on the context's stream (PPM authors
+        'c' / 'ph' on a decomposed grid)."""
+        def trampoline(_user, ptr, count):
+            try:
+                fn(ptr, count)
+                return 0
+            except Exception:          # an exception must not cross the C frame
+                return 1
+        self._reducer = REDUCE_FN(trampoline)       # keep the callback object alive as long as the context
+        self._check(self.lib.astrea_set_flag_reducer(self._h, self._reducer, None))
 
     # -- step program (multi-GPU hosts drive it instruction by instruction)
     def program(self):

@@ -105,6 +105,9 @@ struct astrea_ctx {
     cudaStream_t copy_st = nullptr;
     cudaEvent_t snap_ready = nullptr, snap_done[SNAP_RING] = {nullptr, nullptr, nullptr, nullptr};
 #endif
+    // cross-rank OR of the grid-wide switches of the PPM authors 'c' / 'ph' on a decomposed grid (astrea_set_flag_reducer)
+    astrea_reduce_fn reduce_fn = nullptr;
+    void* reduce_user = nullptr;
     Reg saved;                        // astrea_save_state copy of the grid
     int saved_parity = 0;
     // optional per-launch timing (astrea_profile): event pairs per kernel class
@@ -416,40 +419,42 @@ int corner_field(astrea_ctx* c) {
     const astrea_cfg& g = c->cfg;
     const int64_t nx = c->nrow, ny = c->ncol;
     const bool edge = g.boundary == BC_EDGE;
+    // The reconstruction of each sweep wrote its face states in the OTHER frame (ReconStageParams::wf_t): wfx holds the
+    // face states of the x sweep as a y-frame plane [y][v][x], wfy those of the y sweep as an x-frame plane [x][v][y] —
+    // the frames their transverse reconstruction marches in (mag_field.py:15 ``wF.transpose(ortho_axis)``).
     // "pad the derived array": ghost cells of the face-state arrays are copies, not reconstructions
     const bool xl = c->ext_lo(), xh = c->ext_hi();
-    if (int e = fill_plane_halo(c, c->wfx.plane, nx, ny, xl, xh, false, false)) return e;      // x frame: rows are x
-    if (int e = fill_plane_halo(c, c->wfy.plane, ny, nx, false, false, xl, xh)) return e;      // y frame: columns are x
-    auto transverse_ppm = [&](Plane face_t, Plane d, Plane u, int64_t ns, int64_t ns_glob, int64_t s_off, int64_t nt, int64_t i_hi) -> int {
+    const Plane fx = make_plane(c->wfx.mem, nx, GHOST), fy = make_plane(c->wfy.mem, ny, GHOST);
+    if (int e = fill_plane_halo(c, fx, ny, nx, false, false, xl, xh)) return e;      // y frame: columns are x
+    if (int e = fill_plane_halo(c, fy, nx, ny, xl, xh, false, false)) return e;      // x frame: rows are x
+    auto transverse_ppm = [&](Plane face_t, Plane d, Plane u, int transposed, int64_t ns, int64_t ns_glob, int64_t s_off, int64_t nt, int64_t i_hi) -> int {
         ReconStageParams rp{};
         rp.w = face_t; rp.wp = d; rp.wm = u; rp.wf = Plane{nullptr, 0, 0};
         rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = 0; rp.c_hi = nt;
         rp.i_lo = 0; rp.i_hi = i_hi;
-        rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1;
-        rp.nvar = NVAR;
-        for (int k = 0; k < NVAR; ++k) rp.vars[k] = k;
+        rp.bc = g.boundary; rp.limiter = LIM_MINMOD; rp.seg = 64; rp.cell_aligned = 1; rp.out_t = transposed;
+        // compute_corner reads rho, v_x, v_y, P and B of the corner states (mag_field.py:128-185): v_z is never used
+        rp.nvar = NVAR - 1;
+        const int used[NVAR] = {0, 1, 2, 4, 5, 6, 7, 0};
+        for (int k = 0; k < NVAR; ++k) rp.vars[k] = used[k];
         rp.bulk = (g.flags & 4) ? 0 : 1;
         rp.ppm_author = PPM_MC; rp.pass = 0; rp.force_any3 = 0; rp.ppm_flags = c->ppm_flags; rp.nt = nt;   // mag_field.py:11: author='mc'
         const int nthreads = 128;
         const int gx = (int)((nt + nthreads - 1) / nthreads);
         const int nseg = (int)((rp.i_hi - rp.i_lo + 1 + rp.seg - 1) / rp.seg);
         Timed timed(c, CLS_RECON);
-        ASTREA_TRY(launch_recon(SCH_PPM, rp, gx, nseg * NVAR, nthreads, c->st));
+        ASTREA_TRY(launch_recon(SCH_PPM, rp, gx, nseg * rp.nvar, nthreads, c->st));
         return 0;
     };
-    // bundle 1: face states of the x sweep, reconstructed along y (in the y frame), then brought to the x frame
-    const Plane t1 = make_plane(c->ws.mem, nx, GHOST), d1y = make_plane(c->wp.mem, nx, GHOST), u1y = make_plane(c->wm.mem, nx, GHOST);
-    if (int e = transpose_plane(c, c->wfx.plane, t1, nx, ny)) return e;
-    // cells 0..ny along y (pad(wD)[1:] needs cell ny when periodic); one more column of x when the row behind the slab is genuine
-    if (int e = transverse_ppm(t1, d1y, u1y, ny, ny, 0, xh ? nx + 1 : nx, edge ? ny - 1 : ny)) return e;
+    // bundle 1: face states of the x sweep, reconstructed along y (marching in the y frame), corner states written
+    // transposed, i.e. straight into x-frame planes.  Cells 0..ny along y (pad(wD)[1:] needs cell ny when periodic);
+    // one more column of x when the row behind the slab is genuine.
     const Plane d1 = make_plane(c->qT.mem, ny, GHOST), u1 = make_plane(c->ws.mem, ny, GHOST);
-    if (int e = transpose_plane(c, d1y, d1, ny, nx)) return e;
-    if (int e = transpose_plane(c, u1y, u1, ny, nx)) return e;
-    // bundle 0: face states of the y sweep, reconstructed along x (x frame)
-    const Plane t0 = make_plane(c->wp.mem, ny, GHOST), d0 = make_plane(c->wm.mem, ny, GHOST), u0 = make_plane(c->ct0.mem, ny, GHOST);
-    if (int e = transpose_plane(c, c->wfy.plane, t0, ny, nx)) return e;
-    // cells 0..nx (+1 behind a slab: the corner row nx needs wD of cell nx + 1)
-    if (int e = transverse_ppm(t0, d0, u0, nx, g.nx_global, g.x_offset, ny, xh ? nx + 1 : (edge ? nx - 1 : nx))) return e;
+    if (int e = transverse_ppm(fx, d1, u1, 1, ny, ny, 0, xh ? nx + 1 : nx, edge ? ny - 1 : ny)) return e;
+    // bundle 0: face states of the y sweep, reconstructed along x (x frame); cells 0..nx (+1 behind a slab: the corner
+    // row nx needs wD of cell nx + 1)
+    const Plane d0 = make_plane(c->wm.mem, ny, GHOST), u0 = make_plane(c->ct0.mem, ny, GHOST);
+    if (int e = transverse_ppm(fy, d0, u0, 0, nx, g.nx_global, g.x_offset, ny, xh ? nx + 1 : (edge ? nx - 1 : nx))) return e;
     c->emf_rows = xh ? nx + 1 : nx;
     CornerEmfParams ep{d0, u0, d1, u1, c->emf, nx, ny, g.nx_global, g.x_offset, g.gamma, g.boundary, c->parity};
     Timed timed(c, CLS_UPDATE);
@@ -460,7 +465,7 @@ int corner_field(astrea_ctx* c) {
 int run_special(astrea_ctx* c, const Instr& ins, int external_rows) {
     const astrea_cfg& g = c->cfg;
     if (ins.special == SP_FACE_FIELD) {
-        FaceFieldParams fp{c->regs[c->grid_reg].plane, c->wfx.plane, c->wfy.plane, c->nrow, c->ncol};
+        FaceFieldParams fp{c->regs[c->grid_reg].plane, make_plane(c->wfx.mem, c->nrow, GHOST), make_plane(c->wfy.mem, c->ncol, GHOST), c->nrow, c->ncol};
         Timed timed(c, CLS_UPDATE);
         ASTREA_TRY(launch<FaceFieldKernel>(fp, (int)((c->ncol + 31) / 32), (int)((c->nrow + 31) / 32), 256, FaceFieldKernel::smem_bytes(), c->st));
         return 0;
@@ -580,9 +585,11 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 PrimStageParams pp{};
                 pp.q = qf; pp.w = ws; pp.gamma = g.gamma; pp.high_order = ho ? 1 : 0;
                 pp.r_lo = -(int64_t)(lo + 1); pp.r_hi = ns + hi + 2; pp.c_lo = -(int64_t)ht; pp.c_hi = nt + ht;
-                if (g.magnetic_2d && ax == 1) {      // pcm.py:35: the face state is wS itself, also in the ghost rows of a slab
-                    if (c->ext_lo()) pp.c_lo = -(int64_t)CT_LO;
-                    if (c->ext_hi()) pp.c_hi = nt + CT_HI;
+                if (g.magnetic_2d && ax == 0) {
+                    // pcm.py:35: the face state is wS itself.  The x-frame primitives are kept as the face states of the y
+                    // sweep (corner_field), which constrained transport reconstructs along x: also in the ghost rows of a slab
+                    if (c->ext_lo()) pp.r_lo = std::min<int64_t>(pp.r_lo, -(int64_t)CT_LO);
+                    if (c->ext_hi()) pp.r_hi = std::max<int64_t>(pp.r_hi, ns + CT_HI);
                 }
                 pp.r_min = -(int64_t)GHOST; pp.r_max = ns + GHOST - 1; pp.c_min = -(int64_t)GHOST; pp.c_max = nt + GHOST - 1;
                 const int gx = (int)((pp.c_hi - pp.c_lo + PrimStage<false>::TX - 1) / PrimStage<false>::TX);
@@ -592,11 +599,16 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 else ASTREA_TRY(launch<PrimStage<false>>(pp, gx, gy, 256, PrimStage<false>::smem_bytes(pp.high_order), c->st));
             }
             if (pcm && g.magnetic_2d)      // pcm.py:35: the face state is the cell average
-                ASTREA_TRY(copy_d2d(ax == 0 ? c->wfx.mem : c->wfy.mem, c->ws.mem, c->plane_doubles * sizeof(double), c->st));
+                // the face states of a sweep are kept in the other frame (corner_field): the pointwise primitives of the
+                // x frame are the y sweep's face states as an x-frame plane, and the other way round
+                ASTREA_TRY(copy_d2d(ax == 0 ? c->wfy.mem : c->wfx.mem, c->ws.mem, c->plane_doubles * sizeof(double), c->st));
             if (!pcm) {
                 ReconStageParams rp{};
                 rp.w = ws; rp.wp = wp; rp.wm = wm; rp.wf = Plane{nullptr, 0, 0};
-                if (g.magnetic_2d) rp.wf = (ax == 0) ? c->wfx.plane : c->wfy.plane;       // data[axes]['wF'] (plm.py:57, ppm.py:101, weno.py:184)
+                if (g.magnetic_2d) {       // data[axes]['wF'] (plm.py:57, ppm.py:101, weno.py:184), written in the other frame
+                    rp.wf = (ax == 0) ? make_plane(c->wfx.mem, c->nrow, GHOST) : make_plane(c->wfy.mem, c->ncol, GHOST);
+                    rp.wf_t = 1;
+                }
                 rp.ns = ns; rp.ns_glob = ns_glob; rp.s_off = s_off; rp.c_lo = -(int64_t)ht; rp.c_hi = nt + ht;
                 if (g.magnetic_2d && ax == 1) {      // face states of the y sweep in the ghost rows of a slab (columns here)
                     if (c->ext_lo()) rp.c_lo = -(int64_t)CT_LO;
@@ -617,11 +629,16 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 rp.ppm_author = g.ppm_author; rp.pass = 0; rp.ppm_flags = c->ppm_flags; rp.nt = nt;
                 rp.force_any3 = c->hydro ? 1 : 0;       // an identically zero variable makes `cell_extrema.any()` true (0 * 0 <= 0)
                 if (g.scheme == SCH_PPM && g.ppm_author != PPM_MC) {
+                    if (c->slab() && c->reduce_fn == nullptr)
+                        return fail(c, ASTREA_E_STATE, "PPM authors 'c' / 'ph' switch on grid-wide any() tests (limiters.py:58,164): a decomposed grid "
+                                                       "needs astrea_set_flag_reducer");
                     ASTREA_TRY(dev_zero(c->ppm_flags, 4 * sizeof(int), c->st));
                     for (int pass = 1; pass <= 2; ++pass) {
                         rp.pass = pass;
-                        Timed timed(c, CLS_RECON);
-                        ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * rp.nvar, nthreads, c->st));
+                        { Timed timed(c, CLS_RECON); ASTREA_TRY(launch_recon(g.scheme, rp, gx, nseg * rp.nvar, nthreads, c->st)); }
+                        // the any() is over the whole grid: OR the switches of all slabs before the next pass reads them
+                        if (c->slab() && c->reduce_fn(c->reduce_user, c->ppm_flags, 4) != 0)
+                            return fail(c, ASTREA_E_STATE, "the flag reducer reported a failure");
                     }
                     rp.pass = 0;
                 }
@@ -723,10 +740,6 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
     if (g->boundary != ASTREA_EDGE && g->boundary != ASTREA_WRAP) { why = "boundary must be ASTREA_EDGE or ASTREA_WRAP"; return -1; }
     if (g->scheme < ASTREA_PCM || g->scheme > ASTREA_WENO7) { why = "unknown scheme"; return -1; }
     if (g->ppm_author < ASTREA_PPM_MC || g->ppm_author > ASTREA_PPM_PH) { why = "unknown PPM author"; return -1; }
-    if (g->ppm_author != ASTREA_PPM_MC && g->dimension == 2 && g->nx != g->nx_global) {
-        why = "PPM authors 'c' / 'ph' switch on grid-wide any() tests (limiters.py:58,164): not available on slabs";
-        return -1;
-    }
     if (g->limiter < ASTREA_MINMOD || g->limiter > ASTREA_SUPERBEE) { why = "unknown slope limiter"; return -1; }
     if (g->solver < ASTREA_LLF || g->solver > ASTREA_HLLD) { why = "unknown solver"; return -1; }
     if (g->solver == ASTREA_LW && (g->magnetic_2d || (g->dimension == 2 && g->nx != g->nx_global))) {
@@ -1165,6 +1178,13 @@ int astrea_arith_check(astrea_ctx* c, int64_t samples, uint64_t seed, uint64_t* 
     return 0;
 }
 
+int astrea_set_flag_reducer(astrea_ctx* c, astrea_reduce_fn fn, void* user) {
+    if (!c) return ASTREA_E_ARG;
+    c->reduce_fn = fn;
+    c->reduce_user = user;
+    return 0;
+}
+
 int astrea_program_length(const astrea_ctx* c) { return c ? (int)c->prog.size() : ASTREA_E_ARG; }
 
 int astrea_instr_is_operator(const astrea_ctx* c, int i) {
@@ -1407,7 +1427,7 @@ int astrea_download_face_field(astrea_ctx* c, double* bxy_aos) {
     if (!c->cfg.magnetic_2d) return fail(c, ASTREA_E_ARG, "astrea_download_face_field: magnetic_2d is off");
     // face averages of the last operator, assembled in a scratch plane and unpacked on the host
     Plane tmp = make_plane(c->ws.mem, c->ncol, GHOST);
-    FaceFieldParams fp{tmp, c->wfx.plane, c->wfy.plane, c->nrow, c->ncol};
+    FaceFieldParams fp{tmp, make_plane(c->wfx.mem, c->nrow, GHOST), make_plane(c->wfy.mem, c->ncol, GHOST), c->nrow, c->ncol};
     { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<FaceFieldKernel>(fp, (int)((c->ncol + 31) / 32), (int)((c->nrow + 31) / 32), 256, FaceFieldKernel::smem_bytes(), c->st)); }
     const size_t n = (size_t)c->nrow * c->ncol;
     std::vector<double> host(n * NVAR);

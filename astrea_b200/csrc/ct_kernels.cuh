@@ -1,13 +1,14 @@
 // Constrained transport of the in-plane magnetic field (num_methods/mag_field.py, evolvers.py:26-32,52-58,73-76).
 //
-//   face states (ReconStage ``wf``)  --halo fill = "pad the derived array"-->
-//   transpose --> PPM-mc along the transverse direction (ReconStage<PPM>, cell aligned)   mag_field.py:11-82
+//   face states (ReconStage ``wf``, written in the other sweep's frame)  --halo fill = "pad the derived array"-->
+//   PPM-mc along the transverse direction (ReconStage<PPM>, cell aligned; the bundle that marches in the y frame writes
+//   its corner states transposed, so no transpose kernel is left on this path)             mag_field.py:11-82
 //   CornerEmfKernel: Roe-averaged HLL wave speeds across each corner + upwinded E_z        mag_field.py:125-187
 //   RateKernel (aux_kernels.cuh): dBx/dt = -dE_z/dy, dBy/dt = +dE_z/dx                      evolvers.py:52-58
 //   FaceFieldKernel: B slots of the grid <- face averages, once per step        evolvers.py:73-76
 //   RefineFieldKernel: face-averaged B -> cell-averaged B after every register update        mag_field.py:191-211
 //
-// All kernels here work in the x frame ([x][var][y] planes); arrays produced in the y frame are transposed first.
+// All kernels here work in the x frame ([x][var][y] planes).
 #pragma once
 #include "physics.cuh"
 #include "runtime.cuh"
@@ -88,8 +89,8 @@ struct CornerEmfKernel {
 // ------------------------------------------------------------------------------------------------ face field
 struct FaceFieldParams {
     Plane grid;        // in/out: components 5 and 6 are overwritten
-    Plane wfx;         // face states of the x sweep, x frame
-    Plane wfy;         // face states of the y sweep, y frame
+    Plane wfx;         // face states of the x sweep, kept as a y-frame plane [y][v][x] (api.cu corner_field)
+    Plane wfy;         // face states of the y sweep, kept as an x-frame plane [x][v][y]
     int64_t nrow, ncol;
 };
 struct FaceFieldKernel {
@@ -105,7 +106,7 @@ struct FaceFieldKernel {
             const int tx = tid % TILE;
             for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                 const int64_t yr = c0 + ty, xc = r0 + tx;
-                if (yr < p.ncol && xc < p.nrow) tile[ty * (TILE + 1) + tx] = *p.wfy.at(yr, 6, xc);
+                if (yr < p.ncol && xc < p.nrow) tile[ty * (TILE + 1) + tx] = *p.wfx.at(yr, 5, xc);
             }
         });
         ex.phase([&](int tid) {
@@ -113,8 +114,8 @@ struct FaceFieldKernel {
             for (int ty = tid / TILE; ty < TILE; ty += MAX_THREADS / TILE) {
                 const int64_t r = r0 + ty, c = c0 + tx;
                 if (r >= p.nrow || c >= p.ncol) continue;
-                *p.grid.at(r, 5, c) = *p.wfx.at(r, 5, c);
-                *p.grid.at(r, 6, c) = tile[tx * (TILE + 1) + ty];
+                *p.grid.at(r, 5, c) = tile[tx * (TILE + 1) + ty];
+                *p.grid.at(r, 6, c) = *p.wfy.at(r, 6, c);
             }
         });
     }

@@ -1,13 +1,18 @@
 // ReconStage instantiations, one per reconstruction scheme (PCM needs none: its faces are the cell averages).
 #include "dispatch.cuh"
 namespace astrea {
-#ifdef ASTREA_DEVICE_BUILD
-template <int SCHEME>
-static int launch_bulk(const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
-    using K = ReconStage<SCHEME, false, true>;
+template <class K>
+static int run(const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
     return launch<K>(p, gx, gy, nthreads, K::smem_bytes(nthreads), st);
 }
+// STAGED: transposed outputs (constrained transport) leave the warps through shared-memory tiles (device only)
+template <int SCHEME, bool BULK>
+static int by_outputs(const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
+#ifdef ASTREA_DEVICE_BUILD
+    if (ReconStage<SCHEME>::staged_outputs(p)) return run<ReconStage<SCHEME, false, BULK, true>>(p, gx, gy, nthreads, st);
 #endif
+    return run<ReconStage<SCHEME, false, BULK, false>>(p, gx, gy, nthreads, st);
+}
 int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthreads, Stream st) {
 #ifdef ASTREA_DEVICE_BUILD
     // The march fed by the TMA engine's bulk copies (stages2d.cuh): aligned row segments, default author.  PLM and PPM
@@ -16,20 +21,20 @@ int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthr
     // by its divisions, not by load latency, and loses more to the lower occupancy than the ring gains.
     if (p.bulk && (p.c_lo & 1) == 0 && (p.w.col_pitch & 1) == 0 && (scheme != SCH_PPM || p.ppm_author == PPM_MC)) {
         switch (scheme) {
-            case SCH_PLM: return launch_bulk<SCH_PLM>(p, gx, gy, nthreads, st);
-            case SCH_PPM: return launch_bulk<SCH_PPM>(p, gx, gy, nthreads, st);
+            case SCH_PLM: return by_outputs<SCH_PLM, true>(p, gx, gy, nthreads, st);
+            case SCH_PPM: return by_outputs<SCH_PPM, true>(p, gx, gy, nthreads, st);
             default: break;
         }
     }
 #endif
     switch (scheme) {
-        case SCH_PLM: return launch<ReconStage<SCH_PLM>>(p, gx, gy, nthreads, 0, st);
+        case SCH_PLM: return by_outputs<SCH_PLM, false>(p, gx, gy, nthreads, st);
         case SCH_PPM:
-            if (p.ppm_author != PPM_MC) return launch<ReconStage<SCH_PPM, true>>(p, gx, gy, nthreads, 0, st);
-            return launch<ReconStage<SCH_PPM>>(p, gx, gy, nthreads, 0, st);
-        case SCH_WENO3: return launch<ReconStage<SCH_WENO3>>(p, gx, gy, nthreads, 0, st);
-        case SCH_WENO5: return launch<ReconStage<SCH_WENO5>>(p, gx, gy, nthreads, 0, st);
-        case SCH_WENO7: return launch<ReconStage<SCH_WENO7>>(p, gx, gy, nthreads, 0, st);
+            if (p.ppm_author != PPM_MC) return run<ReconStage<SCH_PPM, true>>(p, gx, gy, nthreads, st);
+            return by_outputs<SCH_PPM, false>(p, gx, gy, nthreads, st);
+        case SCH_WENO3: return by_outputs<SCH_WENO3, false>(p, gx, gy, nthreads, st);
+        case SCH_WENO5: return by_outputs<SCH_WENO5, false>(p, gx, gy, nthreads, st);
+        case SCH_WENO7: return by_outputs<SCH_WENO7, false>(p, gx, gy, nthreads, st);
         default: return -1;
     }
 }

@@ -234,6 +234,12 @@ struct ReconStageParams {
     int* ppm_flags;
     int64_t nt;                // interior columns (the switches look at genuine cells only)
     int bulk;                  // 1: march fed by bulk asynchronous copies (device, aligned row segments; ReconStage BULK)
+    // Outputs written in the OTHER frame, element (row = column t, col = cell i): a marching thread then writes consecutive
+    // addresses cell after cell, which the L2 merges into full sectors, so the transposed copy costs no extra pass.
+    // Constrained transport reads the face states of a sweep along the transverse direction (mag_field.py:15) and the
+    // corner states of both bundles in one frame (:164-185).
+    int wf_t;                  // wf is written transposed
+    int out_t;                 // cell_aligned: wp / wm are written transposed
 };
 
 // accessor over the register stencil: logical offset k relative to the cell, identity boundary map.  The window is a
@@ -265,7 +271,9 @@ struct ColumnAccessor {
 // bulk copies (cp.async.bulk, one 256-byte row segment per copy, NW rows per mbarrier) instead of being requested
 // PF cells ahead into registers: a warp then has 2-3 x NW rows in flight whatever its register budget, and the march
 // reads them with LDS.  Needs 16-byte aligned row segments (even column pitch, even first column): the launcher checks.
-template <int SCHEME, bool CPH = false, bool BULK = false>
+// STAGED (device only): a launch with transposed outputs (constrained transport); a separate instantiation keeps the
+// staging logic out of the marches of every other configuration (it cost them 8-10 % when it was a run-time switch).
+template <int SCHEME, bool CPH = false, bool BULK = false, bool STAGED = false>
 struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
@@ -289,10 +297,27 @@ struct ReconStage {
 #define ASTREA_RECON_BULK_SLOTS 3
 #endif
     static constexpr int NSLOT = ASTREA_RECON_BULK_SLOTS; // BULK: groups of NW rows in the ring of a warp
-    static size_t smem_bytes(int nthreads) {
+    // shared memory of a block, in doubles: [mbarriers + rings of the warps (BULK)] [staging tiles of the warps, only
+    // for launches with transposed outputs].  A staging tile holds SD cells x 32 columns (+ 1 pad) per output array: the
+    // cells of GROUPS unrolled groups, at least 8, so that a flush writes runs of >= 64 bytes per row of the other frame.
+    static constexpr int GROUPS = NW >= 8 ? 1 : (NW >= 4 ? 2 : 4);
+    static constexpr int SD = GROUPS * NW;
+    static constexpr int STG = 2 * SD * 33;      // per warp: wf alone, or wp and wm
+    static HD size_t ring_doubles(int nthreads) {
         if (!BULK) return 0;
-        const size_t nwarp = nthreads / 32, bars = (nwarp * NSLOT * sizeof(uint64_t) + 15) / 16 * 16;
-        return bars + nwarp * NSLOT * NW * 32 * sizeof(double);
+        const size_t nwarp = nthreads / 32;
+        return (nwarp * NSLOT * sizeof(uint64_t) + 15) / 16 * 2 + nwarp * NSLOT * NW * 32;
+    }
+    static size_t smem_bytes(int nthreads) {
+#ifdef ASTREA_DEVICE_BUILD
+        return sizeof(double) * (ring_doubles(nthreads) + (STAGED ? (size_t)(nthreads / 32) * STG : 0));
+#else
+        (void)nthreads;
+        return 0;
+#endif
+    }
+    static HD bool staged_outputs(const Params& p) {
+        return (p.wf_t != 0 && p.wf.base != nullptr && !p.cell_aligned) || (p.cell_aligned && p.out_t != 0);
     }
     // how far the limiter of a cell can reach through nested boundary maps (recon.cuh): stay on the generic path there
     static constexpr int REACH = HI + 2;
@@ -317,8 +342,23 @@ struct ReconStage {
     static HD void march(const Params& p, int bx, int by, Ex& ex, G& g) {
         const int NT = ex.nthreads();
         ex.wphase([&](int tid) {
-            const int64_t t = p.c_lo + (int64_t)bx * NT + tid;
-            if (t >= p.c_hi) return;
+            const int64_t t_lane = p.c_lo + (int64_t)bx * NT + tid;
+#ifdef ASTREA_DEVICE_BUILD
+            // Transposed outputs (wf_t / out_t) leave the warp through a shared-memory tile, NW cells at a time, so that every
+            // store instruction writes full 32-byte sectors of the other frame's rows (a lane writing its own column cell by cell
+            // touches 32 sectors per instruction and was measured 2.5 x slower).  All lanes of a warp that has any column to do
+            // stay for the flush; a lane beyond the range repeats the last column and stores nothing itself.
+            constexpr bool staged = STAGED;
+            const int64_t t_warp = t_lane - (tid & 31);
+            if (staged ? t_warp >= p.c_hi : t_lane >= p.c_hi) return;
+            const bool alive = !staged || t_lane < p.c_hi;
+            const int64_t t = alive ? t_lane : p.c_hi - 1;
+            double* stg = ex.smem() + ring_doubles(NT) + (size_t)(tid >> 5) * STG;
+#else
+            constexpr bool staged = false, alive = true;
+            if (t_lane >= p.c_hi) return;
+            const int64_t t = t_lane;
+#endif
             const int v = p.vars[by % p.nvar];
             const int64_t first = p.i_lo + (int64_t)(by / p.nvar) * p.seg;
             int64_t last = first + p.seg - 1;
@@ -328,10 +368,19 @@ struct ReconStage {
             const int64_t rp = p.w.row_pitch;
             const bool edge = p.bc == BC_EDGE;
             // what to do with the faces of cell i (ig: its global index); in flag passes of the authors 'c' / 'ph' nothing is stored
+            // transposed outputs exist in the STAGED instantiations only (device; the launcher picks them), so that the other
+            // marches keep compile-time strides; the host simulation, one instantiation for both, decides at run time
+#ifdef ASTREA_DEVICE_BUILD
+            const bool wf_t = STAGED && p.wf_t != 0, out_t = STAGED && p.out_t != 0;
+#else
+            const bool wf_t = p.wf_t != 0, out_t = p.out_t != 0;
+#endif
+            auto face_slot = [&](int64_t i) -> double* { return wf_t ? p.wf.at(t, v, i) : p.wf.at(i, v, t); };
             auto store = [&](int64_t i, int64_t ig, double wl, double wr, double wf) {
+                if (!alive) return;
                 if (p.cell_aligned) {
-                    *p.wp.at(i, v, t) = wl;
-                    *p.wm.at(i, v, t) = wr;
+                    *(out_t ? p.wp.at(t, v, i) : p.wp.at(i, v, t)) = wl;
+                    *(out_t ? p.wm.at(t, v, i) : p.wm.at(i, v, t)) = wr;
                     return;
                 }
                 // w_plus[j] = wL[b(j)], w_minus[j] = wR[b(j-1)]  (plm.py:42, ppm.py:82, weno.py:171)
@@ -339,7 +388,7 @@ struct ReconStage {
                 *p.wm.at(i + 1, v, t) = wr;
                 if (edge && ig == 0) *p.wm.at(i, v, t) = wr;                      // j = 0 sees cell 0 on both sides
                 if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;      // j = N sees cell N-1 on both sides
-                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+                if (p.wf.base != nullptr) *face_slot(i) = wf;
             };
             // one cell with accessor ``acc`` centred on offset ``at``; CPH: the authors 'c' / 'ph' with their flag passes
             auto cph_cell = [&](const auto& acc, int64_t at, int64_t i, int64_t ig) {
@@ -352,11 +401,12 @@ struct ReconStage {
                 cell_faces_ppm_cph(acc, at, ph, sw, p.pass, wl, wr, wf, pa, pb, p3);
                 if (p.pass == 1) { if (pa) p.ppm_flags[0] = 1; if (pb) p.ppm_flags[1] = 1; return; }
                 if (p.pass == 2) { if (p3) p.ppm_flags[2] = 1; return; }
+                if (!alive) return;
                 *p.wp.at(i, v, t) = wl;
                 *p.wm.at(i + 1, v, t) = wr;
                 if (edge && ig == 0) *p.wm.at(i, v, t) = wr;
                 if (edge && ig == p.ns_glob - 1) *p.wp.at(i + 1, v, t) = wl;
-                if (p.wf.base != nullptr) *p.wf.at(i, v, t) = wf;
+                if (p.wf.base != nullptr) *face_slot(i) = wf;
             };
             // cells within REACH of a physical 'edge' boundary: generic accessor with the clamp map, straight from memory
             auto near_boundary = [&](int64_t lo_i, int64_t hi_i) {
@@ -390,10 +440,13 @@ struct ReconStage {
 #pragma unroll
                 for (int k = 0; k < NW; ++k) { r[k] = col[(mid_lo - LO + k) * rp]; g.input(r[k]); }
                 if constexpr (SCHEME == SCH_PPM && !CPH) ppm_mc_march_prime<0>(StencilAccessor<LO, NW, 0>{r}, win);
-                double* out_p = p.wp.at(mid_lo, v, t);
-                double* out_m = p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
-                double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? p.wf.at(mid_lo, v, t) : nullptr;
-                const int64_t rp_p = p.wp.row_pitch, rp_m = p.wm.row_pitch, rp_f = p.wf.row_pitch;
+                const bool tr = p.cell_aligned && out_t;
+                double* out_p = tr ? p.wp.at(t, v, mid_lo) : p.wp.at(mid_lo, v, t);
+                double* out_m = tr ? p.wm.at(t, v, mid_lo) : p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
+                double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? face_slot(mid_lo) : nullptr;
+                const int64_t rp_p = tr ? 1 : p.wp.row_pitch, rp_m = tr ? 1 : p.wm.row_pitch, rp_f = wf_t ? 1 : p.wf.row_pitch;
+                int pending = 0;                 // staged outputs: cells in the staging tile, first of them is cell flush_i0
+                int64_t flush_i0 = mid_lo;
                 // one cell of the march: `ahead` is row (i + 1) + HI, which replaces the oldest window entry afterwards
                 auto step = [&](auto uc, int64_t i, double ahead) {
                     constexpr int U = decltype(uc)::value;
@@ -406,13 +459,59 @@ struct ReconStage {
                         if constexpr (SCHEME == SCH_PPM) cell_faces_ppm_mc_march<U>(acc, win, wl, wr, wf, g);
                         else cell_faces<SCHEME>(acc, 0, p.limiter, wl, wr, wf, g);
                         // away from the physical boundaries: w_plus[i] = wL, w_minus[i + 1] = wR (cell aligned: both at i)
-                        *out_p = wl;
-                        *out_m = wr;
-                        if (out_f != nullptr) { *out_f = wf; out_f += rp_f; }
-                        out_p += rp_p;
-                        out_m += rp_m;
+#ifdef ASTREA_DEVICE_BUILD
+                        if constexpr (staged) {
+                            const int lane_ = tid & 31, slot = pending + U;      // cells staged since the last flush
+                            if (tr) { stg[slot * 33 + lane_] = wl; stg[(SD + slot) * 33 + lane_] = wr; }
+                            else {
+                                if (alive) { *out_p = wl; *out_m = wr; }
+                                out_p += rp_p;
+                                out_m += rp_m;
+                                stg[slot * 33 + lane_] = wf;
+                            }
+                        } else
+#endif
+                        {
+                            *out_p = wl;
+                            *out_m = wr;
+                            if (out_f != nullptr) { *out_f = wf; out_f += rp_f; }
+                            out_p += rp_p;
+                            out_m += rp_m;
+                        }
                     }
                     r[U % NW] = ahead;       // the oldest entry makes room for row (i + 1) + HI
+                };
+                // After every unrolled group: once GROUPS groups are staged (or the march ends) the staged cells flush_i0 ..
+                // leave the warp — 4 lanes per row of the other frame, 8 rows per instruction, consecutive lanes on consecutive
+                // addresses, so that the stores fill whole sectors.
+                auto flush = [&](int64_t i0, bool last_group) {
+#ifdef ASTREA_DEVICE_BUILD
+                    if constexpr (staged && !(SCHEME == SCH_PPM && CPH)) {
+                        pending += (int)(mid_hi - i0 + 1 < NW ? mid_hi - i0 + 1 : NW);
+                        if (pending + NW <= SD && !last_group) return;
+                        warp_sync(0xffffffffu);
+                        const int lane_ = tid & 31;
+                        const int64_t rows = p.c_hi - t_warp < 32 ? p.c_hi - t_warp : 32;
+#pragma unroll
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int row = pass * 8 + (lane_ >> 2);
+                            if (row >= rows) continue;
+                            for (int e = lane_ & 3; e < pending; e += 4) {
+                                if (tr) {
+                                    *p.wp.at(t_warp + row, v, flush_i0 + e) = stg[e * 33 + row];
+                                    *p.wm.at(t_warp + row, v, flush_i0 + e) = stg[(SD + e) * 33 + row];
+                                } else {
+                                    *p.wf.at(t_warp + row, v, flush_i0 + e) = stg[e * 33 + row];
+                                }
+                            }
+                        }
+                        warp_sync(0xffffffffu);
+                        flush_i0 += pending;
+                        pending = 0;
+                    }
+#else
+                    (void)i0; (void)last_group;
+#endif
                 };
 #ifdef ASTREA_DEVICE_BUILD
                 if constexpr (BULK) {
@@ -422,7 +521,7 @@ struct ReconStage {
                     const unsigned mask = warp_mask();
                     uint64_t* bars = reinterpret_cast<uint64_t*>(ex.smem()) + warp * NSLOT;
                     double* ring = ex.smem() + ((size_t)nwarp * NSLOT * sizeof(uint64_t) + 15) / 16 * 2 + (size_t)warp * NSLOT * NW * 32;
-                    const int64_t t0 = t - lane;                                     // first column of the warp
+                    const int64_t t0 = t_warp;                                       // first column of the warp
                     const int64_t c_end = p.w.col_pitch - GHOST;                      // columns of a plane row: [-GHOST, c_end)
                     const uint32_t rowbytes = (uint32_t)(8 * (c_end - t0 < 32 ? c_end - t0 : 32));
                     const double* src0 = p.w.at(0, v, t0);
@@ -449,13 +548,14 @@ struct ReconStage {
                             if (lane == 0) arm(k - 1 + NSLOT);
                         }
                         if (i0 < mid_hi) mbar_wait(bars + k % NSLOT, (uint32_t)((k / NSLOT) & 1));
-                        const double* grp = ring + (k % NSLOT) * NW * 32 + lane;
+                        const double* grp = ring + (k % NSLOT) * NW * 32 + (t - t0);   // a lane beyond the range repeats the last column
                         static_for<0, NW>([&](auto uc) {
                             constexpr int U = decltype(uc)::value;
                             const int64_t i = i0 + U;
                             if (i > mid_hi) return;
                             step(uc, i, i < mid_hi ? grp[U * 32] : 0.0);
                         });
+                        flush(i0, i0 + NW > mid_hi);
                     }
                     warp_sync(mask);
                     if (lane == 0) {
@@ -487,6 +587,7 @@ struct ReconStage {
                             in += rp;
                             step(uc, i, ahead);
                         });
+                        flush(i0, i0 + NW > mid_hi);
                     }
                 }
             }

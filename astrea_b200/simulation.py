@@ -26,12 +26,15 @@ class _CudaBlock:
                                          "strides": None}
 
 
-def _tensor_at(ptr, count, on_device, device_index=0):
+def _tensor_at(ptr, count, on_device, device_index=0, int32=False):
     import torch
     if on_device:
-        return torch.as_tensor(_CudaBlock(ptr, count), device=torch.device("cuda", device_index))
-    buf = (ctypes.c_double * count).from_address(ptr)
-    return torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+        block = _CudaBlock(ptr, count)
+        if int32:
+            block.__cuda_array_interface__["typestr"] = "<i4"
+        return torch.as_tensor(block, device=torch.device("cuda", device_index))
+    buf = ((ctypes.c_int32 if int32 else ctypes.c_double) * count).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np.int32 if int32 else np.float64))
 
 
 class SlabExchange:
@@ -133,6 +136,18 @@ class SlabExchange:
             self.ctx.sync()
             dist.all_reduce(self._eig, op=dist.ReduceOp.MAX)
 
+    def reduce_flags(self, ptr, count):
+        """In-place maximum (logical OR) over the ranks of ``count`` int32 switches on the device, ordered on the context's
+        stream: the grid-wide ``any()`` of the PPM authors 'c' / 'ph' (limiters.py:58,164)."""
+        dist = self.dist
+        flags = _tensor_at(ptr, count, self.on_device, self.device_index, int32=True)
+        if self.on_device:
+            with self.torch.cuda.stream(self.stream):
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        else:
+            self.ctx.sync()
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+
     def global_eigmax(self):
         self.reduce_eigmax()
         return self.ctx.read_eigmax()      # synchronises; raises NonFiniteError on every rank if any rank saw one
@@ -173,6 +188,8 @@ class Simulation:
         self.stages = stages_of(self.cfg.integrator)
         self.on_device = self.ctx.lib.astrea_is_device_build() == 1
         self.exchange = SlabExchange(self.ctx, rank, world, self.boundary == "wrap", self.on_device, device) if world > 1 else None
+        if self.exchange is not None and self.cfg.scheme == N.PPM and self.cfg.ppm_author != N.PPM_MC:
+            self.ctx.set_flag_reducer(self.exchange.reduce_flags)
         self.t, self.steps_done = 0.0, 0
         self._program = self.ctx.program()
         self._updates = self.ctx.updates()

@@ -164,6 +164,13 @@ int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);
  *         if astrea_instr_is_operator(ctx, i): <NCCL send/recv on astrea_halo_ptrs(ctx, i, ...)>
  *         astrea_run_instr(ctx, i, external_rows)
  * Each halo block is ghost_rows x 8 variables x col_pitch doubles, contiguous (the [row][var][col] layout). */
+/* The PPM authors 'c' / 'ph' (ASTREA_PPM_COLELLA / ASTREA_PPM_PH) switch their limiters on ``mask.any()`` over the WHOLE
+ * grid (limiters.py:58,164).  On a decomposed grid the library evaluates the masks of its slab into four
+ * int32 switches on the device and then calls ``fn(user, device_ptr, 4)``, which must replace them, in place and ordered
+ * on the context's stream, by their maximum (= logical OR) over all ranks — e.g. one ncclAllReduce(ncclMax) — and
+ * return 0.  Called twice per sweep of such an operator, from inside astrea_run_instr.  Not needed on a whole grid. */
+typedef int (*astrea_reduce_fn)(void* user, void* device_int32, int count);
+int astrea_set_flag_reducer(astrea_ctx* ctx, astrea_reduce_fn fn, void* user);
 int astrea_program_length(const astrea_ctx* ctx);
 int astrea_instr_is_operator(const astrea_ctx* ctx, int instr);
 /* 1 if instruction `instr` reads ghost rows of a register (a spatial operator, or the inverse reconstruction of

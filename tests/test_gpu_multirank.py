@@ -24,11 +24,12 @@ def _worker(rank, world, port, spec, outdir, overlap):
     torch.cuda.set_device(rank)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    config, cells, subgrid, solver, timestep, bc, steps = spec
+    config, cells, subgrid, solver, timestep, bc, steps = spec[:7]
+    author = spec[7] if len(spec) > 7 else "mc"
     full = np.load(os.path.join(outdir, "g0.npy"))
     rows = cells // world
     sim = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, device=rank, rank=rank, world=world,
-                     cells_x=rows, grid=full[rank * rows:(rank + 1) * rows], overlap=overlap)
+                     cells_x=rows, grid=full[rank * rows:(rank + 1) * rows], overlap=overlap, ppm_author=author)
     sim.set_time(0.0)
     for _ in range(steps):
         sim.step_async()
@@ -42,7 +43,9 @@ def _worker(rank, world, port, spec, outdir, overlap):
 
 SPECS = [("ll3", 256, "ppm", "hllc", "ssprk(3,3)", "wrap", 2), ("ll4", 256, "weno5", "lf", "ssprk(2,2)", "edge", 3),
          ("khi", 192, "plm", "hllc", "rk4", "wrap", 2), ("orszag-tang", 192, "plm", "hlld", "ssprk(3,3)", "wrap", 3),
-         ("orszag-tang", 160, "ppm", "hlld", "ssprk(2,2)", "edge", 2)]
+         ("orszag-tang", 160, "ppm", "hlld", "ssprk(2,2)", "edge", 2),
+         # PPM authors 'c' / 'ph': grid-wide any() switches OR-ed across the slabs with one NCCL all-reduce per flag pass
+         ("ll3", 256, "ppm", "hllc", "ssprk(2,2)", "wrap", 2, "c"), ("khi", 192, "ppm", "lf", "ssprk(3,3)", "wrap", 2, "ph")]
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
@@ -52,10 +55,11 @@ def test_two_gpus_equal_one(spec, overlap):
     import torch.multiprocessing as mp
     from astrea_b200.initial import initial_state
     from astrea_b200.simulation import Simulation
-    config, cells, subgrid, solver, timestep, bc, steps = spec
+    config, cells, subgrid, solver, timestep, bc, steps = spec[:7]
+    author = spec[7] if len(spec) > 7 else "mc"
     high = subgrid.startswith("w") or subgrid == "ppm"
     g0 = initial_state(config, cells, 2, 1.4, high, boundary=bc)
-    single = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, grid=g0)
+    single = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, grid=g0, ppm_author=author)
     want_dts = single.run(steps)
     want = single.state()
     single.close()

@@ -18,11 +18,13 @@ def _worker(rank, world, rendezvous, spec, outdir):
     from astrea_b200.simulation import Simulation
     dist.init_process_group("gloo", init_method="file://" + rendezvous, rank=rank, world_size=world)
     lib = _native.bind(build.HOSTSIM_LIB)
-    config, cells, subgrid, solver, timestep, bc, steps = spec
+    config, cells, subgrid, solver, timestep, bc, steps = spec[:7]
+    author = spec[7] if len(spec) > 7 else "mc"
     full = np.load(os.path.join(outdir, "g0.npy"))
     rows = cells // world
     sim = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, rank=rank, world=world, cells_x=rows,
-                     grid=full[rank * rows:(rank + 1) * rows], overlap=(world == 3), _lib=lib, threads_2d=32, segment_2d=9)
+                     grid=full[rank * rows:(rank + 1) * rows], overlap=(world == 3), _lib=lib, threads_2d=32, segment_2d=9,
+                     ppm_author=author)
     dts = sim.run(steps)
     np.save(os.path.join(outdir, f"slab{rank}.npy"), sim.state())
     np.save(os.path.join(outdir, f"dts{rank}.npy"), np.array(dts))
@@ -50,7 +52,10 @@ SPECS = [("ll3", 32, "ppm", "hllc", "ssprk(3,3)", "wrap", 2),
          ("orszag-tang", 32, "plm", "hlld", "ssprk(3,3)", "wrap", 3),
          ("orszag-tang", 36, "ppm", "hlld", "ssprk(2,2)", "edge", 2),
          ("mhd rotor", 32, "weno5", "hllc", "ssprk(3,3)", "wrap", 2),
-         ("orszag-tang", 32, "pcm", "hlld", "ssprk(10,4)", "wrap", 1)]
+         ("orszag-tang", 32, "pcm", "hlld", "ssprk(10,4)", "wrap", 1),
+         # PPM authors 'c' / 'ph': the grid-wide any() switches are OR-ed across the slabs (astrea_set_flag_reducer)
+         ("ll3", 32, "ppm", "hllc", "ssprk(2,2)", "wrap", 2, "c"), ("khi", 36, "ppm", "lf", "ssprk(3,3)", "wrap", 2, "ph"),
+         ("ll4", 32, "ppm", "lf", "euler", "edge", 2, "ph"), ("sod", 32, "ppm", "hllc", "ssprk(2,2)", "edge", 2, "c")]
 
 
 @pytest.mark.parametrize("spec", SPECS, ids=["-".join(map(str, s[:6])) for s in SPECS])
@@ -59,13 +64,14 @@ def test_two_ranks_equal_one(hostsim_lib, spec, world):
     import torch.multiprocessing as mp
     from astrea_b200.initial import initial_state
     from astrea_b200.simulation import Simulation
-    config, cells, subgrid, solver, timestep, bc, steps = spec
+    config, cells, subgrid, solver, timestep, bc, steps = spec[:7]
+    author = spec[7] if len(spec) > 7 else "mc"
     if cells % world:
         cells = cells // world * world
         spec = (config, cells) + spec[2:]
     high = subgrid.startswith("w") or subgrid == "ppm"
     g0 = initial_state(config, cells, 2, 1.4, high, boundary=bc)
-    single = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, grid=g0, _lib=hostsim_lib)
+    single = Simulation(config, cells, 2, subgrid, solver, timestep, boundary=bc, grid=g0, _lib=hostsim_lib, ppm_author=author)
     want_dts = single.run(steps)
     want = single.state()
     want_snapshot = single.snapshot()
