@@ -30,7 +30,13 @@ int launch_recon(int scheme, const ReconStageParams& p, int gx, int gy, int nthr
     switch (scheme) {
         case SCH_PLM: return by_outputs<SCH_PLM, false>(p, gx, gy, nthreads, st);
         case SCH_PPM:
-            if (p.ppm_author != PPM_MC) return run<ReconStage<SCH_PPM, true>>(p, gx, gy, nthreads, st);
+            if (p.ppm_author != PPM_MC) {
+#ifdef ASTREA_DEVICE_BUILD
+                // authors 'c' / 'ph' with constrained transport: transposed face states, stored lane by lane (rare path)
+                if (ReconStage<SCH_PPM, true>::staged_outputs(p)) return run<ReconStage<SCH_PPM, true, false, true>>(p, gx, gy, nthreads, st);
+#endif
+                return run<ReconStage<SCH_PPM, true>>(p, gx, gy, nthreads, st);
+            }
             return by_outputs<SCH_PPM, false>(p, gx, gy, nthreads, st);
         case SCH_WENO3: return by_outputs<SCH_WENO3, false>(p, gx, gy, nthreads, st);
         case SCH_WENO5: return by_outputs<SCH_WENO5, false>(p, gx, gy, nthreads, st);
