@@ -154,12 +154,26 @@ struct PrimBothStage {
         double* W = Q + VS::N * SX * SY;           // pointwise primitives of the same cells
         double* T = W + VS::N * SX * SY;           // [N][TX][PT] y-frame result, staged for the transposed write
         ex.phase([&](int tid) {
-            for (int e = tid; e < SX * SY; e += MAX_THREADS) {
+            // the tile (with its ring) is PER cells per thread: all their loads are issued before the first conversion, so
+            // that a thread has PER x N loads in flight instead of N (the stage is bound by load latency and its barriers)
+            constexpr int PER = (SX * SY + MAX_THREADS - 1) / MAX_THREADS;
+            double qs[PER][VS::N];
+#pragma unroll
+            for (int m = 0; m < PER; ++m) {
+                const int e = tid + m * MAX_THREADS;
                 const int x = e % SX, y = e / SX;
-                const int64_t c = clamp_index(c0 - 1 + x, p.c_min, p.c_max), r = clamp_index(r0 - 1 + y, p.r_min, p.r_max);
+                const int64_t c = clamp_index(c0 - 1 + x, p.c_min, p.c_max), r = clamp_index(r0 - 1 + (y < SY ? y : SY - 1), p.r_min, p.r_max);
+#pragma unroll
+                for (int k = 0; k < VS::N; ++k) qs[m][k] = *p.q.at(r, VS::at(k), c);
+            }
+#pragma unroll
+            for (int m = 0; m < PER; ++m) {
+                const int e = tid + m * MAX_THREADS;
+                if (e >= SX * SY) continue;
+                const int x = e % SX, y = e / SX;
                 double q[NVAR], w[NVAR];
 #pragma unroll
-                for (int k = 0; k < VS::N; ++k) q[VS::at(k)] = *p.q.at(r, VS::at(k), c);
+                for (int k = 0; k < VS::N; ++k) q[VS::at(k)] = qs[m][k];
                 prim_of_cons_t<HYDRO>(q, w, gamma, g);
 #pragma unroll
                 for (int k = 0; k < VS::N; ++k) { Q[(k * SY + y) * SX + x] = q[VS::at(k)]; W[(k * SY + y) * SX + x] = w[VS::at(k)]; }
