@@ -481,10 +481,10 @@ int run_special(astrea_ctx* c, const Instr& ins, int external_rows) {
     Plane reg = c->regs[ins.out].plane;
     if (int e = fill_halo(c, reg, external_rows)) return e;
     RefineFieldParams rp{reg, make_plane(c->ws.mem, c->ncol, GHOST), c->nrow, c->ncol, g.nx_global, g.x_offset, g.boundary, 0};
-    const int gx = (int)((c->ncol + 127) / 128);
-    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, (int)c->nrow, 128, 0, c->st)); }
-    rp.copy_back = 1;
-    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, (int)c->nrow, 128, 0, c->st)); }
+    const int gx = (int)((c->ncol + RefineFieldKernel::TX - 1) / RefineFieldKernel::TX), gy = (int)((c->nrow + RefineFieldKernel::TY - 1) / RefineFieldKernel::TY);
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, gy, 256, RefineFieldKernel::smem_bytes(), c->st)); }
+    rp.copy_back = 1;       // the refinement reads neighbours of what it replaces: out of place, then copied back
+    { Timed timed(c, CLS_UPDATE); ASTREA_TRY(launch<RefineFieldKernel>(rp, gx, gy, 256, 0, c->st)); }
     return 0;
 }
 

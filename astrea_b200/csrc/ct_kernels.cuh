@@ -130,52 +130,92 @@ struct RefineFieldParams {
     int bc;
     int copy_back;     // 1: this launch copies out -> in instead
 };
+// Tiled: a block refines TX x TY cells.  The three levels of the reconstruction (face-centred value, 4-point centre
+// interpolation, centre -> average) are built once per tile in shared memory instead of being re-derived per cell (the
+// per-cell form evaluates ~60 loads and ~20 face conversions per cell and component; 4.3 ms per step at 4096^2).  Every
+// level is read at the MAPPED index ("pad the derived array": at a physical 'edge' boundary the neighbour beyond the
+// domain is the boundary entry of the derived array itself, not a value derived from ghost cells), so a level only has
+// to exist at positions of the domain, and a mapped index never leaves the tile's halo.
 struct RefineFieldKernel {
     using Params = RefineFieldParams;
-    static constexpr int MAX_THREADS = 128;
+    static constexpr int MAX_THREADS = 256;
+    static constexpr int TX = 32, TY = 8, H = 3;
+    static constexpr int GW = TX + 2 * H, GH = TY + 2 * H;     // every level is stored on the tile + H halo grid
+    static size_t smem_bytes() { return sizeof(double) * 6 * GW * GH; }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
-        const int NT = ex.nthreads();
-        ex.phase([&](int tid) {
-            const int64_t j = (int64_t)bx * NT + tid, i = by;
-            if (j >= p.ncol) return;
-            if (p.copy_back) {
+        const int64_t c0 = (int64_t)bx * TX, r0 = (int64_t)by * TY;
+        if (p.copy_back) {
+            ex.phase([&](int tid) {
+                const int64_t j = c0 + tid % TX, i = r0 + tid / TX;
+                if (j >= p.ncol || i >= p.nrow) return;
                 *p.in.at(i, 5, j) = *p.out.at(i, 5, j);
                 *p.in.at(i, 6, j) = *p.out.at(i, 6, j);
-                return;
-            }
-            const bool edge = p.bc == BC_EDGE;
-            const double c24 = 1.0 / 24.0;
-            auto mx = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.x_off, 0, p.nx_glob - 1) - p.x_off : r; };
-            auto my = [&](int64_t c) -> int64_t { return edge ? clamp_index(c, 0, p.ncol - 1) : c; };
-            // Bx: sweep direction x (rows), transverse y.  mag_field.py:199-207 in the x frame.
-            {
-                auto g = [&](int64_t r, int64_t c) { return *p.in.at(r, 5, c); };
-                auto fc = [&](int64_t r, int64_t c) {      // fv.high_order_convert('avg', ., 'face'): x - d2_y/24
-                    const double a = g(r, c);
-                    return a - c24 * ((g(r, my(c + 1)) - a) - (a - g(r, my(c - 1))));
-                };
-                auto cc = [&](int64_t r, int64_t c) {      // 4-point face -> centre interpolation along x
-                    return -1.0 / 16.0 * (fc(mx(r - 1), c) + fc(mx(r + 2), c)) + 9.0 / 16.0 * (fc(r, c) + fc(mx(r + 1), c));
-                };
-                const double a = cc(i, j);
-                double ca = a + c24 * ((cc(mx(i + 1), j) - a) - (a - cc(mx(i - 1), j)));
-                ca = ca + c24 * ((cc(i, my(j + 1)) - a) - (a - cc(i, my(j - 1))));
+            });
+            return;
+        }
+        double* G5 = ex.smem();            // face averages of Bx / By
+        double* G6 = G5 + GW * GH;
+        double* F5 = G6 + GW * GH;         // face-centred values
+        double* F6 = F5 + GW * GH;
+        double* C5 = F6 + GW * GH;         // cell-centred values
+        double* C6 = C5 + GW * GH;
+        const bool edge = p.bc == BC_EDGE;
+        const double c24 = 1.0 / 24.0;
+        // boundary maps of the reference's np.pad on the derived arrays; tile-local addressing
+        auto mx = [&](int64_t r) -> int64_t { return edge ? clamp_index(r + p.x_off, 0, p.nx_glob - 1) - p.x_off : r; };
+        auto my = [&](int64_t c) -> int64_t { return edge ? clamp_index(c, 0, p.ncol - 1) : c; };
+        auto at = [&](const double* a, int64_t r, int64_t c) -> double { return a[(r - r0 + H) * GW + (c - c0 + H)]; };
+        auto inside = [&](int64_t r, int64_t c) -> bool {      // positions at which a derived array exists
+            return !edge || (r + p.x_off >= 0 && r + p.x_off <= p.nx_glob - 1 && c >= 0 && c <= p.ncol - 1);
+        };
+        // visit the tile grown by (hr, hc) cells
+        auto region = [&](int tid, int hr_lo, int hr_hi, int hc_lo, int hc_hi, auto&& f) {
+            const int w = TX + hc_lo + hc_hi, h = TY + hr_lo + hr_hi;
+            for (int e = tid; e < w * h; e += MAX_THREADS) f(r0 - hr_lo + e / w, c0 - hc_lo + e % w);
+        };
+        ex.phase([&](int tid) {
+            region(tid, H, H, H, H, [&](int64_t r, int64_t c) {
+                const int k = (int)((r - r0 + H) * GW + (c - c0 + H));
+                G5[k] = *p.in.at(r, 5, c);
+                G6[k] = *p.in.at(r, 6, c);
+            });
+        });
+        ex.phase([&](int tid) {
+            // fv.high_order_convert('avg', ., 'face'): x - d2_transverse / 24      (mag_field.py:199-207)
+            region(tid, 2, 3, 1, 1, [&](int64_t r, int64_t c) {          // Bx: sweep x, transverse y
+                if (!inside(r, c)) return;
+                const double a = at(G5, r, c);
+                F5[(r - r0 + H) * GW + (c - c0 + H)] = a - c24 * ((at(G5, r, my(c + 1)) - a) - (a - at(G5, r, my(c - 1))));
+            });
+            region(tid, 1, 1, 2, 3, [&](int64_t r, int64_t c) {          // By: sweep y, transverse x
+                if (!inside(r, c)) return;
+                const double a = at(G6, r, c);
+                F6[(r - r0 + H) * GW + (c - c0 + H)] = a - c24 * ((at(G6, mx(r + 1), c) - a) - (a - at(G6, mx(r - 1), c)));
+            });
+        });
+        ex.phase([&](int tid) {
+            // 4-point face -> centre interpolation along the sweep
+            region(tid, 1, 1, 1, 1, [&](int64_t r, int64_t c) {
+                if (!inside(r, c)) return;
+                const int k = (int)((r - r0 + H) * GW + (c - c0 + H));
+                C5[k] = -1.0 / 16.0 * (at(F5, mx(r - 1), c) + at(F5, mx(r + 2), c)) + 9.0 / 16.0 * (at(F5, r, c) + at(F5, mx(r + 1), c));
+                C6[k] = -1.0 / 16.0 * (at(F6, r, my(c - 1)) + at(F6, r, my(c + 2))) + 9.0 / 16.0 * (at(F6, r, c) + at(F6, r, my(c + 1)));
+            });
+        });
+        ex.phase([&](int tid) {
+            const int64_t j = c0 + tid % TX, i = r0 + tid / TX;
+            if (j >= p.ncol || i >= p.nrow) return;
+            {   // centre -> average, axis 0 of the component's own frame first: x then y for Bx
+                const double a = at(C5, i, j);
+                double ca = a + c24 * ((at(C5, mx(i + 1), j) - a) - (a - at(C5, mx(i - 1), j)));
+                ca = ca + c24 * ((at(C5, i, my(j + 1)) - a) - (a - at(C5, i, my(j - 1))));
                 *p.out.at(i, 5, j) = ca;
             }
-            // By: sweep direction y (columns), transverse x: the same in the transposed frame (axis 0 = y first)
-            {
-                auto g = [&](int64_t r, int64_t c) { return *p.in.at(r, 6, c); };
-                auto fc = [&](int64_t r, int64_t c) {
-                    const double a = g(r, c);
-                    return a - c24 * ((g(mx(r + 1), c) - a) - (a - g(mx(r - 1), c)));
-                };
-                auto cc = [&](int64_t r, int64_t c) {
-                    return -1.0 / 16.0 * (fc(r, my(c - 1)) + fc(r, my(c + 2))) + 9.0 / 16.0 * (fc(r, c) + fc(r, my(c + 1)));
-                };
-                const double a = cc(i, j);
-                double ca = a + c24 * ((cc(i, my(j + 1)) - a) - (a - cc(i, my(j - 1))));
-                ca = ca + c24 * ((cc(mx(i + 1), j) - a) - (a - cc(mx(i - 1), j)));
+            {   // y then x for By
+                const double a = at(C6, i, j);
+                double ca = a + c24 * ((at(C6, i, my(j + 1)) - a) - (a - at(C6, i, my(j - 1))));
+                ca = ca + c24 * ((at(C6, mx(i + 1), j) - a) - (a - at(C6, mx(i - 1), j)));
                 *p.out.at(i, 6, j) = ca;
             }
         });
