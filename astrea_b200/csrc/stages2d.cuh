@@ -134,7 +134,14 @@ struct PrimBothStage {
     using Params = PrimBothParams;
     using VS = VarSet<HYDRO>;
     static constexpr int MAX_THREADS = 256;
-    static constexpr int TX = 32, TY = 16, SX = TX + 2, SY = TY + 2, PT = TY + 1;
+#ifndef ASTREA_PRIM_TY
+#define ASTREA_PRIM_TY 16
+#endif
+#ifndef ASTREA_PRIM_MIN_BLOCKS
+#define ASTREA_PRIM_MIN_BLOCKS 0
+#endif
+    static constexpr int MIN_BLOCKS = ASTREA_PRIM_MIN_BLOCKS;      // 0: let ptxas choose
+    static constexpr int TX = 32, TY = ASTREA_PRIM_TY, SX = TX + 2, SY = TY + 2, PT = TY + 1;
     static size_t smem_bytes() { return sizeof(double) * VS::N * (2 * SX * SY + TX * PT); }
     template <class Ex>
     static HD void block(const Params& p, int bx, int by, Ex& ex) {
@@ -510,13 +517,13 @@ struct ReconStage {
                         for (int pass = 0; pass < 4; ++pass) {
                             const int row = pass * 8 + (lane_ >> 2);
                             if (row >= rows) continue;
-                            for (int e = lane_ & 3; e < pending; e += 4) {
-                                if (tr) {
-                                    *p.wp.at(t_warp + row, v, flush_i0 + e) = stg[e * 33 + row];
-                                    *p.wm.at(t_warp + row, v, flush_i0 + e) = stg[(SD + e) * 33 + row];
-                                } else {
-                                    *p.wf.at(t_warp + row, v, flush_i0 + e) = stg[e * 33 + row];
-                                }
+                            if (tr) {
+                                double* dp = p.wp.at(t_warp + row, v, flush_i0);
+                                double* dm = p.wm.at(t_warp + row, v, flush_i0);
+                                for (int e = lane_ & 3; e < pending; e += 4) { dp[e] = stg[e * 33 + row]; dm[e] = stg[(SD + e) * 33 + row]; }
+                            } else {
+                                double* df = p.wf.at(t_warp + row, v, flush_i0);
+                                for (int e = lane_ & 3; e < pending; e += 4) df[e] = stg[e * 33 + row];
                             }
                         }
                         warp_sync(0xffffffffu);
@@ -641,15 +648,17 @@ struct FluxStage {
     using VS = VarSet<HYDRO>;
     static constexpr int MAX_THREADS = 128;
 #ifndef ASTREA_FLUX_MIN_BLOCKS
-#define ASTREA_FLUX_MIN_BLOCKS 4
+#define ASTREA_FLUX_MIN_BLOCKS 3
 #endif
 #ifndef ASTREA_FLUX_MIN_BLOCKS_HYDRO
-#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 5
+#define ASTREA_FLUX_MIN_BLOCKS_HYDRO 4
 #endif
-    // 8-variable kernels: 128 threads x 4 blocks = 16 warps per SM at 128 registers (measured best of 2..5);
-    // hydro kernels: 5 blocks = 20 warps at 96 registers.  With the branch-free division the compiler interleaves
+    // 8-variable kernels: 128 threads x 3 blocks = 12 warps per SM at 168 registers (the HLLD kernel spills 1.4 KB per
+    // thread at 128 registers; Orszag-Tang 4096^2, flux stages per step at 4 / 3 / 2 blocks: 15.3 / 14.4 / 16.2 ms);
+    // hydro kernels: 4 blocks = 16 warps at 128 registers too.  With the branch-free division the compiler interleaves
     // independent chains, so registers buy more than warps: 7 blocks (72 registers, ~70 spill instructions per thread)
-    // 2.06 ms, 6 blocks 2.04 ms, 5 blocks (no spills) 2.01 ms per step of flux stages at 2048^2 (r1l).
+    // 2.06 ms, 6 blocks 2.04 ms, 5 blocks 2.01 ms per step of flux stages at 2048^2 (r1l); round 2 (same kernels with the
+    // shared-memory exchange): 5 / 4 / 3 blocks 1.85 / 1.78 / 1.94 ms at 2048^2 and 27.5 / 26.8 / 29.1 ms at 8192^2.
     // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
     // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
     static constexpr int MIN_BLOCKS = HYDRO ? ASTREA_FLUX_MIN_BLOCKS_HYDRO : ASTREA_FLUX_MIN_BLOCKS;
@@ -664,6 +673,8 @@ struct FluxStage {
     // transverse exchange through shared memory instead of shuffles (runtime.cuh put / nbr): hydro kernels only, the
     // nine exchanged arrays of a four-variable state are 9 KB per warp (37 KB per block, 5 blocks per SM).  Measured at
     // 2048^2 PPM+HLLC: 2.01 -> 1.89 ms of flux stages per step (-250 of ~2150 static instructions per thread)
+    // (the eight-variable kernels keep the shuffles: with 72 slots per warp in shared memory the HLLD flux stages of
+    // Orszag-Tang 4096^2 took 17.1 instead of 14.4 ms per step, both at 3 blocks per SM)
     static constexpr bool XS = HYDRO && !LW && (ASTREA_FLUX_SMEM_EXCHANGE != 0);
 #ifndef ASTREA_FLUX_BLOCK_TILE
 #define ASTREA_FLUX_BLOCK_TILE 1
@@ -927,7 +938,8 @@ struct FluxStage {
                 cfp[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], S_FP * VS::N + kv, [&](int k) { return tls[k].fp[v]; });
                 cfm[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], S_FM * VS::N + kv, [&](int k) { return tls[k].fm[v]; });
             }
-            // (solving both Riemann problems of the interface here, side by side, was measured slower: 2.05 vs 2.01 ms)
+            // (solving both Riemann problems of the interface here, side by side, was measured slower twice: round 1 at 96
+            // registers 2.05 vs 2.01 ms at 2048^2, round 2 at 128 registers 27.6 vs 26.8 ms at 8192^2)
             solve(st, st.xp, st.xm, cqp, cqm, cfp, cfm, st.fc);
         });
         // D: F = F_c - d2_t(F_avg)/24 (fv.py:147-153)

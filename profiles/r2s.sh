@@ -1,0 +1,19 @@
+#!/bin/bash
+out=gpurun_out; tag=r2s; mkdir -p $out
+Q="--no-cpu --no-e2e --no-parity-check"
+b() { name=$1; shift; timeout 300 python bench.py $Q "$@" > $out/${tag}_$name.json 2> $out/${tag}_$name.err; python - <<PY
+import json
+try:
+    d=json.load(open("$out/${tag}_$name.json")); r=d["roofline"]["class_ms_per_step"]
+    print("$name", round(d["ms_per_step"],4), {k:round(v,3) for k,v in r.items()}, d["gpu_launches"])
+except Exception as e: print("$name failed", e)
+PY
+}
+ASTREA_B200_LIB=astrea_b200/lib/variants/sbs4.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "golden or matrix" 2>&1 | tail -2
+for v in sbs4 sbs5; do
+ASTREA_B200_LIB=astrea_b200/lib/variants/$v.so b c5_$v --workload c5 --steps 20
+ASTREA_B200_LIB=astrea_b200/lib/variants/$v.so b c2_$v --workload c2 --steps 300
+done
+ASTREA_B200_LIB=astrea_b200/lib/variants/fb4.so b c2_fb4_bt1 --workload c2 --steps 300 --flux-block-tile 1
+ASTREA_B200_LIB=astrea_b200/lib/variants/fb4.so b c5_fb4_bt0 --workload c5 --steps 20 --flux-block-tile 0
+ASTREA_B200_LIB=astrea_b200/lib/variants/fb4.so b c3_fb4 --workload c3 --steps 40

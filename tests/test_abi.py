@@ -69,6 +69,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         '  printf("%zu %zu %zu %zu\\n", sizeof(astrea_cfg), offsetof(astrea_cfg, gamma), offsetof(astrea_cfg, nx_global), offsetof(astrea_cfg, flags));\n'
         '  printf("%zu %zu %zu\\n", sizeof(astrea_region), offsetof(astrea_region, a), offsetof(astrea_region, state));\n'
         '  printf("%zu %zu %zu %zu\\n", sizeof(astrea_init_spec), offsetof(astrea_init_spec, background), offsetof(astrea_init_spec, nregions), offsetof(astrea_init_spec, regions));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(astrea_init_profile), offsetof(astrea_init_profile, along), offsetof(astrea_init_profile, values));\n'
         '  return 0;\n}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
@@ -76,5 +77,6 @@ def test_struct_layouts_match_the_header(tmp_path):
     got = [int(x) for x in out]
     want = [ctypes.sizeof(N.Cfg), N.Cfg.gamma.offset, N.Cfg.nx_global.offset, N.Cfg.flags.offset,
             ctypes.sizeof(N.Region), N.Region.a.offset, N.Region.state.offset,
-            ctypes.sizeof(N.InitSpec), N.InitSpec.background.offset, N.InitSpec.nregions.offset, N.InitSpec.regions.offset]
+            ctypes.sizeof(N.InitSpec), N.InitSpec.background.offset, N.InitSpec.nregions.offset, N.InitSpec.regions.offset,
+            ctypes.sizeof(N.InitProfile), N.InitProfile.along.offset, N.InitProfile.values.offset]
     assert got == want
