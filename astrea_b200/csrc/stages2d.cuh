@@ -299,10 +299,11 @@ struct ReconStage {
     using Params = ReconStageParams;
     static constexpr int MAX_THREADS = 128;
 #ifndef ASTREA_RECON_MIN_BLOCKS
-#define ASTREA_RECON_MIN_BLOCKS 5
+#define ASTREA_RECON_MIN_BLOCKS 4
 #endif
-    // the march is bound by load latency: 5 blocks (20 warps, 96 registers, a few spills) measured best of 4 / 5 / 6 / 8
-    // with the prefetch queue (PPM 2048^2: 0.99 / 0.91 / 1.11 ms per step; WENO5 4096^2: 4.93 / 4.42 / 4.47 ms)
+    // register-prefetch march: 4 blocks (16 warps, 128 registers, no spills).  Round 1 measured 5 blocks best (PPM 2048^2:
+    // 4 / 5 / 6 blocks 0.99 / 0.91 / 1.11 ms per step); with the branch-free limiters and the unrolled window of this round
+    // WENO5 4096^2 takes 4.25 / 4.52 / 4.40 ms at 4 / 5 / 6 blocks.
 #ifndef ASTREA_RECON_MIN_BLOCKS_BULK
 #define ASTREA_RECON_MIN_BLOCKS_BULK 4
 #endif
