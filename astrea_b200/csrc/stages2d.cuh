@@ -465,7 +465,12 @@ struct ReconStage {
                 const bool tr = p.cell_aligned && out_t;
                 double* out_p = tr ? p.wp.at(t, v, mid_lo) : p.wp.at(mid_lo, v, t);
                 double* out_m = tr ? p.wm.at(t, v, mid_lo) : p.wm.at(p.cell_aligned ? mid_lo : mid_lo + 1, v, t);
+#ifdef ASTREA_DEVICE_BUILD
+                // on the device face states are wanted by constrained transport only, whose launches are the STAGED ones
+                double* out_f = (STAGED && p.wf.base != nullptr && !p.cell_aligned) ? face_slot(mid_lo) : nullptr;
+#else
                 double* out_f = (p.wf.base != nullptr && !p.cell_aligned) ? face_slot(mid_lo) : nullptr;
+#endif
                 const int64_t rp_p = tr ? 1 : p.wp.row_pitch, rp_m = tr ? 1 : p.wm.row_pitch, rp_f = wf_t ? 1 : p.wf.row_pitch;
                 int pending = 0;                 // staged outputs: cells in the staging tile, first of them is cell flush_i0
                 int64_t flush_i0 = mid_lo;
@@ -571,12 +576,16 @@ struct ReconStage {
                         }
                         if (i0 < mid_hi) mbar_wait(bars + k % NSLOT, (uint32_t)((k / NSLOT) & 1));
                         const double* grp = ring + (k % NSLOT) * NW * 32 + (t - t0);   // a lane beyond the range repeats the last column
-                        static_for<0, NW>([&](auto uc) {
-                            constexpr int U = decltype(uc)::value;
-                            const int64_t i = i0 + U;
-                            if (i > mid_hi) return;
-                            step(uc, i, i < mid_hi ? grp[U * 32] : 0.0);
-                        });
+                        if (i0 + NW <= mid_hi) {          // a full group: every cell exists and has a row ahead of it
+                            static_for<0, NW>([&](auto uc) { step(uc, i0 + decltype(uc)::value, grp[decltype(uc)::value * 32]); });
+                        } else {
+                            static_for<0, NW>([&](auto uc) {
+                                constexpr int U = decltype(uc)::value;
+                                const int64_t i = i0 + U;
+                                if (i > mid_hi) return;
+                                step(uc, i, i < mid_hi ? grp[U * 32] : 0.0);
+                            });
+                        }
                         flush(i0, i0 + NW > mid_hi);
                     }
                     warp_sync(mask);
@@ -598,17 +607,28 @@ struct ReconStage {
                     // The march is unrolled by the window length: in step U the stencil value at offset k sits in register
                     // (k + LO + U) mod NW, the oldest one is replaced by the row requested one cell early.
                     for (int64_t i0 = mid_lo; i0 <= mid_hi; i0 += NW) {
-                        static_for<0, NW>([&](auto uc) {
-                            constexpr int U = decltype(uc)::value;
-                            const int64_t i = i0 + U;
-                            if (i > mid_hi) return;
-                            const double ahead = queue[0];                      // row (i + 1) + HI
+                        if (i0 + NW + PF <= mid_hi) {      // a full group whose prefetches all stay inside the segment
+                            static_for<0, NW>([&](auto uc) {
+                                const double ahead = queue[0];                      // row (i + 1) + HI
 #pragma unroll
-                            for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
-                            queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
-                            in += rp;
-                            step(uc, i, ahead);
-                        });
+                                for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
+                                queue[PF - 1] = *in;                               // row (i + 1 + PF) + HI
+                                in += rp;
+                                step(uc, i0 + decltype(uc)::value, ahead);
+                            });
+                        } else {
+                            static_for<0, NW>([&](auto uc) {
+                                constexpr int U = decltype(uc)::value;
+                                const int64_t i = i0 + U;
+                                if (i > mid_hi) return;
+                                const double ahead = queue[0];                      // row (i + 1) + HI
+#pragma unroll
+                                for (int k = 0; k + 1 < PF; ++k) queue[k] = queue[k + 1];
+                                queue[PF - 1] = (i + 1 + PF <= mid_hi) ? *in : 0.0;    // row (i + 1 + PF) + HI
+                                in += rp;
+                                step(uc, i, ahead);
+                            });
+                        }
                         flush(i0, i0 + NW > mid_hi);
                     }
                 }
