@@ -60,7 +60,7 @@ typedef struct astrea_cfg {
     int64_t nx_global;
     int64_t x_offset;
     int32_t threads_2d;    /* 0 = default (128); threads per block of the 2D flux stage (a multiple of 32, <= 128) */
-    int32_t segment_2d;    /* 0 = default (64); cells a thread of the 2D reconstruction stage marches along the sweep */
+    int32_t segment_2d;    /* 0 = default (64; 128 from 4096 cells per sweep); cells a thread of the 2D reconstruction stage marches along the sweep */
     int32_t tile_1d;       /* 0 = default; cells per block of the 1D sweep kernel */
     int32_t flags;         /* bit 0: keep the general 8-variable kernels even when the grid has no v_z / B (testing);
                               bit 1: never replay astrea_step_async as a CUDA graph (small grids do by default);
