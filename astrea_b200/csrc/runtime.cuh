@@ -187,11 +187,18 @@ struct Stream { cudaStream_t s; };
 
 template <class K>
 inline int launch(const typename K::Params& p, int gx, int gy, int nthreads, size_t smem_bytes, Stream st) {
-    static size_t configured_bytes = 48 * 1024;     // per kernel: the opt-in dynamic shared-memory size set so far
-    if (smem_bytes > configured_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        configured_bytes = smem_bytes;
+    // per kernel and device (function attributes belong to the device's context; the entry points select the context's
+    // device before they launch): the opt-in dynamic shared-memory size set so far
+    if (smem_bytes > 48 * 1024) {
+        static size_t configured_bytes[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& have = configured_bytes[dev & 63];
+        if (smem_bytes > have) {
+            cudaError_t e = cudaFuncSetAttribute(kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return (int)e;
+            have = smem_bytes;
+        }
     }
     kernel_entry<K><<<dim3(gx, gy, 1), dim3(nthreads, 1, 1), smem_bytes, st.s>>>(p);
     return (int)cudaGetLastError();

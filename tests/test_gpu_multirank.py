@@ -70,3 +70,33 @@ def test_two_gpus_equal_one(spec, overlap):
         for r in range(2):
             assert list(np.load(os.path.join(tmp, f"dts{r}.npy"))) == want_dts
     assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")
+def test_two_devices_driven_by_one_host_thread():
+    """Contexts on different GPUs driven alternately from one thread (every entry point selects its context's device and
+    restores the caller's; kernel attributes are kept per device): both give the single-device result."""
+    import torch
+    from astrea_b200 import _native as N
+    from astrea_b200.initial import initial_state, problem
+    from astrea_b200.selectors import make_cfg
+    cells = 96
+    prob = problem("ll6", cells, 1.4)
+    g0 = initial_state("ll6", cells, 2, 1.4, True)
+    ctxs = []
+    for dev in (0, 1):
+        cfg = make_cfg(dimension=2, cells=cells, boundary="wrap", gamma=1.4, dx=prob["dx"], cfl=.5, subgrid="ppm", solver="hllc",
+                       timestep="ssprk(3,3)", device=dev)
+        ctxs.append(N.Context(cfg))
+    before = torch.cuda.current_device()
+    for c in ctxs:
+        c.upload(g0)
+    dts = [[], []]
+    for _ in range(3):
+        for k, c in enumerate(ctxs):          # interleaved: device 0, device 1, device 0, ...
+            dts[k].append(c.step())
+    a, b = ctxs[0].download(), ctxs[1].download()
+    assert torch.cuda.current_device() == before
+    for c in ctxs:
+        c.close()
+    assert dts[0] == dts[1] and np.array_equal(a, b)
