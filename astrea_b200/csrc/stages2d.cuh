@@ -8,14 +8,18 @@
 //                              pointwise conversion is evaluated once.
 //   ReconStage  wS -> w+, w-   reconstruction + limiter (schemes/*.py, limiters.py).  Thread per (column, variable)
 //                              marching along the sweep with the stencil in a rotating register window (the march is
-//                              unrolled by the window length): one load and two stores per cell and variable, rows
-//                              requested four cells ahead, no shared memory, no barrier.
+//                              unrolled by the window length): one load and two stores per cell and variable, no
+//                              block barrier.  The rows ahead arrive through the TMA engine's bulk copies into a per-warp
+//                              shared-memory ring (PLM, PPM: BULK) or through a register prefetch queue (WENO); outputs
+//                              wanted in the other frame by constrained transport leave through a shared-memory tile
+//                              (STAGED).
 //   FluxStage   w+- -> F       face conversion (fv.py:105-122 'face'), physical fluxes (constructor.py:113-125),
 //                              averaged-state wave speed (fv.py:157-169), Riemann flux of the face averages and of
 //                              the face-centred states, F = F_c - d2_t(F_avg)/24 (solvers.py:44-57, fv.py:147-153).
-//                              One warp per 32 transverse points of one interface row; transverse neighbours are
-//                              exchanged through per-warp shared-memory slots (four-variable hydro states) or by
-//                              warp shuffle (eight-variable states), everything else lives in registers.
+//                              One warp per 32 transverse points of one interface row — or, on wide grids, one block
+//                              per row of NT points (BTILE); transverse neighbours are exchanged through shared-memory
+//                              slots (four-variable hydro states) or by warp shuffle (eight-variable states),
+//                              everything else lives in registers.
 //
 // Every division and square root goes through a guard (common.cuh): the kernels run a branch-free pass first and a
 // warp (block, for the tiled primitive stages) repeats its work with the compiler's IEEE routines if an operand was
