@@ -86,6 +86,7 @@ _SIGNATURES = {
     "astrea_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_download_face_field": (C.c_int, [C.c_void_p, C.c_void_p]),
     "astrea_set_flag_reducer": (C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
+    "astrea_set_key_reducer": (C.c_int, [C.c_void_p, REDUCE_FN, C.c_void_p]),
     "astrea_program_length": (C.c_int, [C.c_void_p]),
     "astrea_instr_is_operator": (C.c_int, [C.c_void_p, C.c_int]),
     "astrea_instr_needs_halo": (C.c_int, [C.c_void_p, C.c_int]),
@@ -327,6 +328,18 @@ class Context:
                 return 1
         self._reducer = REDUCE_FN(trampoline)       # keep the callback object alive as long as the context
         self._check(self.lib.astrea_set_flag_reducer(self._h, self._reducer, None))
+
+    def set_key_reducer(self, fn):
+        """``fn(device_ptr, count)``: in-place cross-rank minimum of ``count`` uint64 on the context's stream (the
+        Lax-Wendroff column search on a decomposed grid)."""
+        def trampoline(_user, ptr, count):
+            try:
+                fn(ptr, count)
+                return 0
+            except Exception:
+                return 1
+        self._key_reducer = REDUCE_FN(trampoline)
+        self._check(self.lib.astrea_set_key_reducer(self._h, self._key_reducer, None))
 
     # -- step program (multi-GPU hosts drive it instruction by instruction)
     def program(self):

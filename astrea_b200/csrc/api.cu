@@ -109,6 +109,9 @@ struct astrea_ctx {
     // cross-rank OR of the grid-wide switches of the PPM authors 'c' / 'ph' on a decomposed grid (astrea_set_flag_reducer)
     astrea_reduce_fn reduce_fn = nullptr;
     void* reduce_user = nullptr;
+    // cross-rank minimum of the Lax-Wendroff search keys on a decomposed grid (astrea_set_key_reducer)
+    astrea_reduce_fn key_reduce_fn = nullptr;
+    void* key_reduce_user = nullptr;
     // transfers between the device and a pageable host array (the first grid of a run, np.empty destinations): LANES
     // host threads, each with its own stream and two page-locked bounce buffers (staged_copy)
     static constexpr int LANES = 12;
@@ -672,10 +675,16 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
                 fp.lw_pass = 0; fp.lw_keys = c->lw_keys;
                 if (lw) {      // search pass of the Lax-Wendroff column pick, per sweep
+                    if (c->slab() && c->key_reduce_fn == nullptr)
+                        return fail(c, ASTREA_E_STATE, "Lax-Wendroff picks its spectrum column over the whole grid (solvers.py:79-88): a decomposed "
+                                                       "grid needs astrea_set_key_reducer");
                     ASTREA_TRY(dev_ones(c->lw_keys, 4 * sizeof(unsigned long long), c->st));
                     fp.lw_pass = 1;
                     { Timed timed(c, CLS_SWEEP); ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, 1, fp, gx, gy, nthreads, c->st)); }
                     fp.lw_pass = 0;
+                    // first non-zero entry of each column over the whole grid: the smallest key of all slabs
+                    if (c->slab() && c->key_reduce_fn(c->key_reduce_user, c->lw_keys, 4) != 0)
+                        return fail(c, ASTREA_E_STATE, "the key reducer reported a failure");
                 }
                 Timed timed(c, CLS_SWEEP);
                 ASTREA_TRY(launch_flux(kind, g.solver, ax, sax, c->hydro ? 1 : 0, fp, gx, gy, nthreads, c->st));
@@ -754,9 +763,9 @@ int check_cfg(const astrea_cfg* g, std::string& why) {
     if (g->ppm_author < ASTREA_PPM_MC || g->ppm_author > ASTREA_PPM_PH) { why = "unknown PPM author"; return -1; }
     if (g->limiter < ASTREA_MINMOD || g->limiter > ASTREA_SUPERBEE) { why = "unknown slope limiter"; return -1; }
     if (g->solver < ASTREA_LLF || g->solver > ASTREA_HLLD) { why = "unknown solver"; return -1; }
-    if (g->solver == ASTREA_LW && (g->magnetic_2d || (g->dimension == 2 && g->nx != g->nx_global))) {
+    if (g->solver == ASTREA_LW && g->magnetic_2d) {
         why = "Lax-Wendroff (solvers.py:79-88) picks a spectrum column by a grid-wide lexicographic sort (SURVEY Q11): "
-              "available for states without v_z / B on one GPU";
+              "available for states without v_z / B";
         return -1;
     }
     if (g->integrator < ASTREA_EULER || g->integrator > ASTREA_SSPRK104) { why = "unknown integrator"; return -1; }
@@ -1282,6 +1291,13 @@ int astrea_set_flag_reducer(astrea_ctx* c, astrea_reduce_fn fn, void* user) {
     if (!c) return ASTREA_E_ARG;
     c->reduce_fn = fn;
     c->reduce_user = user;
+    return 0;
+}
+
+int astrea_set_key_reducer(astrea_ctx* c, astrea_reduce_fn fn, void* user) {
+    if (!c) return ASTREA_E_ARG;
+    c->key_reduce_fn = fn;
+    c->key_reduce_user = user;
     return 0;
 }
 

@@ -825,22 +825,24 @@ struct FluxStage {
                 const int64_t j = (int64_t)by * nwarp + w, t = (int64_t)bx * OWN - H + lane_id;
                 const int64_t n = p.ns_glob;
                 const int64_t first = PCM ? 0 : 1, last = PCM ? n - 1 : n;     // interfaces 1..N, or cells 0..N-1
-                if (lane_id < H || lane_id >= 32 - H || t < 0 || t >= p.nt || j < first || j > last) return;
+                // a slab searches the entries it holds; positions in the array are those of the whole grid
+                const int64_t jg = j + p.s_off, tg = t + p.t_off;
+                if (lane_id < H || lane_id >= 32 - H || t < 0 || t >= p.nt || j > p.ns || jg < first || jg > last) return;
                 double a[NVAR];
                 state_at(j, t, a);
                 const double u = a[1 + AX], c = dsqrt(ddiv(gamma * a[4], a[0], g), g);
                 const double col[3] = {u - c, u, u + c};
                 // padded rows this entry appears in
-                int64_t rows[3] = {PCM ? j + 1 : j, -1, -1};
+                int64_t rows[3] = {PCM ? jg + 1 : jg, -1, -1};
                 const bool wrap = p.bc == BC_WRAP;
-                if (j == (wrap ? last : first)) rows[1] = 0;            // pad in front: np.pad wraps / repeats the edge
-                if (j == (wrap ? first : last)) rows[2] = n + 1;
+                if (jg == (wrap ? last : first)) rows[1] = 0;            // pad in front: np.pad wraps / repeats the edge
+                if (jg == (wrap ? first : last)) rows[2] = n + 1;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (!(col[k] != 0.0)) continue;
                     for (int q = 0; q < 3; ++q) {
                         if (rows[q] < 0) continue;
-                        const unsigned long long kk = ((unsigned long long)(rows[q] * p.nt + t) << 1) | (col[k] > 0.0 ? 1ull : 0ull);
+                        const unsigned long long kk = ((unsigned long long)(rows[q] * p.nt_glob + tg) << 1) | (col[k] > 0.0 ? 1ull : 0ull);
                         if (kk < key[k]) key[k] = kk;
                     }
                 }

@@ -11,6 +11,7 @@ first operator it all-reduces (MAX) the two per-axis wave speeds so that every r
 """
 import ctypes
 
+import os
 import numpy as np
 
 from . import _native as N
@@ -26,15 +27,16 @@ class _CudaBlock:
                                          "strides": None}
 
 
-def _tensor_at(ptr, count, on_device, device_index=0, int32=False):
+def _tensor_at(ptr, count, on_device, device_index=0, int32=False, int64=False):
     import torch
     if on_device:
         block = _CudaBlock(ptr, count)
-        if int32:
-            block.__cuda_array_interface__["typestr"] = "<i4"
+        if int32 or int64:
+            block.__cuda_array_interface__["typestr"] = "<i4" if int32 else "<i8"
         return torch.as_tensor(block, device=torch.device("cuda", device_index))
-    buf = ((ctypes.c_int32 if int32 else ctypes.c_double) * count).from_address(ptr)
-    return torch.from_numpy(np.frombuffer(buf, dtype=np.int32 if int32 else np.float64))
+    ctype, dtype = (ctypes.c_int32, np.int32) if int32 else ((ctypes.c_int64, np.int64) if int64 else (ctypes.c_double, np.float64))
+    buf = (ctype * count).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=dtype))
 
 
 class SlabExchange:
@@ -148,6 +150,24 @@ class SlabExchange:
             self.ctx.sync()
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
 
+    def reduce_keys(self, ptr, count):
+        """In-place minimum over the ranks of ``count`` unsigned 64-bit keys on the device, ordered on the context's
+        stream: the first non-zero entry of the Lax-Wendroff spectrum columns over the whole grid (solvers.py:79-88).
+        torch has no uint64 reduction: flipping the top bit maps the unsigned order onto the signed one."""
+        dist = self.dist
+        keys = _tensor_at(ptr, count, self.on_device, self.device_index, int64=True)
+        top = -(1 << 63)
+        if self.on_device:
+            with self.torch.cuda.stream(self.stream):
+                keys.bitwise_xor_(top)
+                dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+                keys.bitwise_xor_(top)
+        else:
+            self.ctx.sync()
+            keys.bitwise_xor_(top)
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+            keys.bitwise_xor_(top)
+
     def global_eigmax(self):
         self.reduce_eigmax()
         return self.ctx.read_eigmax()      # synchronises; raises NonFiniteError on every rank if any rank saw one
@@ -190,6 +210,8 @@ class Simulation:
         self.exchange = SlabExchange(self.ctx, rank, world, self.boundary == "wrap", self.on_device, device) if world > 1 else None
         if self.exchange is not None and self.cfg.scheme == N.PPM and self.cfg.ppm_author != N.PPM_MC:
             self.ctx.set_flag_reducer(self.exchange.reduce_flags)
+        if self.exchange is not None and self.cfg.solver == N.LW:
+            self.ctx.set_key_reducer(self.exchange.reduce_keys)
         self.t, self.steps_done = 0.0, 0
         self._program = self.ctx.program()
         self._updates = self.ctx.updates()

@@ -171,6 +171,13 @@ int astrea_download_face_field(astrea_ctx* ctx, double* bxy_aos);
  * return 0.  Called twice per sweep of such an operator, from inside astrea_run_instr.  Not needed on a whole grid. */
 typedef int (*astrea_reduce_fn)(void* user, void* device_int32, int count);
 int astrea_set_flag_reducer(astrea_ctx* ctx, astrea_reduce_fn fn, void* user);
+/* Lax-Wendroff (solvers.py:79-88) takes column 1 of ``np.unique(characteristics, axis=-1)``: a lexicographic sort of the
+ * spectrum columns over the WHOLE padded array.  For states without v_z / B the pick is fixed by the first
+ * non-zero entry of each of three columns; a slab finds its own (uint64 keys: 2 x position in the whole array + sign
+ * bit, all ones = none) and then calls ``fn(user, device_ptr, 4)``, which must replace the ``count`` UNSIGNED 64-bit
+ * values, in place and ordered on the context's stream, by their minimum over all ranks — e.g. one
+ * ncclAllReduce(ncclUint64, ncclMin) — and return 0.  Called once per sweep of such an operator. */
+int astrea_set_key_reducer(astrea_ctx* ctx, astrea_reduce_fn fn, void* user);
 int astrea_program_length(const astrea_ctx* ctx);
 int astrea_instr_is_operator(const astrea_ctx* ctx, int instr);
 /* 1 if instruction `instr` reads ghost rows of a register (a spatial operator, or the inverse reconstruction of

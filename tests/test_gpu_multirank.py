@@ -45,7 +45,9 @@ SPECS = [("ll3", 256, "ppm", "hllc", "ssprk(3,3)", "wrap", 2), ("ll4", 256, "wen
          ("khi", 192, "plm", "hllc", "rk4", "wrap", 2), ("orszag-tang", 192, "plm", "hlld", "ssprk(3,3)", "wrap", 3),
          ("orszag-tang", 160, "ppm", "hlld", "ssprk(2,2)", "edge", 2),
          # PPM authors 'c' / 'ph': grid-wide any() switches OR-ed across the slabs with one NCCL all-reduce per flag pass
-         ("ll3", 256, "ppm", "hllc", "ssprk(2,2)", "wrap", 2, "c"), ("khi", 192, "ppm", "lf", "ssprk(3,3)", "wrap", 2, "ph")]
+         ("ll3", 256, "ppm", "hllc", "ssprk(2,2)", "wrap", 2, "c"), ("khi", 192, "ppm", "lf", "ssprk(3,3)", "wrap", 2, "ph"),
+         # Lax-Wendroff: minimum of the slabs' column-search keys (one NCCL all-reduce per sweep)
+         ("ll3", 256, "plm", "lw", "ssprk(2,2)", "wrap", 2), ("ll4", 192, "ppm", "lw", "ssprk(3,3)", "edge", 2)]
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs two GPUs")

@@ -242,6 +242,18 @@ def test_unsupported_selectors_fail_loudly(hostsim_lib):
         ctx.step()
     assert err.value.code == N.E_ARG and "Lax-Wendroff" in str(err.value)
     ctx.close()
+    # a slab needs the grid-wide hooks: Lax-Wendroff's column search (astrea_set_key_reducer) and the any() switches of
+    # the PPM authors 'c' / 'ph' (astrea_set_flag_reducer); without them the operator stops instead of using local values
+    from astrea_b200.selectors import make_cfg
+    for solver, author, hook in (("lw", "mc", "astrea_set_key_reducer"), ("hllc", "c", "astrea_set_flag_reducer")):
+        cfg = make_cfg(dimension=2, nx=12, ny=24, boundary="wrap", gamma=1.4, dx=1.0 / 24, cfl=.5, subgrid="ppm", solver=solver,
+                       timestep="ssprk(2,2)", nx_global=24, x_offset=0, ppm_author=author)
+        ctx = N.Context(cfg, lib=hostsim_lib)
+        ctx.upload(initial_state("ll6", 24, 2, 1.4, True)[:12])
+        with pytest.raises(N.AstreaError) as err:
+            ctx.run_instr(0, external_rows=True)
+        assert err.value.code == N.E_STATE and hook in str(err.value)
+        ctx.close()
     # unknown enums
     cfg = native_cfg(_meta("sod", 64, 1, "plm", "lf", "ssprk(2,2)", None))
     cfg.solver = 9

@@ -55,7 +55,11 @@ SPECS = [("ll3", 32, "ppm", "hllc", "ssprk(3,3)", "wrap", 2),
          ("orszag-tang", 32, "pcm", "hlld", "ssprk(10,4)", "wrap", 1),
          # PPM authors 'c' / 'ph': the grid-wide any() switches are OR-ed across the slabs (astrea_set_flag_reducer)
          ("ll3", 32, "ppm", "hllc", "ssprk(2,2)", "wrap", 2, "c"), ("khi", 36, "ppm", "lf", "ssprk(3,3)", "wrap", 2, "ph"),
-         ("ll4", 32, "ppm", "lf", "euler", "edge", 2, "ph"), ("sod", 32, "ppm", "hllc", "ssprk(2,2)", "edge", 2, "c")]
+         ("ll4", 32, "ppm", "lf", "euler", "edge", 2, "ph"), ("sod", 32, "ppm", "hllc", "ssprk(2,2)", "edge", 2, "c"),
+         # Lax-Wendroff: the column pick over the whole padded array is the minimum of the slabs' search keys
+         # (astrea_set_key_reducer)
+         ("ll3", 32, "plm", "lw", "ssprk(2,2)", "wrap", 2), ("ll4", 32, "ppm", "lw", "ssprk(3,3)", "edge", 2),
+         ("sod", 32, "pcm", "lw", "euler", "edge", 3), ("khi", 36, "weno3", "lw", "ssprk(2,2)", "wrap", 2)]
 
 
 @pytest.mark.parametrize("spec", SPECS, ids=["-".join(map(str, s[:6])) for s in SPECS])
