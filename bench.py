@@ -253,6 +253,9 @@ def run_ours(a):
     if world != a.gpus:
         if world == 1 and a.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU), see the module docstring")
+    # host threads and page-locked arrays of this rank on the socket its GPU hangs off (before anything is allocated)
+    from astrea_b200.hostbind import bind_host_to_gpu
+    host_binding = {"bound": False, "why": "--no-host-bind"} if a.no_host_bind else bind_host_to_gpu(local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -428,7 +431,8 @@ def run_ours(a):
                            "finite_horizon_steps": horizon, "dt": "computed on the device every step (cfl*min(dx/eigmax)), no host round trip",
                            "l2": "state per register (%.0f MB) exceeds the 126 MB L2" % (cells_per_rank * 64 / 1e6)
                                  if cells_per_rank * 64 > 126e6 else "working set fits L2 (small workload)",
-                           "restore": f"device-to-device return to the initial state every {batch} steps, inside the timed region"},
+                           "restore": f"device-to-device return to the initial state every {batch} steps, inside the timed region",
+                           "host_binding": host_binding},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "parity_check": check}
         if cpu:
             line["cpu_baseline"] = cpu
@@ -547,6 +551,7 @@ def main():
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-recon-bulk", action="store_true", help="A/B: reconstruction march with register prefetch instead of cp.async.bulk")
     ap.add_argument("--flux-block-tile", type=int, default=None, help="A/B: 0 = warp-wide, 1 = block-wide rows in the flux stage (default: by grid width)")
+    ap.add_argument("--no-host-bind", action="store_true", help="A/B: leave the rank's CPU affinity alone (default: the CPUs local to its GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the self-check before the timed region (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
