@@ -674,6 +674,7 @@ int run_operator(astrea_ctx* c, const Instr& ins, int external_rows, bool first)
                 flux_stage_geometry(kind, g.solver, (!lw && c->hydro) ? 1 : 0, fp.block_tile, nthreads, own, nwarp);
                 const int gx = (int)((nt + own - 1) / own), gy = (int)((ns + 1 + nwarp - 1) / nwarp);
                 fp.lw_pass = 0; fp.lw_keys = c->lw_keys;
+                fp.need_speed = (first || (g.flags & 64)) ? 1 : 0;      // flags bit 6: evaluate them in every operator (A/B runs)
                 if (lw) {      // search pass of the Lax-Wendroff column pick, per sweep
                     if (c->slab() && c->key_reduce_fn == nullptr)
                         return fail(c, ASTREA_E_STATE, "Lax-Wendroff picks its spectrum column over the whole grid (solvers.py:79-88): a decomposed "

@@ -659,7 +659,22 @@ struct FluxStageParams {
     int lw_pass;
     unsigned long long* lw_keys;
     int block_tile;            // 1: the hydro kernels of LLF / HLLC take the block-wide row of transverse points (FluxStage BT)
+    // 1: the interface speeds are wanted (first operator of a step: CFL reduction, astrea.py:70-71).  0: they only serve the
+    // reference's non-finite check (fv.py:158) — HLLC / HLLD then skip them for states that cannot give a non-finite speed
+    int need_speed;
 };
+
+// Entries of both states in [1e-25, 1e25] (density) / [-1e25, 1e25] (the rest): the Roe or mean state and the closed-form
+// spectral radius of it are finite whatever the values (square roots of positive numbers, denominators >= 1e-25,
+// magnitudes far from overflow: |B|^2 / rho <= 3e125, its square 1e251), so the evaluation can say nothing the
+// non-finite check would report.  NaN fails every comparison.
+template <bool H>
+HD bool speed_surely_finite(const double* a, const double* b) {
+    bool ok = a[0] >= 1e-25 && a[0] <= 1e25 && b[0] >= 1e-25 && b[0] <= 1e25;
+#pragma unroll
+    for (int k = 1; k < VarSet<H>::N; ++k) { const int v = VarSet<H>::at(k); ok = ok && fabs(a[v]) <= 1e25 && fabs(b[v]) <= 1e25; }
+    return ok;
+}
 
 // KIND: 0 = PCM (faces are the padded cell arrays), 1 = pointwise face conversion (PLM), 2 = 4th-order (PPM/WENO)
 // MEAN: arithmetic mean (PLM) instead of the Roe average for the wave-speed state.  AX = physical sweep axis,
@@ -883,13 +898,17 @@ struct FluxStage {
             if (SOLVER == SOL_HLLD) st.bn = *p.ws.at(smap(j), 5 + SAX, tc);
             // wave speeds: the per-interface estimate feeds the CFL reduction, LLF also uses it as its dissipation
             const int64_t jg = j + p.s_off;
-            double lam_here;
+            double lam_here = 0.0;
             bool counts;
+            // the later operators of a step use the speed for nothing but the non-finite check: skipped where it cannot fire
+            const bool speed = LLF || p.need_speed != 0 || !speed_surely_finite<HYDRO>(st.wp, st.wm);
             if (PCM) {
                 // pcm.py:30: Jacobian at the padded cells; interface j sees cells b(j-1) and b(j)
-                lam_here = spectral_radius_t<AX, HYDRO>(st.wp, gamma, g);
+                if (speed) lam_here = spectral_radius_t<AX, HYDRO>(st.wp, gamma, g);
                 counts = jg >= 0 && jg < p.ns_glob && j < p.ns;
                 if (LLF) st.lam = npmax(dissipation(st.wm), dissipation(st.wp));
+            } else if (!speed) {
+                counts = jg >= 1 && jg <= p.ns_glob && j >= 1;
             } else {
                 double a[NVAR];
                 if (KIND == 1) mean_state_t<HYDRO>(st.wp, st.wm, a); else roe_state_t<HYDRO>(st.wp, st.wm, a, g);

@@ -97,7 +97,7 @@ def stages_of(integrator):
 def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cfl, subgrid, solver, timestep,
              solver_category_name=None, magnetic_2d=False, limiter="minmod", low_mach=False, device=0,
              nx_global=None, x_offset=0, threads_2d=0, segment_2d=0, tile_1d=0, general_path=False, ppm_author="mc",
-             step_graph=True, recon_bulk=True, flux_block_tile=None):
+             step_graph=True, recon_bulk=True, flux_block_tile=None, stage_speeds=False):
     cfg = N.Cfg()
     cfg.dimension = int(dimension)
     cfg.boundary = boundary_enum(boundary)
@@ -118,8 +118,9 @@ def make_cfg(*, dimension, cells=None, nx=None, ny=None, boundary, gamma, dx, cf
     # bit 0: keep the 8-variable kernels for a grid without v_z / B (testing); bit 1: no CUDA-graph replay of small steps;
     # bit 2: reconstruction march with register prefetch instead of the TMA engine's bulk copies (A/B measurements)
     # bit 3 / 4: flux stage with warp-wide / block-wide rows of transverse points (None: by grid width)
+    # bit 6: interface wave speeds evaluated in every operator of a step, not only where they are used (A/B measurements)
     cfg.flags = ((1 if general_path else 0) | (0 if step_graph else 2) | (0 if recon_bulk else 4)
-                 | (0 if flux_block_tile is None else (16 if flux_block_tile else 8)))
+                 | (0 if flux_block_tile is None else (16 if flux_block_tile else 8)) | (64 if stage_speeds else 0))
     return cfg
 
 

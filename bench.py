@@ -281,6 +281,8 @@ def run_ours(a):
         geometry["recon_bulk"] = False
     if a.flux_block_tile is not None:
         geometry["flux_block_tile"] = bool(a.flux_block_tile)
+    if a.stage_speeds:
+        geometry["stage_speeds"] = True
     sim = Simulation(config, cells, dim, subgrid, solver, timestep, device=local, rank=rank, world=world,
                      cells_x=cells if dim == 2 else None, overlap=a.overlap, **geometry)
     ctx = sim.ctx
@@ -550,6 +552,7 @@ def main():
     ap.add_argument("--threads-2d", type=int, default=0)
     ap.add_argument("--segment-2d", type=int, default=0)
     ap.add_argument("--no-recon-bulk", action="store_true", help="A/B: reconstruction march with register prefetch instead of cp.async.bulk")
+    ap.add_argument("--stage-speeds", action="store_true", help="A/B: evaluate the interface wave speeds in every operator of a step")
     ap.add_argument("--flux-block-tile", type=int, default=None, help="A/B: 0 = warp-wide, 1 = block-wide rows in the flux stage (default: by grid width)")
     ap.add_argument("--no-host-bind", action="store_true", help="A/B: leave the rank's CPU affinity alone (default: the CPUs local to its GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

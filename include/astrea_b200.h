@@ -66,7 +66,10 @@ typedef struct astrea_cfg {
                               bit 1: never replay astrea_step_async as a CUDA graph (small grids do by default);
                               bit 2: reconstruction march with register prefetch instead of bulk asynchronous copies (A/B runs);
                               bit 3 / bit 4: flux stage with warp-wide / block-wide rows of transverse points whatever the
-                              grid width (default: block-wide from 4096 columns) */
+                              grid width (default: block-wide from 4096 columns);
+                              bit 6: evaluate the interface wave speeds in every operator of a step (A/B runs).  Default:
+                              the operators after the first, whose speeds the reference computes but uses only to raise on
+                              NaN / Inf (fv.py:158), evaluate them just for states that could give a non-finite one */
 } astrea_cfg;
 
 /* sim_variables -> device context.  Stands in for the namedtuple built at astrea.py:132-133. */

@@ -688,3 +688,39 @@ def test_run_steps_falls_back_in_2d(hostsim_lib):
     assert ctx.get_time()[1] == 3 and ctx.dt_history(3) == dts
     assert np.array_equal(ctx.download(), want, equal_nan=True)
     ctx.close()
+
+
+@pytest.mark.parametrize("case", [("ll3", 64, "ppm", "hllc", "ssprk(3,3)"), ("ll6", 32, "ppm", "hllc", "ssprk(3,3)"),
+                                  ("ll3", 32, "weno7", "hllc", "rk4"), ("ll3", 32, "weno5", "hllc", "ssprk(3,3)"),
+                                  ("orszag-tang", 32, "ppm", "hlld", "ssprk(3,3)"), ("ll12", 32, "ppm", "hllc", "ssprk(3,3)")],
+                         ids=lambda c: "-".join(map(str, c)))
+def test_later_operators_still_raise_where_the_reference_does(hostsim_lib, case):
+    """The operators after the first of a step evaluate the interface wave speeds only where they could be non-finite
+    (FluxStage, `need_speed`): the reference computes them in every evolve_space call but uses them only to raise on
+    NaN / Inf (fv.py:158).  The step and the half of the seam (evolve_space / evolve_time) that raises, and every grid
+    before it, must not depend on that: same as with the speeds evaluated everywhere (flags bit 6)."""
+    from astrea_b200 import _native as N
+    from astrea_b200.simulation import Simulation
+    config, cells, subgrid, solver, timestep = case
+    runs = []
+    for speeds in (False, True):
+        sim = Simulation(config, cells, 2, subgrid, solver, timestep, _lib=hostsim_lib, stage_speeds=speeds)
+        ctx, where, grids = sim.ctx, None, []
+        for n in range(16):
+            try:
+                eig = ctx.evolve_space(n & 1)
+            except N.NonFiniteError:
+                where = (n, "evolve_space")
+                break
+            try:
+                ctx.evolve_time(sim.cfl * min(sim.dx / e for e in eig))
+            except N.NonFiniteError:
+                where = (n, "evolve_time")
+                break
+            grids.append(ctx.download())
+        runs.append((where, grids))
+        sim.close()
+    assert runs[0][0] == runs[1][0] and runs[0][0] is not None
+    assert len(runs[0][1]) == len(runs[1][1])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert np.array_equal(a, b)
