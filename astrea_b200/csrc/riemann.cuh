@@ -17,54 +17,66 @@ HD void llf_flux_t(double lam, const double* qp, const double* qm, const double*
     for (int k = 0; k < VarSet<H>::N; ++k) { const int v = VarSet<H>::at(k); out[v] = 0.5 * (fm[v] + fp[v]) - 0.5 * ((qp[v] - qm[v]) * lam); }
 }
 
-template <int SAX, bool H = false, class G = Exact>
-HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* wm, const double* qp, const double* qm,
-                  const double* fp, const double* fm, double* out, G&& g = G()) {
-    constexpr int NV = VarSet<H>::N;
+// HLLC in two steps, so that a caller can decide from the waves which side's conservative state and physical flux it has
+// to produce at all (FluxStage, face-centred solve): the wave speeds and the branch of solvers.py:124-137 follow from the
+// primitive states alone; the flux then reads one side only.
+struct HllcWaves {
+    double sL, sR, sM;
+    int side;          // 0: the plus flux as it is; 1: star state on the plus side; 2: star state on the minus side
+};
+template <int SAX, class G = Exact>
+HD HllcWaves hllc_waves(double gamma, bool low_mach, const double* wp, const double* wm, G&& g = G()) {
     const double rL = wm[0], uL = wm[1 + SAX], pL = wm[4];
     const double rR = wp[0], uR = wp[1 + SAX], pR = wp[4];
     const double cL = dsqrt(gamma * sdiv(pL, rL, g), g), cR = dsqrt(gamma * sdiv(pR, rR, g), g);
     const double sqL = dsqrt(rL, g), sqR = dsqrt(rR, g);
     const double u_roe = sdiv(uL * sqL + uR * sqR, sqL + sqR, g);
     const double c2_roe = sdiv(sqL * (cL * cL) + sqR * (cR * cR), sqL + sqR, g) + 0.5 * sq(uR - uL) * sdiv(sqL * sqR, sq(sqL + sqR), g);
-    double sL = npmin(uL - cL, u_roe - dsqrt(c2_roe, g));
-    double sR = npmax(uR + cR, u_roe + dsqrt(c2_roe, g));
-    const double sM = sdiv(pR - pL + rL * uL * (sL - uL) - rR * uR * (sR - uR), rL * (sL - uL) - rR * (sR - uR), g);
+    HllcWaves wv;
+    wv.sL = npmin(uL - cL, u_roe - dsqrt(c2_roe, g));
+    wv.sR = npmax(uR + cR, u_roe + dsqrt(c2_roe, g));
+    wv.sM = sdiv(pR - pL + rL * uL * (wv.sL - uL) - rR * uR * (wv.sR - uR), rL * (wv.sL - uL) - rR * (wv.sR - uR), g);
     if (low_mach) {   // solvers.py:118-122
         const double mach = npmax(fabs(sdiv(uL, cL, g)), fabs(sdiv(uR, cR, g)));
         const double phi = sin(0.5 * 3.141592653589793 * npmin(1.0, ddiv(mach, 0.1, g)));
-        sL = phi * sL;
-        sR = phi * sR;
+        wv.sL = phi * wv.sL;
+        wv.sR = phi * wv.sR;
     }
-    const double kL = sdiv(sL - uL, sL - sM, g), kR = sdiv(sR - uR, sR - sM, g);
-    const bool useL = (sL <= 0.0) && (0.0 < sM);
-    const bool useR = (sM <= 0.0) && (0.0 <= sR);
-    const bool sup = sR < 0.0;
+    const bool useL = (wv.sL <= 0.0) && (0.0 < wv.sM);
+    const bool useR = (wv.sM <= 0.0) && (0.0 <= wv.sR);
+    const bool sup = wv.sR < 0.0;
     // later masks override earlier ones (solvers.py:135-137)
-    if (sup || !(useL || useR)) {
+    wv.side = (sup || !(useL || useR)) ? 0 : (useR ? 1 : 2);
+    return wv;
+}
+// w, q, f: primitive state, conservative state and physical flux of the side `wv.side` names (plus for 0 and 1, minus for 2);
+// side 0 reads f only
+template <int SAX, bool H = false, class G = Exact>
+HD void hllc_side(const HllcWaves& wv, const double* w, const double* q, const double* f, double* out, G&& g = G()) {
+    constexpr int NV = VarSet<H>::N;
+    if (wv.side == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) { const int v = VarSet<H>::at(k); out[v] = fp[v]; }
+        for (int k = 0; k < NV; ++k) { const int v = VarSet<H>::at(k); out[v] = f[v]; }
         return;
     }
-    if (useR) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int v = VarSet<H>::at(k);
-            double qs = qp[v] * kR;
-            if (v == 1) qs = rR * kR * sM;
-            if (v == 4) qs = qs + kR * (sM - uR) * (rR * sM + sdiv(pR, sR - uR, g));
-            out[v] = fp[v] + (qs - qp[v]) * sR;
-        }
-        return;
-    }
+    const double r = w[0], u = w[1 + SAX], p = w[4];
+    const double s = wv.side == 1 ? wv.sR : wv.sL, sM = wv.sM;
+    const double kk = sdiv(s - u, s - sM, g);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const int v = VarSet<H>::at(k);
-        double qs = qm[v] * kL;
-        if (v == 1) qs = rL * kL * sM;
-        if (v == 4) qs = qs + kL * (sM - uL) * (rL * sM + sdiv(pL, sL - uL, g));
-        out[v] = fm[v] + (qs - qm[v]) * sL;
+        double qs = q[v] * kk;
+        if (v == 1) qs = r * kk * sM;
+        if (v == 4) qs = qs + kk * (sM - u) * (r * sM + sdiv(p, s - u, g));
+        out[v] = f[v] + (qs - q[v]) * s;
     }
+}
+template <int SAX, bool H = false, class G = Exact>
+HD void hllc_flux(double gamma, bool low_mach, const double* wp, const double* wm, const double* qp, const double* qm,
+                  const double* fp, const double* fm, double* out, G&& g = G()) {
+    const HllcWaves wv = hllc_waves<SAX>(gamma, low_mach, wp, wm, g);
+    if (wv.side == 2) hllc_side<SAX, H>(wv, wm, qm, fm, out, g);
+    else hllc_side<SAX, H>(wv, wp, qp, fp, out, g);
 }
 
 template <class G = Exact>

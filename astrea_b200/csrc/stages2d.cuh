@@ -975,6 +975,31 @@ struct FluxStage {
         ex.template xphase<BT>([&](int tid) {
             Tls& st = tls[tid];
             if (!st.live) return;
+            if constexpr (SOLVER == SOL_HLLC && XS) {
+                // the waves follow from the primitive states; only the side they pick is converted (the neighbours' values
+                // come from shared-memory slots, which a lane may read on its own)
+                const HllcWaves wv = hllc_waves<SAX>(gamma, p.low_mach != 0, st.xp, st.xm, g);
+                double cq[NVAR], cf[NVAR];
+                if (wv.side == 2) {
+#pragma unroll
+                    for (int kv = 0; kv < VS::N; ++kv) {
+                        const int v = VS::at(kv);
+                        cq[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], S_AM * VS::N + kv, [&](int k) { return tls[k].am[v]; });
+                        cf[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], S_FM * VS::N + kv, [&](int k) { return tls[k].fm[v]; });
+                    }
+                    hllc_side<SAX, HYDRO>(wv, st.xm, cq, cf, st.fc, g);
+                } else {
+#pragma unroll
+                    for (int kv = 0; kv < VS::N; ++kv) {
+                        const int v = VS::at(kv);
+                        cq[v] = 0.0;
+                        if (wv.side == 1) cq[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], S_AP * VS::N + kv, [&](int k) { return tls[k].ap[v]; });
+                        cf[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], S_FP * VS::N + kv, [&](int k) { return tls[k].fp[v]; });
+                    }
+                    hllc_side<SAX, HYDRO>(wv, st.xp, cq, cf, st.fc, g);
+                }
+                return;
+            }
             double cqp[NVAR], cqm[NVAR], cfp[NVAR], cfm[NVAR];
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
