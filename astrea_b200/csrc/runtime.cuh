@@ -80,6 +80,9 @@ struct DeviceExec {
     }
     template <bool BLOCK>
     __device__ __forceinline__ bool group_any(bool b) const { if constexpr (BLOCK) return block_any(b); else return warp_any(b); }
+    // OR over the lanes of the group of ``get(thread)``, the same answer in every lane (called by all threads of the block)
+    template <bool BLOCK, class G>
+    __device__ __forceinline__ bool group_or(G&& get) const { return group_any<BLOCK>(get((int)threadIdx.x)); }
     __device__ __forceinline__ bool warp_any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
     __device__ __forceinline__ bool block_any(bool b) const { return __syncthreads_or(b) != 0; }
     // Max of a non-negative, finite per-thread value -> atomicMax on the bit pattern of *dst (for such values the
@@ -251,6 +254,12 @@ struct HostExec {
     }
     template <bool BLOCK>
     bool group_any(bool b) const { return b; }
+    template <bool BLOCK, class G>
+    bool group_or(G&& get) const {              // the whole block stands in for the group (a superset of a warp)
+        bool any = false;
+        for (int t = 0; t < nthr; ++t) any = any || get(t);
+        return any;
+    }
     bool warp_any(bool b) const { return b; }      // the host simulation runs a block thread by thread: one guard per block
     bool block_any(bool b) const { return b; }
     template <class G>

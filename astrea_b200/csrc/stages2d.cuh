@@ -687,6 +687,9 @@ struct FluxStage {
     using Params = FluxStageParams;
     using VS = VarSet<HYDRO>;
     static constexpr int MAX_THREADS = 128;
+#ifndef ASTREA_FLUX_SMEM_EXCHANGE
+#define ASTREA_FLUX_SMEM_EXCHANGE 1
+#endif
 #ifndef ASTREA_FLUX_MIN_BLOCKS
 #define ASTREA_FLUX_MIN_BLOCKS 3
 #endif
@@ -701,15 +704,18 @@ struct FluxStage {
     // shared-memory exchange): 5 / 4 / 3 blocks 1.85 / 1.78 / 1.94 ms at 2048^2 and 27.5 / 26.8 / 29.1 ms at 8192^2.
     // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
     // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
-    static constexpr int MIN_BLOCKS = HYDRO ? ASTREA_FLUX_MIN_BLOCKS_HYDRO : ASTREA_FLUX_MIN_BLOCKS;
+    // The LAZY instantiations (HLLC, four variables, 4th order; see below) hold one side's q / f instead of two: 5 blocks
+    // at 96 registers (80-104 B of spills) against 4 at 116: 8192^2 23.45 vs 23.88 ms of flux stages per step.
+#ifndef ASTREA_FLUX_MIN_BLOCKS_LAZY
+#define ASTREA_FLUX_MIN_BLOCKS_LAZY 5
+#endif
+    static constexpr int MIN_BLOCKS = !HYDRO ? ASTREA_FLUX_MIN_BLOCKS
+        : ((SOLVER == SOL_HLLC && KIND == 2 && ASTREA_FLUX_SMEM_EXCHANGE != 0) ? ASTREA_FLUX_MIN_BLOCKS_LAZY : ASTREA_FLUX_MIN_BLOCKS_HYDRO);
     static constexpr bool HO = KIND == 2, PCM = KIND == 0;
     static constexpr int H = HO ? 2 : 1;            // halo lanes on each side of a warp
     static constexpr int OWN = 32 - 2 * H;          // transverse points a warp owns
     static constexpr bool LW = SOLVER == SOL_LW;
     static constexpr bool LLF = SOLVER == SOL_LLF || LW;     // Lax-Wendroff has LLF's form with another coefficient
-#ifndef ASTREA_FLUX_SMEM_EXCHANGE
-#define ASTREA_FLUX_SMEM_EXCHANGE 1
-#endif
     // transverse exchange through shared memory instead of shuffles (runtime.cuh put / nbr): hydro kernels only, the
     // nine exchanged arrays of a four-variable state are 9 KB per warp (37 KB per block, 5 blocks per SM).  Measured at
     // 2048^2 PPM+HLLC: 2.01 -> 1.89 ms of flux stages per step (-250 of ~2150 static instructions per thread)
@@ -746,7 +752,14 @@ struct FluxStage {
         double lam, bn, lam_max;
         int64_t j, t;
         bool live, bad;
+        HllcWaves wva, wvc;            // LAZY: waves of the face-averaged (A) and of the face-centred states (B)
     };
+    // LAZY (HLLC on four-variable states, 4th order): the waves of both Riemann problems of an interface follow from the
+    // primitive states alone and name the one side (plus or minus) whose conservative state and physical flux the solver
+    // reads (riemann.cuh, hllc_waves / hllc_side).  The group of lanes that forms a row votes on the sides any of its
+    // lanes needs, and cons_of_prim / physical_flux / the face conversion of q are evaluated for those only: one side in
+    // smooth flow, both where the lanes of a row disagree.  Same values, fewer of them.
+    static constexpr bool LAZY = SOLVER == SOL_HLLC && XS && HO;
 
     // The warps of a block are independent (warp phases, warp-scope reduction).  On the device the work is done with
     // the branch-free Fast division / square root first; a warp in which any lane met an operand outside the range
@@ -890,11 +903,17 @@ struct FluxStage {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
-                cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma, g);
-                cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma, g);
+                if constexpr (!LAZY) {
+                    cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma, g);
+                    cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma, g);
+                }
             }
-            physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma, g);
-            physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma, g);
+            if constexpr (LAZY) {
+                st.wva = hllc_waves<SAX>(gamma, p.low_mach != 0, st.wp, st.wm, g);
+            } else {
+                physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma, g);
+                physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma, g);
+            }
             if (SOLVER == SOL_HLLD) st.bn = *p.ws.at(smap(j), 5 + SAX, tc);
             // wave speeds: the per-interface estimate feeds the CFL reduction, LLF also uses it as its dissipation
             const int64_t jg = j + p.s_off;
@@ -936,10 +955,13 @@ struct FluxStage {
             for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv);
                 ex.template put<XS, NS, BT>(S_WP * VS::N + kv, st.wp[v]); ex.template put<XS, NS, BT>(S_WM * VS::N + kv, st.wm[v]);
-                ex.template put<XS, NS, BT>(S_QP * VS::N + kv, st.qp[v]); ex.template put<XS, NS, BT>(S_QM * VS::N + kv, st.qm[v]);
-                ex.template put<XS, NS, BT>(S_FP * VS::N + kv, st.fp[v]); ex.template put<XS, NS, BT>(S_FM * VS::N + kv, st.fm[v]);
+                if constexpr (!LAZY) {
+                    ex.template put<XS, NS, BT>(S_QP * VS::N + kv, st.qp[v]); ex.template put<XS, NS, BT>(S_QM * VS::N + kv, st.qm[v]);
+                    ex.template put<XS, NS, BT>(S_FP * VS::N + kv, st.fp[v]); ex.template put<XS, NS, BT>(S_FM * VS::N + kv, st.fm[v]);
+                }
             }
         });
+        if constexpr (LAZY) { lazy_phases(p, ex, tls, g, d2t); return; }
         // B: w - d2_t(w)/24, face conversion of q (fv.py:105-122), Riemann flux of the face averages
         ex.template xphase<BT>([&](int tid) {
             Tls& st = tls[tid];
@@ -975,31 +997,6 @@ struct FluxStage {
         ex.template xphase<BT>([&](int tid) {
             Tls& st = tls[tid];
             if (!st.live) return;
-            if constexpr (SOLVER == SOL_HLLC && XS) {
-                // the waves follow from the primitive states; only the side they pick is converted (the neighbours' values
-                // come from shared-memory slots, which a lane may read on its own)
-                const HllcWaves wv = hllc_waves<SAX>(gamma, p.low_mach != 0, st.xp, st.xm, g);
-                double cq[NVAR], cf[NVAR];
-                if (wv.side == 2) {
-#pragma unroll
-                    for (int kv = 0; kv < VS::N; ++kv) {
-                        const int v = VS::at(kv);
-                        cq[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], S_AM * VS::N + kv, [&](int k) { return tls[k].am[v]; });
-                        cf[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], S_FM * VS::N + kv, [&](int k) { return tls[k].fm[v]; });
-                    }
-                    hllc_side<SAX, HYDRO>(wv, st.xm, cq, cf, st.fc, g);
-                } else {
-#pragma unroll
-                    for (int kv = 0; kv < VS::N; ++kv) {
-                        const int v = VS::at(kv);
-                        cq[v] = 0.0;
-                        if (wv.side == 1) cq[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], S_AP * VS::N + kv, [&](int k) { return tls[k].ap[v]; });
-                        cf[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], S_FP * VS::N + kv, [&](int k) { return tls[k].fp[v]; });
-                    }
-                    hllc_side<SAX, HYDRO>(wv, st.xp, cq, cf, st.fc, g);
-                }
-                return;
-            }
             double cqp[NVAR], cqm[NVAR], cfp[NVAR], cfm[NVAR];
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
@@ -1019,6 +1016,118 @@ struct FluxStage {
             if (!st.live) return;
             const int lane_id = BT ? tid : (tid & 31);
             const bool owned = st.live && lane_id >= H && lane_id < width - H && st.t >= 0 && st.t < p.nt;
+#pragma unroll
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
+                const double f = st.fc[v] - c24 * d2t(tid, st, st.fa[v], S_FA * VS::N + kv, [&](int k) { return tls[k].fa[v]; });
+                if (owned) *p.f.at(st.j, v, st.t) = f;
+            }
+        });
+    }
+
+    // Phases B .. D of the LAZY instantiations (see LAZY above); phase A has loaded and published wp / wm and holds the waves
+    // of the face-averaged problem.
+    template <class Ex, class L, class G, class D2>
+    static HD void lazy_phases(const Params& p, Ex& ex, L& tls, G& g, D2& d2t) {
+        const int NT = ex.nthreads();
+        const int width = BT ? NT : 32;
+        const double gamma = p.gamma, c24 = 1.0 / 24.0;
+        // B: face-centred primitives of both sides, their waves
+        ex.template xphase<BT>([&](int tid) {
+            Tls& st = tls[tid];
+            if (!st.live) return;
+#pragma unroll
+            for (int kv = 0; kv < VS::N; ++kv) {
+                const int v = VS::at(kv);
+                st.xp[v] = st.wp[v] - c24 * d2t(tid, st, st.wp[v], S_WP * VS::N + kv, [&](int k) { return tls[k].wp[v]; });
+                st.xm[v] = st.wm[v] - c24 * d2t(tid, st, st.wm[v], S_WM * VS::N + kv, [&](int k) { return tls[k].wm[v]; });
+            }
+            st.wvc = hllc_waves<SAX>(gamma, p.low_mach != 0, st.xp, st.xm, g);
+        });
+        // the sides any lane of the row reads: plus for sides 0 and 1, minus for side 2
+        const bool plus = ex.template group_or<BT>([&](int k) { return tls[k].live && (tls[k].wva.side != 2 || tls[k].wvc.side != 2); });
+        const bool minus = ex.template group_or<BT>([&](int k) { return tls[k].live && (tls[k].wva.side == 2 || tls[k].wvc.side == 2); });
+        // B': pointwise conversions of the sides in use
+        ex.template xphase<BT>([&](int tid) {
+            Tls& st = tls[tid];
+            if (!st.live) return;
+            if (plus) {
+                cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma, g);
+                physical_flux_t<AX, HYDRO>(st.wp, st.fp, gamma, g);
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    ex.template put<XS, NS, BT>(S_QP * VS::N + kv, st.qp[v]); ex.template put<XS, NS, BT>(S_FP * VS::N + kv, st.fp[v]);
+                }
+            }
+            if (minus) {
+                cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma, g);
+                physical_flux_t<AX, HYDRO>(st.wm, st.fm, gamma, g);
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    ex.template put<XS, NS, BT>(S_QM * VS::N + kv, st.qm[v]); ex.template put<XS, NS, BT>(S_FM * VS::N + kv, st.fm[v]);
+                }
+            }
+        });
+        // B'': face conversion of q (fv.py:105-122), Riemann flux of the face averages
+        ex.template xphase<BT>([&](int tid) {
+            Tls& st = tls[tid];
+            if (!st.live) return;
+            double qx[NVAR];
+            if (plus) {
+                cons_of_prim_t<HYDRO>(st.xp, qx, gamma, g);
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    st.ap[v] = qx[v] + c24 * d2t(tid, st, st.qp[v], S_QP * VS::N + kv, [&](int k) { return tls[k].qp[v]; });
+                    ex.template put<XS, NS, BT>(S_AP * VS::N + kv, st.ap[v]);
+                }
+            }
+            if (minus) {
+                cons_of_prim_t<HYDRO>(st.xm, qx, gamma, g);
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    st.am[v] = qx[v] + c24 * d2t(tid, st, st.qm[v], S_QM * VS::N + kv, [&](int k) { return tls[k].qm[v]; });
+                    ex.template put<XS, NS, BT>(S_AM * VS::N + kv, st.am[v]);
+                }
+            }
+            if (st.wva.side == 2) hllc_side<SAX, HYDRO>(st.wva, st.wm, st.am, st.fm, st.fa, g);
+            else hllc_side<SAX, HYDRO>(st.wva, st.wp, st.ap, st.fp, st.fa, g);
+#pragma unroll
+            for (int kv = 0; kv < VS::N; ++kv) ex.template put<XS, NS, BT>(S_FA * VS::N + kv, st.fa[VS::at(kv)]);
+        });
+        // C: face-centred q and physical flux of the side the centred waves pick (solvers.py:47-52), its Riemann flux
+        ex.template xphase<BT>([&](int tid) {
+            Tls& st = tls[tid];
+            if (!st.live) return;
+            double cq[NVAR], cf[NVAR];
+            if (st.wvc.side == 2) {
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    cq[v] = st.am[v] - c24 * d2t(tid, st, st.am[v], S_AM * VS::N + kv, [&](int k) { return tls[k].am[v]; });
+                    cf[v] = st.fm[v] - c24 * d2t(tid, st, st.fm[v], S_FM * VS::N + kv, [&](int k) { return tls[k].fm[v]; });
+                }
+                hllc_side<SAX, HYDRO>(st.wvc, st.xm, cq, cf, st.fc, g);
+            } else {
+#pragma unroll
+                for (int kv = 0; kv < VS::N; ++kv) {
+                    const int v = VS::at(kv);
+                    cq[v] = 0.0;
+                    if (st.wvc.side == 1) cq[v] = st.ap[v] - c24 * d2t(tid, st, st.ap[v], S_AP * VS::N + kv, [&](int k) { return tls[k].ap[v]; });
+                    cf[v] = st.fp[v] - c24 * d2t(tid, st, st.fp[v], S_FP * VS::N + kv, [&](int k) { return tls[k].fp[v]; });
+                }
+                hllc_side<SAX, HYDRO>(st.wvc, st.xp, cq, cf, st.fc, g);
+            }
+        });
+        // D: F = F_c - d2_t(F_avg)/24 (fv.py:147-153)
+        ex.template xphase<BT>([&](int tid) {
+            Tls& st = tls[tid];
+            if (!st.live) return;
+            const int lane_id = BT ? tid : (tid & 31);
+            const bool owned = lane_id >= H && lane_id < width - H && st.t >= 0 && st.t < p.nt;
 #pragma unroll
             for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv);
