@@ -705,7 +705,8 @@ struct FluxStage {
     // Walking several interface rows per warp with the next row's loads issued early was tried and lost: the
     // per-thread state then lives across a loop and ptxas spills it (flux stage 2.6 -> 3.5 ms per step).
     // The LAZY instantiations (HLLC, four variables, 4th order; see below) hold one side's q / f instead of two: 5 blocks
-    // at 96 registers (80-104 B of spills) against 4 at 116: 8192^2 23.45 vs 23.88 ms of flux stages per step.
+    // at 96 registers (80-104 B of spills) against 4 at 116: 8192^2 23.45 vs 23.88 ms of flux stages per step (6 blocks at 80
+    // registers, 160 B of spills: 24.0).
 #ifndef ASTREA_FLUX_MIN_BLOCKS_LAZY
 #define ASTREA_FLUX_MIN_BLOCKS_LAZY 5
 #endif
