@@ -19,7 +19,9 @@
 //                              One warp per 32 transverse points of one interface row — or, on wide grids, one block
 //                              per row of NT points (BTILE); transverse neighbours are exchanged through shared-memory
 //                              slots (four-variable hydro states) or by warp shuffle (eight-variable states),
-//                              everything else lives in registers.
+//                              everything else lives in registers.  Work whose result nobody reads is left out: the
+//                              wave speed in the operators after the first of a step (need_speed), and for HLLC on
+//                              four-variable states the conversions of the side the waves of a row do not pick (LAZY).
 //
 // Every division and square root goes through a guard (common.cuh): the kernels run a branch-free pass first and a
 // warp (block, for the tiled primitive stages) repeats its work with the compiler's IEEE routines if an operand was
