@@ -174,6 +174,12 @@ __host__ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* s
     (void)dst_smem; (void)src_global; (void)bytes; (void)bar;
 }
 
+// hint: bring the line of `p` into L2 (no register, no dependency; an address outside any allocation must not be passed)
+__host__ __device__ __forceinline__ void prefetch_l2(const void* p) {
+    ASTREA_DEVICE_ONLY(asm volatile("prefetch.global.L2 [%0];" ::"l"(p));)
+    (void)p;
+}
+
 // resident blocks per SM the register allocation should allow: K::MIN_BLOCKS when the kernel declares it, else 1
 template <class K, class = void>
 struct min_blocks_of { static constexpr int value = 0; };   // 0 = let ptxas choose (same as omitting the argument)

@@ -692,6 +692,9 @@ struct FluxStage {
 #ifndef ASTREA_FLUX_SMEM_EXCHANGE
 #define ASTREA_FLUX_SMEM_EXCHANGE 1
 #endif
+#ifndef ASTREA_FLUX_PREFETCH_ROWS
+#define ASTREA_FLUX_PREFETCH_ROWS 16
+#endif
 #ifndef ASTREA_FLUX_MIN_BLOCKS
 #define ASTREA_FLUX_MIN_BLOCKS 3
 #endif
@@ -906,6 +909,17 @@ struct FluxStage {
 #pragma unroll
                 for (int kv = 0; kv < VS::N; ++kv) {
                 const int v = VS::at(kv); st.wp[v] = *p.wp.at(j, v, tc); st.wm[v] = *p.wm.at(j, v, tc); }
+#if defined(ASTREA_DEVICE_BUILD) && ASTREA_FLUX_PREFETCH_ROWS > 0
+                // a block starts with these loads and has nothing to overlap them with (long scoreboard is the largest stall
+                // of the stage): the blocks that run a few waves later find their interface states in L2
+                if (LAZY && j + ASTREA_FLUX_PREFETCH_ROWS <= p.ns) {
+#pragma unroll
+                    for (int kv = 0; kv < VS::N; ++kv) {
+                        const int v = VS::at(kv);
+                        prefetch_l2(p.wp.at(j + ASTREA_FLUX_PREFETCH_ROWS, v, tc)); prefetch_l2(p.wm.at(j + ASTREA_FLUX_PREFETCH_ROWS, v, tc));
+                    }
+                }
+#endif
                 if constexpr (!LAZY) {
                     cons_of_prim_t<HYDRO>(st.wp, st.qp, gamma, g);
                     cons_of_prim_t<HYDRO>(st.wm, st.qm, gamma, g);
